@@ -1,0 +1,123 @@
+"""Loading of the committed golden fixtures (tests/golden/, made by make_golden.py from the
+reference's regression suite) and the small amount of DRIVER-SIDE logic needed to replay a
+case without Fortran: netstat <-> serialised parameter vector (network.F90:397-459), feature
+assembly order (features.F90:200-265), elastic-net term (nestedtypes.F90:336-370), the
+normalisation + steepest-descent step of TBpnn_update (bpnn.F90:751-776, steepdesc.F90:186-202).
+Test infrastructure only.
+"""
+import json
+import os
+
+import numpy as np
+
+from fortnet_b200.dataset import Dataset
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ATOL, RTOL = 1e-10, 1e-9   # test/prog/fortnet/bin/testwithworkdir.py:24-25
+
+
+def index():
+    with open(os.path.join(GOLD, "index.json")) as fh:
+        return json.load(fh)
+
+
+def load_dataset(name):
+    return Dataset.from_golden(np.load(os.path.join(GOLD, "datasets", name + ".npz")))
+
+
+class Case:
+    def __init__(self, entry):
+        self.entry = entry
+        self.name = entry["case"]
+        z = np.load(os.path.join(GOLD, "cases", entry["file"]))
+        self.arr = {k: z[k] for k in z.files}
+        self.meta = json.loads(bytes(self.arr.pop("meta")).decode())
+        ns = self.meta["netstat"]
+        self.mode = self.meta["mode"]
+        self.dims = self.arr["in_dims"].astype(np.int32)
+        self.activation = ns["activation"]
+        self.nG, self.nA = ns["nglobaltargets"], ns["natomictargets"]
+        self.funcs = ns.get("functions", [])
+        self.atomic_numbers = self.arr["in_atomicnumbers"]
+        self.zmeans = self.arr.get("in_zmeans")
+        self.zsigmas = self.arr.get("in_zsigmas")
+        self.ext_indices = self.arr.get("in_extindices")  # 1-based rows of extfeatures
+        self.dataset = load_dataset(self.meta["dataset"])
+        self.training = self.meta.get("training") or {}
+        self.forces = (self.meta.get("forces") or {}).get("_type")
+
+    # --- netstat <-> serialised parameters (network.F90:397-459) -----------------------
+    def wb(self, prefix="in_"):
+        L = len(self.dims)
+        out = []
+        for sp in range(len(self.atomic_numbers)):
+            ws, bs = [], [np.zeros(self.dims[0])]
+            for l in range(1, L):
+                ws.append(self.arr["%sw_%d_%d" % (prefix, sp, l)].reshape(-1))  # ww(d_l,d_{l+1}) col-major
+                bs.append(self.arr["%sb_%d_%d" % (prefix, sp, l)].reshape(-1))
+            ws.append(np.zeros(self.dims[-1]))                                    # dummy ww(d_L,1)
+            out.append(np.concatenate(ws + bs))
+        return np.asarray(out)
+
+    def n_weights(self):
+        d = self.dims
+        return int(sum(d[i] * d[i + 1] for i in range(len(d) - 1)) + d[-1])
+
+    def loss_name(self):
+        return str(self.training.get("loss", "mse")).strip("'\"").lower()
+
+    # --- TBpnn_update restated for SD (bpnn.F90:708-778) -----------------------------
+    def sd_update(self, wb, dd):
+        tr = self.training
+        nW = self.n_weights()
+        dd = dd.copy()
+        regu = tr.get("regularization")
+        if regu:
+            kind = regu.get("_type")
+            lam = float(regu.get("strength", 0.0))
+            alpha = {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
+            w = wb[:, :nW]
+            dd[:, :nW] += lam / nW * ((1.0 - alpha) * w + alpha * np.sign(w))
+        dd /= float(np.sum(self.dataset.weights))
+        lr = float(tr["learningrate"])
+        maxd = float(tr["maxdisplacement"])
+        thr = float(tr.get("threshold", 0.0))
+        new = wb.copy()
+        for sp in range(wb.shape[0]):
+            if np.max(np.abs(dd[sp])) < thr:
+                continue
+            step = -lr * dd[sp]
+            mx = np.max(np.abs(step))
+            new[sp] = wb[sp] + (step if mx <= maxd else (maxd / mx) * step)
+        return new, float(np.sqrt(np.sum(dd ** 2)))
+
+    def assemble_features(self, acsf_vals):
+        """features.F90:200-265: [ACSF ; ext(indices)]"""
+        parts = []
+        if acsf_vals is not None and acsf_vals.shape[1]:
+            parts.append(acsf_vals)
+        if self.ext_indices is not None and len(self.ext_indices):
+            parts.append(self.dataset.ext[:, self.ext_indices.astype(int) - 1])
+        return np.ascontiguousarray(np.concatenate(parts, axis=1))
+
+
+def cases(mode=None, training=None, forces=None, limit=None):
+    out = []
+    for e in index():
+        if mode is not None and e["mode"] not in mode:
+            continue
+        if training is not None and e["training"] not in training:
+            continue
+        if forces is not None and e["forces"] not in forces:
+            continue
+        out.append(e)
+    return out[:limit] if limit else out
+
+
+def allclose(a, b):
+    return np.allclose(a, b, rtol=RTOL, atol=ATOL)
+
+
+def maxdiff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
