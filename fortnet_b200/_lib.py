@@ -1,0 +1,41 @@
+"""ctypes loader of libfnetgpu.so (C ABI: include/fnetgpu.h).  Fails loudly when the CUDA
+library is missing -- there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfnetgpu.so")
+_lib = None
+
+SYMBOLS = [
+    "fnetgpu_init", "fnetgpu_finalize", "fnetgpu_last_error", "fnetgpu_synchronize",
+    "fnetgpu_dataset_upload", "fnetgpu_coords_update", "fnetgpu_acsf_set", "fnetgpu_features_config",
+    "fnetgpu_acsf_calculate", "fnetgpu_features_get", "fnetgpu_features_set", "fnetgpu_net_set",
+    "fnetgpu_ntot", "fnetgpu_params_set", "fnetgpu_grad", "fnetgpu_predict", "fnetgpu_loss",
+    "fnetgpu_forces", "fnetgpu_comm_unique_id", "fnetgpu_comm_init", "fnetgpu_set_stream",
+    "fnetgpu_launch_count", "fnetgpu_profile", "fnetgpu_profile_get", "fnetgpu_kernel_name",
+    "fnetgpu_max_neighbors",
+]
+
+
+class FnetGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FnetGpuError(
+                "libfnetgpu.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C fortnet_b200/csrc`).  There is no CPU fallback." % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib.fnetgpu_last_error.restype = C.c_char_p
+        _lib.fnetgpu_last_error.argtypes = [C.c_void_p]
+        _lib.fnetgpu_kernel_name.restype = C.c_char_p
+        _lib.fnetgpu_launch_count.restype = C.c_longlong
+        _lib.fnetgpu_launch_count.argtypes = [C.c_void_p]
+        _lib.fnetgpu_ntot.argtypes = [C.c_void_p]
+    return _lib

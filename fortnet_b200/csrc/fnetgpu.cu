@@ -1,0 +1,971 @@
+// fnetgpu.cu -- the C ABI of libfnetgpu.so (include/fnetgpu.h): host-side orchestration of the
+// sm_100a kernels in cells.cuh / acsf.cuh / acsf_force.cuh / mlp.cuh.  No torch types, no CPU
+// fallback: every entry point either runs the CUDA path or returns an error.
+#include "internal.h"
+#include "cells.cuh"
+#include "acsf.cuh"
+#include "acsf_force.cuh"
+#include "mlp.cuh"
+
+#include <dlfcn.h>
+#include <map>
+#include <tuple>
+
+static const char *kKernelNames[K_NUM_KERNELS] = {
+    "bin_count", "bin_scan", "bin_fill", "bin_sort", "neigh_count", "acsf", "zstat", "zstat_final",
+    "zapply", "ext_concat", "mlp_fwd", "struct_loss", "loss_final", "mlp_grad", "grad_reduce",
+    "mlp_ingrad", "acsf_force", "misc"};
+
+extern "C" const char *fnetgpu_kernel_name(int kernelId) {
+  return (kernelId >= 0 && kernelId < K_NUM_KERNELS) ? kKernelNames[kernelId] : nullptr;
+}
+
+static thread_local std::string g_err;  // errors before a context exists
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) { g_err = "null context"; return 1; } (ctx)->err.clear(); } while (0)
+#define CHECK_SLOT(ctx, slot)                                                        \
+  do { if ((slot) < 0 || (slot) >= FNETGPU_MAX_SLOTS) FNET_FAIL(ctx, "slot out of range"); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int deterministic) {
+  if (!out) { g_err = "null out pointer"; return 1; }
+  *out = nullptr;
+  if (precision != 64 && precision != 32) { g_err = "precision must be 64 or 32"; return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_err = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return 1;
+  }
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % ndev : 0;
+  }
+  if (device >= ndev) { g_err = "device index out of range"; return 1; }
+  fnetgpu_ctx *ctx = new fnetgpu_ctx();
+  ctx->device = device; ctx->precision = precision; ctx->deterministic = deterministic;
+  memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->klaunch, 0, sizeof(ctx->klaunch));
+  memset(&ctx->acsf, 0, sizeof(ctx->acsf)); memset(&ctx->net, 0, sizeof(ctx->net));
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; delete ctx; return 1; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->nSM = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "stream creation failed"; delete ctx; return 1; }
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  cudaMalloc((void **)&ctx->d_flags, 8 * sizeof(int));
+  cudaMemset(ctx->d_flags, 0, 8 * sizeof(int));
+  *out = ctx;
+  return 0;
+}
+
+static void free_slot(Slot &s) {
+  cudaFree(s.d_offsets); cudaFree(s.d_structOf); cudaFree(s.d_atnum); cudaFree(s.d_sp); cudaFree(s.d_periodic);
+  cudaFree(s.d_coords); cudaFree(s.d_fpos); cudaFree(s.d_cpos); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
+  cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
+  cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat); cudaFree(s.d_neighCount);
+  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
+  cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
+  s = Slot();
+}
+
+extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) free_slot(ctx->slots[i]);
+  cudaFree(ctx->d_rgroups); cudaFree(ctx->d_rfeat); cudaFree(ctx->d_rp1); cudaFree(ctx->d_rp2);
+  cudaFree(ctx->d_apasses); cudaFree(ctx->d_extIdx); cudaFree(ctx->d_zprec); cudaFree(ctx->d_wb);
+  cudaFree(ctx->d_wb64); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->comm && ctx->nccl) {
+    typedef int (*destroy_t)(void *);
+    destroy_t d = (destroy_t)dlsym(ctx->nccl, "ncclCommDestroy");
+    if (d) d(ctx->comm);
+  }
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" const char *fnetgpu_last_error(const fnetgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int fnetgpu_synchronize(fnetgpu_ctx *ctx) {
+  CHECK_CTX(ctx);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fnetgpu_set_stream(fnetgpu_ctx *ctx, void *stream) {
+  CHECK_CTX(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)stream;
+  ctx->ownStream = false;
+  return 0;
+}
+
+extern "C" long long fnetgpu_launch_count(const fnetgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fnetgpu_profile(fnetgpu_ctx *ctx, int enable) {
+  CHECK_CTX(ctx);
+  ctx->profiling = enable != 0;
+  if (enable) { memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->klaunch, 0, sizeof(ctx->klaunch)); }
+  return 0;
+}
+extern "C" int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kid, double *ms, long long *launches) {
+  CHECK_CTX(ctx);
+  if (kid < 0 || kid >= K_NUM_KERNELS) FNET_FAIL(ctx, "kernel id out of range");
+  if (ms) *ms = ctx->kms[kid];
+  if (launches) *launches = ctx->klaunch[kid];
+  return 0;
+}
+
+static int ensure_pinned(fnetgpu_ctx *ctx, size_t n) {
+  if (ctx->pinnedN >= n) return 0;
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  ctx->h_pinned = nullptr; ctx->pinnedN = 0;
+  CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinned, n * sizeof(double)));
+  ctx->pinnedN = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dataset upload
+// ------------------------------------------------------------------------------------------
+extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, const int *offsets,
+                                      const double *coords, const int *periodic, const double *latvecs,
+                                      const int *atnum, const int *globalsp, const int *dsWeights,
+                                      const double *atomicWeights, int nG, const double *gTargets, int nA,
+                                      const double *aTargets, int nExt, const double *ext) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  if (nStruct <= 0 || !offsets || !atnum || !globalsp) FNET_FAIL(ctx, "dataset_upload: missing arrays");
+  cudaSetDevice(ctx->device);
+  Slot &s = ctx->slots[slot];
+  free_slot(s);
+  const int N = offsets[nStruct];
+  if (N <= 0 || offsets[0] != 0) FNET_FAIL(ctx, "dataset_upload: offsets must start at 0 and end at N > 0");
+  s.used = true; s.nStruct = nStruct; s.N = N; s.nG = nG; s.nA = nA; s.nExt = nExt;
+  s.h_offsets.assign(offsets, offsets + nStruct + 1);
+  s.h_periodic.assign(nStruct, 0);
+  if (periodic) s.h_periodic.assign(periodic, periodic + nStruct);
+  s.h_lat.assign((size_t)9 * nStruct, 0.0);
+  if (latvecs) s.h_lat.assign(latvecs, latvecs + (size_t)9 * nStruct);
+  std::vector<int> structOf(N);
+  for (int st = 0; st < nStruct; st++) {
+    if (offsets[st + 1] <= offsets[st]) FNET_FAIL(ctx, "dataset_upload: empty structure");
+    for (int i = offsets[st]; i < offsets[st + 1]; i++) structOf[i] = st;
+  }
+  int maxSp = 0;
+  s.h_globalsp.resize(N);
+  for (int i = 0; i < N; i++) {
+    if (globalsp[i] < 1) FNET_FAIL(ctx, "dataset_upload: globalsp must be 1-based");
+    s.h_globalsp[i] = globalsp[i] - 1;
+    maxSp = std::max(maxSp, globalsp[i]);
+  }
+  // species-sorted processing order (stable)
+  std::vector<int> perm(N);
+  s.spBeg.assign(maxSp + 1, 0);
+  for (int i = 0; i < N; i++) s.spBeg[s.h_globalsp[i] + 1]++;
+  for (int k = 0; k < maxSp; k++) s.spBeg[k + 1] += s.spBeg[k];
+  {
+    std::vector<int> cur(s.spBeg.begin(), s.spBeg.end() - 1);
+    for (int i = 0; i < N; i++) perm[cur[s.h_globalsp[i]]++] = i;
+  }
+  std::vector<double> dsw(nStruct, 1.0), aw(N, 1.0);
+  if (dsWeights) for (int st = 0; st < nStruct; st++) dsw[st] = (double)dsWeights[st];
+  if (atomicWeights) aw.assign(atomicWeights, atomicWeights + N);
+  if (dev_upload(ctx, &s.d_offsets, offsets, (size_t)nStruct + 1)) return 1;
+  if (dev_upload(ctx, &s.d_structOf, structOf.data(), (size_t)N)) return 1;
+  if (dev_upload(ctx, &s.d_atnum, atnum, (size_t)N)) return 1;
+  if (dev_upload(ctx, &s.d_sp, s.h_globalsp.data(), (size_t)N)) return 1;
+  if (dev_upload(ctx, &s.d_perm, perm.data(), (size_t)N)) return 1;
+  if (dev_upload(ctx, &s.d_dsw, dsw.data(), (size_t)nStruct)) return 1;
+  if (dev_upload(ctx, &s.d_aw, aw.data(), (size_t)N)) return 1;
+  if (coords) { if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * N)) return 1; }
+  if (nG > 0) { if (!gTargets) FNET_FAIL(ctx, "gTargets missing"); if (dev_upload(ctx, &s.d_gt, gTargets, (size_t)nG * nStruct)) return 1; }
+  if (nA > 0) { if (!aTargets) FNET_FAIL(ctx, "aTargets missing"); if (dev_upload(ctx, &s.d_at, aTargets, (size_t)nA * N)) return 1; }
+  if (nExt > 0) { if (!ext) FNET_FAIL(ctx, "ext missing"); if (dev_upload(ctx, &s.d_ext, ext, (size_t)nExt * N)) return 1; }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used) FNET_FAIL(ctx, "coords_update: empty slot");
+  cudaSetDevice(ctx->device);
+  if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * s.N)) return 1;
+  if (latvecs) s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
+  s.cellRc = -1.0; s.maxNeigh = -1; s.featValid = false;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// ACSF configuration: grouping of the function list into radial groups and angular passes
+// ------------------------------------------------------------------------------------------
+extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const double *rcut,
+                                const double *kappa, const double *rs, const double *eta,
+                                const double *lambda, const double *xi, const int *atomid,
+                                const int *atomicnumbers) {
+  CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  if (F < 0) FNET_FAIL(ctx, "acsf_set: negative function count");
+  AcsfTables &T = ctx->acsf;
+  memset(&T, 0, sizeof(T));
+  T.F = F;
+  ctx->h_rgroups.clear(); ctx->h_apasses.clear();
+  std::vector<int> rfeat; std::vector<double> rp1, rp2;
+  // species codes
+  std::vector<int> codes;
+  auto code_of = [&](int z) -> int {
+    for (size_t c = 0; c < codes.size(); c++) if (codes[c] == z) return (int)c;
+    codes.push_back(z);
+    return (int)codes.size() - 1;
+  };
+  double rcMax = 0.0;
+  int anyAtomId = 0;
+  typedef std::tuple<int, double, int, int> RKey;                       // type, rc, atomId, code
+  typedef std::tuple<int, double, double, int, int, int> AKey;          // type, rc, eta, atomId, code1, code2
+  std::vector<RKey> rkeys; std::vector<std::vector<int>> rmembers;
+  std::vector<AKey> akeys; std::vector<std::vector<int>> amembers;
+  for (int a = 0; a < F; a++) {
+    if (type[a] < 1 || type[a] > 5) FNET_FAIL(ctx, "acsf_set: invalid function type (expected 1..5 for G1..G5)");
+    if (!(rcut[a] > 0.0)) FNET_FAIL(ctx, "acsf_set: invalid cutoff");
+    if (atomid[a] < 0) FNET_FAIL(ctx, "acsf_set: negative atomId");
+    rcMax = std::max(rcMax, rcut[a]);
+    if (atomid[a] > 0) anyAtomId = 1;
+    const int z1 = atomicnumbers[2 * a], z2 = atomicnumbers[2 * a + 1];
+    const bool resolved = !(z1 == 0 && z2 == 0);                        // acsf.F90:992-996
+    if (type[a] <= 3) {
+      RKey k(type[a], rcut[a], atomid[a], resolved ? code_of(z1) : -1);
+      size_t g = 0;
+      for (; g < rkeys.size(); g++) if (rkeys[g] == k) break;
+      if (g == rkeys.size()) { rkeys.push_back(k); rmembers.emplace_back(); }
+      rmembers[g].push_back(a);
+    } else {
+      int c1 = -1, c2 = -1;
+      if (resolved) { c1 = code_of(z1); c2 = code_of(z2); }
+      AKey k(type[a], rcut[a], eta[a], atomid[a], c1, c2);
+      size_t g = 0;
+      for (; g < akeys.size(); g++) if (akeys[g] == k) break;
+      if (g == akeys.size()) { akeys.push_back(k); amembers.emplace_back(); }
+      amembers[g].push_back(a);
+    }
+  }
+  if ((int)codes.size() > FNET_MAX_CODES) FNET_FAIL(ctx, "acsf_set: too many distinct atomic numbers in species-resolved functions");
+  T.nCodes = (int)codes.size();
+  for (size_t c = 0; c < codes.size(); c++) T.zcodes[c] = codes[c];
+  T.rcMax = rcMax; T.anyAtomId = anyAtomId;
+  // radial groups (<= 32 chunks of FNET_RCHUNK functions each)
+  for (size_t g = 0; g < rkeys.size(); g++) {
+    const std::vector<int> &m = rmembers[g];
+    for (size_t beg = 0; beg < m.size(); beg += 32 * FNET_RCHUNK) {
+      size_t cnt = std::min(m.size() - beg, (size_t)32 * FNET_RCHUNK);
+      RadialGroup G;
+      G.type = std::get<0>(rkeys[g]); G.rc = std::get<1>(rkeys[g]); G.atomId = std::get<2>(rkeys[g]);
+      G.code = std::get<3>(rkeys[g]);
+      G.fBeg = (int)rfeat.size(); G.fCnt = (int)cnt;
+      int nch = ((int)cnt + FNET_RCHUNK - 1) / FNET_RCHUNK, p2 = 1;
+      while (p2 < nch) p2 <<= 1;
+      G.nChunksP2 = p2;
+      for (size_t q = 0; q < cnt; q++) {
+        int a = m[beg + q];
+        rfeat.push_back(a);
+        if (G.type == FNETGPU_G2) { rp1.push_back(eta[a]); rp2.push_back(rs[a]); }
+        else if (G.type == FNETGPU_G3) { rp1.push_back(kappa[a]); rp2.push_back(0.0); }
+        else { rp1.push_back(0.0); rp2.push_back(0.0); }
+      }
+      ctx->h_rgroups.push_back(G);
+    }
+  }
+  // angular passes: per key, split by lambda, sort by xi, cut into arithmetic ladders
+  for (size_t g = 0; g < akeys.size(); g++) {
+    std::vector<LadderSlot> slots;
+    std::vector<int> m = amembers[g];
+    std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
+      if (lambda[a] != lambda[b]) return lambda[a] > lambda[b];
+      return xi[a] < xi[b];
+    });
+    size_t p = 0;
+    while (p < m.size()) {
+      LadderSlot sl; memset(&sl, 0, sizeof(sl));
+      sl.lam = lambda[m[p]]; sl.xi0 = xi[m[p]]; sl.dxi = 0.0; sl.count = 1;
+      size_t q = p + 1;
+      if (q < m.size() && lambda[m[q]] == sl.lam) {
+        sl.dxi = xi[m[q]] - xi[m[p]];
+        while (q < m.size() && sl.count < FNET_LADDER && lambda[m[q]] == sl.lam) {
+          double expect = sl.xi0 + sl.count * sl.dxi;
+          if (fabs(xi[m[q]] - expect) > 1e-12 * std::max(1.0, fabs(expect))) break;
+          sl.count++; q++;
+        }
+      }
+      if (sl.count == 1) sl.dxi = 0.0;
+      for (int f = 0; f < sl.count; f++) {
+        int a = m[p + f];
+        sl.feat[f] = a; sl.xi[f] = xi[a]; sl.pref[f] = pow(2.0, 1.0 - xi[a]);   // acsf.F90:1434,1490
+      }
+      slots.push_back(sl);
+      p += sl.count;
+    }
+    for (size_t b = 0; b < slots.size(); b += FNET_SLOTS) {
+      AngularPass P; memset(&P, 0, sizeof(P));
+      P.type = std::get<0>(akeys[g]); P.rc = std::get<1>(akeys[g]); P.eta = std::get<2>(akeys[g]);
+      P.atomId = std::get<3>(akeys[g]); P.code1 = std::get<4>(akeys[g]); P.code2 = std::get<5>(akeys[g]);
+      P.same = (P.code1 == P.code2) ? 1 : 0;   // unresolved (-1,-1) or Z1 == Z2 (acsf.F90:1573)
+      P.nSlots = (int)std::min(slots.size() - b, (size_t)FNET_SLOTS);
+      for (int q = 0; q < P.nSlots; q++) P.slot[q] = slots[b + q];
+      ctx->h_apasses.push_back(P);
+    }
+  }
+  T.nRadialGroups = (int)ctx->h_rgroups.size();
+  T.nAngularPasses = (int)ctx->h_apasses.size();
+  if (dev_upload(ctx, &ctx->d_rgroups, ctx->h_rgroups.data(), ctx->h_rgroups.size())) return 1;
+  if (dev_upload(ctx, &ctx->d_rfeat, rfeat.data(), rfeat.size())) return 1;
+  if (dev_upload(ctx, &ctx->d_rp1, rp1.data(), rp1.size())) return 1;
+  if (dev_upload(ctx, &ctx->d_rp2, rp2.data(), rp2.size())) return 1;
+  if (dev_upload(ctx, &ctx->d_apasses, ctx->h_apasses.data(), ctx->h_apasses.size())) return 1;
+  T.rgroups = ctx->d_rgroups; T.rfeat = ctx->d_rfeat; T.rp1 = ctx->d_rp1; T.rp2 = ctx->d_rp2;
+  T.apasses = ctx->d_apasses;
+  if (dev_alloc(ctx, &ctx->d_zprec, (size_t)2 * std::max(F, 1))) return 1;
+  ctx->haveZ = false;
+  ctx->acsfSet = true;
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fnetgpu_features_config(fnetgpu_ctx *ctx, int nExtSel, const int *extIndices) {
+  CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  ctx->extIdx.clear();
+  for (int e = 0; e < nExtSel; e++) {
+    if (extIndices[e] < 1) FNET_FAIL(ctx, "features_config: external feature indices are 1-based");
+    ctx->extIdx.push_back(extIndices[e] - 1);
+  }
+  if (dev_upload(ctx, &ctx->d_extIdx, ctx->extIdx.data(), ctx->extIdx.size())) return 1;
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) ctx->slots[i].featValid = false;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// cell list construction for a slot (host: per-structure bin geometry; device: binning)
+// ------------------------------------------------------------------------------------------
+static bool invert3(const double *L /* L[3*k+c] = lat vec k comp c */, double *inv /* inv[3*k+c] */) {
+  // M[c][k] = L[3k+c]; inv = M^-1, inv[3*k+c] = (M^-1)[k][c]
+  double m[3][3];
+  for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) m[c][k] = L[3 * k + c];
+  double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+               m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  if (fabs(det) < 1e-12) return false;   // fnetdata.F90:1155-1158
+  double id = 1.0 / det;
+  double r[3][3];
+  r[0][0] = (m[1][1] * m[2][2] - m[1][2] * m[2][1]) * id;
+  r[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id;
+  r[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+  r[1][0] = (m[1][2] * m[2][0] - m[1][0] * m[2][2]) * id;
+  r[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id;
+  r[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+  r[2][0] = (m[1][0] * m[2][1] - m[1][1] * m[2][0]) * id;
+  r[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id;
+  r[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+  for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) inv[3 * k + c] = r[k][c];
+  return true;
+}
+
+static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_coords_or_null) {
+  if (s.cellRc == rc) return 0;
+  if (!s.d_coords) FNET_FAIL(ctx, "slot has no geometry (coords were not uploaded)");
+  // non-periodic structures need their bounding box: fetch coordinates once
+  std::vector<double> hc;
+  bool anyCluster = false;
+  for (int st = 0; st < s.nStruct; st++) if (!s.h_periodic[st]) { anyCluster = true; break; }
+  if (anyCluster) {
+    hc.resize((size_t)3 * s.N);
+    CUDA_TRY(ctx, cudaMemcpyAsync(hc.data(), s.d_coords, hc.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  (void)h_coords_or_null;
+  std::vector<StructInfo> si(s.nStruct);
+  long long totalBins = 0;
+  for (int st = 0; st < s.nStruct; st++) {
+    StructInfo &S = si[st];
+    memset(&S, 0, sizeof(S));
+    S.atomBeg = s.h_offsets[st]; S.atomEnd = s.h_offsets[st + 1];
+    const int nAt = S.atomEnd - S.atomBeg;
+    S.periodic = s.h_periodic[st];
+    if (S.periodic) {
+      memcpy(S.lat, &s.h_lat[(size_t)9 * st], 9 * sizeof(double));
+      if (!invert3(S.lat, S.inv)) FNET_FAIL(ctx, "dependent lattice vectors");
+    } else {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int i = S.atomBeg; i < S.atomEnd; i++)
+        for (int c = 0; c < 3; c++) { lo[c] = std::min(lo[c], hc[3 * (size_t)i + c]); hi[c] = std::max(hi[c], hc[3 * (size_t)i + c]); }
+      for (int c = 0; c < 3; c++) {
+        double len = std::max(hi[c] - lo[c], 1e-3) * (1.0 + 1e-9) + 1e-9;
+        S.lo[c] = lo[c];
+        S.lat[3 * c + c] = len;
+        S.inv[3 * c + c] = 1.0 / len;
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      double bn = sqrt(S.inv[3 * k] * S.inv[3 * k] + S.inv[3 * k + 1] * S.inv[3 * k + 1] + S.inv[3 * k + 2] * S.inv[3 * k + 2]);
+      double h = 1.0 / bn;                       // spacing of the lattice planes normal to b_k
+      int nb = (int)floor(h / rc);
+      if (nb < 1) nb = 1;
+      S.nb[k] = nb;
+      S.D[k] = (h / nb >= rc) ? 1 : (int)ceil(rc / h);
+      if (!S.periodic) S.D[k] = std::min(S.D[k], 1);
+    }
+    // keep the number of bins comparable to the number of atoms
+    while ((long long)S.nb[0] * S.nb[1] * S.nb[2] > 2LL * nAt + 8) {
+      int k = 0;
+      if (S.nb[1] > S.nb[k]) k = 1;
+      if (S.nb[2] > S.nb[k]) k = 2;
+      if (S.nb[k] == 1) break;
+      S.nb[k] = (S.nb[k] + 1) / 2;
+    }
+    S.binBase = (int)totalBins;
+    totalBins += (long long)S.nb[0] * S.nb[1] * S.nb[2];
+    if (totalBins > 2000000000LL) FNET_FAIL(ctx, "cell list too large");
+  }
+  s.totalBins = (int)totalBins;
+  if (dev_upload(ctx, &s.d_sinfo, si.data(), si.size())) return 1;
+  if (dev_alloc(ctx, &s.d_fpos, (size_t)3 * s.N)) return 1;
+  if (dev_alloc(ctx, &s.d_cpos, (size_t)3 * s.N)) return 1;
+  if (dev_alloc(ctx, &s.d_atomCell, (size_t)s.N)) return 1;
+  if (dev_alloc(ctx, &s.d_cellAtoms, (size_t)s.N)) return 1;
+  if (dev_alloc(ctx, &s.d_cellStart, (size_t)s.totalBins + 1)) return 1;
+  if (dev_alloc(ctx, &s.d_cellCount, (size_t)s.totalBins)) return 1;
+  CUDA_TRY(ctx, cudaMemsetAsync(s.d_cellCount, 0, (size_t)s.totalBins * sizeof(int), ctx->stream));
+  const int B = 256;
+  LAUNCH(ctx, K_BIN_COUNT, (k_bin_count<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_coords, s.d_structOf, s.d_sinfo, s.d_fpos, s.d_atomCell, s.d_cellCount)));
+  LAUNCH(ctx, K_BIN_SCAN, (k_bin_scan<<<1, 1024, 0, ctx->stream>>>(s.totalBins, s.d_cellCount, s.d_cellStart)));
+  CUDA_TRY(ctx, cudaMemsetAsync(s.d_cellCount, 0, (size_t)s.totalBins * sizeof(int), ctx->stream));
+  LAUNCH(ctx, K_BIN_FILL, (k_bin_fill<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_atomCell, s.d_cellStart, s.d_cellCount, s.d_cellAtoms)));
+  LAUNCH(ctx, K_BIN_SORT, (k_bin_sort<<<(s.totalBins + B - 1) / B, B, 0, ctx->stream>>>(s.totalBins, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos)));
+  s.cellRc = rc;
+  s.maxNeigh = -1;
+  return 0;
+}
+
+static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
+  if (s.maxNeigh >= 0) return 0;
+  const double rc = ctx->acsf.rcMax;
+  if (dev_alloc(ctx, &s.d_neighCount, (size_t)s.N)) return 1;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+  const int B = 128;
+  const int grid = (int)(((long long)s.N * 32 + B - 1) / B);
+  LAUNCH(ctx, K_NEIGH_COUNT, (k_neigh_count<<<grid, B, 0, ctx->stream>>>(s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos, rc * rc, s.d_neighCount, ctx->d_flags)));
+  int h[8];
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  s.maxNeigh = h[0];
+  unsigned long long tot;
+  memcpy(&tot, &h[2], sizeof(tot));
+  s.meanNeigh = (double)tot / (double)s.N;
+  return 0;
+}
+
+extern "C" int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used || !ctx->acsfSet || ctx->acsf.F == 0) FNET_FAIL(ctx, "max_neighbors: need a dataset and an ACSF configuration");
+  cudaSetDevice(ctx->device);
+  if (ensure_cells(ctx, s, ctx->acsf.rcMax, nullptr)) return 1;
+  if (ensure_neigh_count(ctx, s)) return 1;
+  if (maxNeigh) *maxNeigh = s.maxNeigh;
+  if (meanNeigh) *meanNeigh = s.meanNeigh;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU plumbing: NCCL loaded lazily (dlopen) so the library has no link-time dependency
+// ------------------------------------------------------------------------------------------
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_getuid_t)(NcclUid *);
+typedef int (*nccl_initrank_t)(void **, int, NcclUid, int);
+typedef int (*nccl_allreduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_t)(int);
+static void *g_nccl = nullptr;
+static void *nccl_handle() {
+  if (!g_nccl) g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl) g_nccl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return g_nccl;
+}
+
+extern "C" int fnetgpu_comm_unique_id(char *id) {
+  void *h = nccl_handle();
+  if (!h) { g_err = std::string("cannot load libnccl: ") + dlerror(); return 1; }
+  nccl_getuid_t f = (nccl_getuid_t)dlsym(h, "ncclGetUniqueId");
+  NcclUid u;
+  if (!f || f(&u) != 0) { g_err = "ncclGetUniqueId failed"; return 1; }
+  memcpy(id, u.internal, FNETGPU_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+extern "C" int fnetgpu_comm_init(fnetgpu_ctx *ctx, int nRanks, int rank, const char *id) {
+  CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  if (nRanks < 1 || rank < 0 || rank >= nRanks) FNET_FAIL(ctx, "comm_init: bad rank / size");
+  void *h = nccl_handle();
+  if (!h) FNET_FAIL(ctx, std::string("cannot load libnccl: ") + dlerror());
+  nccl_initrank_t f = (nccl_initrank_t)dlsym(h, "ncclCommInitRank");
+  if (!f) FNET_FAIL(ctx, "ncclCommInitRank not found");
+  NcclUid u;
+  memcpy(u.internal, id, FNETGPU_UNIQUE_ID_BYTES);
+  void *comm = nullptr;
+  int rc = f(&comm, nRanks, u, rank);
+  if (rc != 0) FNET_FAIL(ctx, "ncclCommInitRank failed (" + std::to_string(rc) + ")");
+  ctx->nccl = h; ctx->comm = comm; ctx->nRanks = nRanks; ctx->rank = rank;
+  return 0;
+}
+
+// in-place sum all-reduce of n doubles on the library's stream (no-op for a single rank)
+static int allreduce_sum(fnetgpu_ctx *ctx, double *d_buf, size_t n) {
+  if (ctx->nRanks <= 1 || !ctx->comm) return 0;
+  nccl_allreduce_t f = (nccl_allreduce_t)dlsym(ctx->nccl, "ncclAllReduce");
+  if (!f) FNET_FAIL(ctx, "ncclAllReduce not found");
+  int rc = f(d_buf, d_buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+  if (rc != 0) FNET_FAIL(ctx, "ncclAllReduce failed (" + std::to_string(rc) + ")");
+  ctx->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// ACSF calculation
+// ------------------------------------------------------------------------------------------
+template <typename real>
+static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *zprec, int have_zprec) {
+  const AcsfTables &T = ctx->acsf;
+  const int F = T.F, nExtSel = (int)ctx->extIdx.size();
+  const int nFeat = F + nExtSel;
+  if (nFeat == 0) FNET_FAIL(ctx, "acsf_calculate: no features configured");
+  if (nExtSel > 0) {
+    for (int e : ctx->extIdx) if (e >= s.nExt) FNET_FAIL(ctx, "external feature index exceeds the dataset's extfeatures");
+  }
+  if (s.nFeat != nFeat || !s.d_feat) {
+    real *p = nullptr;
+    if (dev_alloc(ctx, &p, (size_t)s.N * nFeat)) return 1;
+    cudaFree(s.d_feat);
+    s.d_feat = p; s.nFeat = nFeat;
+  }
+  real *feat = (real *)s.d_feat;
+  const bool useGiven = standardize && have_zprec;
+  if (useGiven) {
+    if (!zprec) FNET_FAIL(ctx, "acsf_calculate: zprec missing");
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zprec, zprec, (size_t)2 * F * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->haveZ = true;
+  }
+  if (F > 0) {
+    if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
+    if (ensure_neigh_count(ctx, s)) return 1;
+    int cap = std::max(32, (s.maxNeigh + 31) & ~31);
+    const int WPB = 4;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      size_t smem = acsf_warp_smem_bytes(cap, F) * WPB;
+      int wpb = WPB;
+      while (smem > 220 * 1024 && wpb > 1) { wpb >>= 1; smem = acsf_warp_smem_bytes(cap, F) * wpb; }
+      if (smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+      const int grid = (s.N + wpb - 1) / wpb;
+      LAUNCH(ctx, K_ACSF, (k_acsf<real><<<grid, wpb * 32, smem, ctx->stream>>>(
+                              s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos,
+                              s.d_cpos, s.d_atnum, s.nExt, s.d_ext, T, cap, feat, nFeat,
+                              useGiven ? ctx->d_zprec : nullptr, nExtSel, ctx->d_extIdx, ctx->d_flags)));
+      int h[8];
+      CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (h[1] == 0) break;
+      if (attempt == 1) FNET_FAIL(ctx, "neighbour buffer overflow");
+      cap = (h[1] + 31) & ~31;
+    }
+  } else {
+    const int B = 256;
+    const long long tot = (long long)s.N * nExtSel;
+    LAUNCH(ctx, K_EXT_CONCAT, (k_ext_concat<real><<<(int)((tot + B - 1) / B), B, 0, ctx->stream>>>(s.N, s.nExt, s.d_ext, 0, nExtSel, ctx->d_extIdx, feat, nFeat)));
+  }
+  if (standardize && !have_zprec && F > 0) {
+    // acsf.F90:445-486 two-pass statistics with the dataset weights
+    const int apb = 256;
+    const int nb = (s.N + apb - 1) / apb;
+    size_t need = (size_t)nb * F + 2 * F + 8;
+    if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
+    double *part = ctx->d_partials, *sums = ctx->d_partials + (size_t)nb * F;   // sums[F] (+1 count)
+    if (ensure_pinned(ctx, (size_t)2 * F + 8)) return 1;
+    double wN = 0.0;
+    for (int st = 0; st < s.nStruct; st++) wN += 1.0;  // placeholder, replaced below
+    {
+      std::vector<double> dsw(s.nStruct);
+      CUDA_TRY(ctx, cudaMemcpyAsync(dsw.data(), s.d_dsw, s.nStruct * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      wN = 0.0;
+      for (int st = 0; st < s.nStruct; st++) wN += dsw[st] * (double)(s.h_offsets[st + 1] - s.h_offsets[st]);
+    }
+    double *h = ctx->h_pinned;
+    for (int pass = 0; pass < 2; pass++) {
+      LAUNCH(ctx, K_ZSTAT, (k_zstat<real><<<nb, 128, 0, ctx->stream>>>(s.N, F, nFeat, feat, s.d_structOf, s.d_dsw, pass ? ctx->d_zprec : nullptr, apb, part)));
+      LAUNCH(ctx, K_ZSTAT_FINAL, (k_zstat_final<<<(F + 127) / 128, 128, 0, ctx->stream>>>(nb, F, part, sums)));
+      if (pass == 0) {
+        // append the weighted atom count so one all-reduce carries both
+        CUDA_TRY(ctx, cudaMemcpyAsync(sums + F, &wN, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (allreduce_sum(ctx, sums, (size_t)F + 1)) return 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, sums, ((size_t)F + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        wN = h[F];
+        for (int a = 0; a < F; a++) h[a] = h[a] / wN;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zprec, h, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (zprec) memcpy(zprec, h, (size_t)F * sizeof(double));
+      } else {
+        if (allreduce_sum(ctx, sums, (size_t)F)) return 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, sums, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int a = 0; a < F; a++) h[a] = sqrt(h[a] / wN);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zprec + F, h, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (zprec) memcpy(zprec + F, h, (size_t)F * sizeof(double));
+      }
+    }
+    ctx->haveZ = true;
+    const long long tot = (long long)s.N * F;
+    LAUNCH(ctx, K_ZAPPLY, (k_zapply<real><<<(int)((tot + 255) / 256), 256, 0, ctx->stream>>>((size_t)s.N, F, nFeat, feat, ctx->d_zprec)));
+  }
+  if (!standardize) ctx->haveZ = false;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  s.featValid = true;
+  s.zscored = standardize && F > 0;
+  return 0;
+}
+
+extern "C" int fnetgpu_acsf_calculate(fnetgpu_ctx *ctx, int slot, int standardize, double *zprec, int have_zprec) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used) FNET_FAIL(ctx, "acsf_calculate: empty slot");
+  if (!ctx->acsfSet && ctx->extIdx.empty()) FNET_FAIL(ctx, "acsf_calculate: call fnetgpu_acsf_set / fnetgpu_features_config first");
+  cudaSetDevice(ctx->device);
+  if (ctx->precision == 64) return acsf_calculate_t<double>(ctx, s, standardize, zprec, have_zprec);
+  return acsf_calculate_t<float>(ctx, s, standardize, zprec, have_zprec);
+}
+
+template <typename real> __global__ void k_convert_out(size_t n, const real *__restrict__ in, double *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (double)in[t];
+}
+template <typename real> __global__ void k_convert_in(size_t n, const double *__restrict__ in, real *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (real)in[t];
+}
+
+// device real buffer -> host double buffer
+static int download_real(fnetgpu_ctx *ctx, const void *d_src, size_t n, double *h_dst) {
+  if (ctx->precision == 64) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    double *tmp = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&tmp, n * sizeof(double)));
+    LAUNCH(ctx, K_MISC, (k_convert_out<float><<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(n, (const float *)d_src, tmp)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fnetgpu_features_get(fnetgpu_ctx *ctx, int slot, double *out) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used || !s.featValid) FNET_FAIL(ctx, "features_get: features not computed");
+  cudaSetDevice(ctx->device);
+  return download_real(ctx, s.d_feat, (size_t)s.N * s.nFeat, out);
+}
+
+extern "C" int fnetgpu_features_set(fnetgpu_ctx *ctx, int slot, int nFeat, const double *in) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used) FNET_FAIL(ctx, "features_set: empty slot");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)s.N * nFeat;
+  cudaFree(s.d_feat); s.d_feat = nullptr;
+  if (ctx->precision == 64) {
+    double *p = nullptr;
+    if (dev_upload(ctx, &p, in, n)) return 1;
+    s.d_feat = p;
+  } else {
+    double *tmp = nullptr; float *p = nullptr;
+    if (dev_upload(ctx, &tmp, in, n)) return 1;
+    if (dev_alloc(ctx, &p, n)) return 1;
+    LAUNCH(ctx, K_MISC, (k_convert_in<float><<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(n, tmp, p)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    s.d_feat = p;
+  }
+  s.nFeat = nFeat; s.featValid = true;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// network
+// ------------------------------------------------------------------------------------------
+extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, const int *dims, int activationId) {
+  CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  if (nSpecies < 1) FNET_FAIL(ctx, "net_set: nSpecies < 1");
+  if (nLayers < 2 || nLayers > FNET_MAX_LAYERS) FNET_FAIL(ctx, "net_set: unsupported number of layers");
+  if (activationId < 0 || activationId > FNETGPU_ACT_LINEAR) FNET_FAIL(ctx, "net_set: unknown activation (no fallback)");
+  NetTables &n = ctx->net;
+  memset(&n, 0, sizeof(n));
+  n.nSpecies = nSpecies; n.L = nLayers; n.act = activationId; n.nOut = dims[nLayers - 1];
+  int ind = 0, rows = 0;
+  for (int l = 0; l < nLayers; l++) {
+    if (dims[l] < 1) FNET_FAIL(ctx, "net_set: layer width < 1");
+    n.dims[l] = dims[l];
+    n.aoff[l] = rows; rows += dims[l];
+  }
+  n.rowsA = rows;
+  for (int l = 0; l < nLayers; l++) { n.woff[l] = ind; ind += dims[l] * (l + 1 < nLayers ? dims[l + 1] : 1); }   // network.F90:413-419
+  for (int l = 0; l < nLayers; l++) { n.boff[l] = ind; ind += dims[l]; }                                        // network.F90:422-425
+  n.nTot = ind;
+  cudaFree(ctx->d_wb); ctx->d_wb = nullptr;
+  size_t bytes = (size_t)n.nTot * nSpecies * (ctx->precision == 64 ? 8 : 4);
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_wb, bytes));
+  if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
+  if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
+  ctx->netSet = true; ctx->paramsSet = false;
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) ctx->slots[i].nTiles = 0;
+  return 0;
+}
+
+extern "C" int fnetgpu_ntot(const fnetgpu_ctx *ctx) { return (ctx && ctx->netSet) ? ctx->net.nTot : -1; }
+
+extern "C" int fnetgpu_params_set(fnetgpu_ctx *ctx, const double *wb) {
+  CHECK_CTX(ctx);
+  if (!ctx->netSet) FNET_FAIL(ctx, "params_set: call fnetgpu_net_set first");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->net.nTot * ctx->net.nSpecies;
+  if (ctx->precision == 64) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wb, wb, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wb64, wb, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, K_MISC, (k_convert_in<float><<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_wb64, (float *)ctx->d_wb)));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->paramsSet = true;
+  return 0;
+}
+
+// tile table of the species-sorted atom order; T = threads (= atoms) per CTA
+template <typename real>
+static int ensure_tiles(fnetgpu_ctx *ctx, Slot &s) {
+  if (s.nTiles > 0) return 0;
+  const NetTables &n = ctx->net;
+  if ((int)s.spBeg.size() - 1 > n.nSpecies) FNET_FAIL(ctx, "dataset references more species than the network has sub-networks");
+  const SmemNet sn = smem_net_layout(n);
+  const int rowsD = n.rowsA - n.dims[0];
+  int T = 32;
+  const int cand[4] = {128, 96, 64, 32};
+  for (int c = 0; c < 4; c++) {
+    size_t sm = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (cand[c] + 1)) * sizeof(real);
+    if (sm <= 100 * 1024 || (cand[c] == 32 && sm <= 220 * 1024)) { T = cand[c]; break; }
+    if (cand[c] == 32) FNET_FAIL(ctx, "network too large for the shared-memory tile (layer widths sum too big)");
+  }
+  std::vector<int> tiles;
+  for (int sp = 0; sp + 1 < (int)s.spBeg.size(); sp++)
+    for (int b = s.spBeg[sp]; b < s.spBeg[sp + 1]; b += T) {
+      tiles.push_back(b); tiles.push_back(std::min(T, s.spBeg[sp + 1] - b)); tiles.push_back(sp);
+    }
+  s.nTiles = (int)tiles.size() / 3; s.tileT = T;
+  if (dev_upload(ctx, &s.d_tiles, tiles.data(), tiles.size())) return 1;
+  real *raw = nullptr;
+  if (dev_alloc(ctx, &raw, (size_t)s.N * n.nOut)) return 1;
+  cudaFree(s.d_raw); s.d_raw = raw;
+  if (dev_alloc(ctx, &s.d_gS, (size_t)s.nStruct * std::max(s.nG, 1))) return 1;
+  if (dev_alloc(ctx, &s.d_Es, (size_t)s.nStruct * std::max(s.nG, 1))) return 1;
+  if (dev_alloc(ctx, &s.d_lossPart, (size_t)2 * s.nStruct)) return 1;
+  return 0;
+}
+
+template <typename real>
+static int check_ready(fnetgpu_ctx *ctx, Slot &s, bool needTargets) {
+  if (!s.used) FNET_FAIL(ctx, "empty dataset slot");
+  if (!ctx->netSet || !ctx->paramsSet) FNET_FAIL(ctx, "network / parameters not set");
+  if (!s.featValid) FNET_FAIL(ctx, "features of this slot have not been computed");
+  if (s.nFeat != ctx->net.dims[0]) FNET_FAIL(ctx, "feature count does not match the input layer width");
+  if (needTargets && s.nG + s.nA != ctx->net.nOut) FNET_FAIL(ctx, "number of targets does not match the output layer width");
+  return ensure_tiles<real>(ctx, s);
+}
+
+template <typename real>
+static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
+  const NetTables &n = ctx->net;
+  const SmemNet sn = smem_net_layout(n);
+  int dmax = 1;
+  for (int l = 0; l < n.L; l++) dmax = std::max(dmax, n.dims[l]);
+  const int T = s.tileT;
+  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)2 * dmax * (T + 1)) * sizeof(real);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_fwd<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = std::max(1, (int)(200 * 1024 / smem));
+  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
+  LAUNCH(ctx, K_MLP_FWD, (k_mlp_fwd<real><<<grid, T, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, dmax, (real *)s.d_raw)));
+  return 0;
+}
+
+template <typename real>
+static int run_struct_loss(fnetgpu_ctx *ctx, Slot &s, int lossId) {
+  const NetTables &n = ctx->net;
+  const int B = 128;
+  const int grid = (int)(((long long)s.nStruct * 32 + B - 1) / B);
+  LAUNCH(ctx, K_STRUCT_LOSS, (k_struct_loss<real><<<grid, B, 0, ctx->stream>>>(s.nStruct, s.d_offsets, n.nOut, s.nG, s.nA, (const real *)s.d_raw, s.d_gt, s.d_at, s.d_aw, s.d_dsw, lossId, s.d_Es, s.d_gS, s.d_lossPart)));
+  const size_t nDD = (size_t)n.nTot * n.nSpecies;
+  LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
+  return 0;
+}
+
+template <typename real>
+static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, double *loss, double *globalPred) {
+  if (check_ready<real>(ctx, s, true)) return 1;
+  const NetTables &n = ctx->net;
+  const size_t nDD = (size_t)n.nTot * n.nSpecies;
+  if (run_forward<real>(ctx, s)) return 1;
+  if (run_struct_loss<real>(ctx, s, lossId)) return 1;
+  const SmemNet sn = smem_net_layout(n);
+  const int T = s.tileT, rowsD = n.rowsA - n.dims[0];
+  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (T + 1)) * sizeof(real);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_bwd<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = std::max(1, (int)(200 * 1024 / smem));
+  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
+  size_t need = (size_t)grid * nDD;
+  if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_partials, 0, need * sizeof(double), ctx->stream));
+  LAUNCH(ctx, K_MLP_GRAD, (k_mlp_bwd<real, 0><<<grid, T, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (real *)nullptr)));
+  LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
+  if (allreduce_sum(ctx, ctx->d_dd, nDD + 2)) return 1;   // gradient | loss numerator | denominator
+  if (ddSerial || loss) {
+    if (ensure_pinned(ctx, nDD + 8)) return 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dd, (nDD + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ddSerial) memcpy(ddSerial, ctx->h_pinned, nDD * sizeof(double));
+    if (loss) *loss = ctx->h_pinned[nDD] / ctx->h_pinned[nDD + 1];
+  }
+  if (globalPred && s.nG > 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(globalPred, s.d_Es, (size_t)s.nG * s.nStruct * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int fnetgpu_grad(fnetgpu_ctx *ctx, int slot, int lossId, const int *shuffle, double *ddSerial,
+                            double *loss, double *globalPred) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  (void)shuffle;   // only permutes the summation order in the reference (bpnn.F90:436-437)
+  if (lossId < 0 || lossId > FNETGPU_LOSS_MAPE) FNET_FAIL(ctx, "grad: unknown loss id");
+  cudaSetDevice(ctx->device);
+  Slot &s = ctx->slots[slot];
+  if (ctx->precision == 64) return grad_t<double>(ctx, s, lossId, ddSerial, loss, globalPred);
+  return grad_t<float>(ctx, s, lossId, ddSerial, loss, globalPred);
+}
+
+template <typename real>
+static int predict_t(fnetgpu_ctx *ctx, Slot &s, double *raw) {
+  if (check_ready<real>(ctx, s, false)) return 1;
+  if (run_forward<real>(ctx, s)) return 1;
+  if (raw) return download_real(ctx, s.d_raw, (size_t)s.N * ctx->net.nOut, raw);
+  return 0;
+}
+
+extern "C" int fnetgpu_predict(fnetgpu_ctx *ctx, int slot, double *raw) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  cudaSetDevice(ctx->device);
+  Slot &s = ctx->slots[slot];
+  if (ctx->precision == 64) return predict_t<double>(ctx, s, raw);
+  return predict_t<float>(ctx, s, raw);
+}
+
+template <typename real>
+static int loss_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *loss) {
+  if (check_ready<real>(ctx, s, true)) return 1;
+  const size_t nDD = (size_t)ctx->net.nTot * ctx->net.nSpecies;
+  if (run_forward<real>(ctx, s)) return 1;
+  if (run_struct_loss<real>(ctx, s, lossId)) return 1;
+  if (allreduce_sum(ctx, ctx->d_dd + nDD, 2)) return 1;
+  double h[2];
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_dd + nDD, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (loss) *loss = h[0] / h[1];
+  return 0;
+}
+
+extern "C" int fnetgpu_loss(fnetgpu_ctx *ctx, int slot, int lossId, double *loss) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  if (lossId < 0 || lossId > FNETGPU_LOSS_MAPE) FNET_FAIL(ctx, "loss: unknown loss id");
+  cudaSetDevice(ctx->device);
+  Slot &s = ctx->slots[slot];
+  if (ctx->precision == 64) return loss_t<double>(ctx, s, lossId, loss);
+  return loss_t<float>(ctx, s, lossId, loss);
+}
+
+// ------------------------------------------------------------------------------------------
+// forces
+// ------------------------------------------------------------------------------------------
+template <typename real>
+static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
+  if (check_ready<real>(ctx, s, false)) return 1;
+  const AcsfTables &T = ctx->acsf;
+  const NetTables &n = ctx->net;
+  if (!ctx->acsfSet || T.F == 0) FNET_FAIL(ctx, "forces: need an ACSF configuration");
+  if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "forces: not defined with external features (initprogram.F90:1543-1548)");
+  if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
+  if (ensure_neigh_count(ctx, s)) return 1;
+  // (1) dE_k/dG for every atom and output: one reverse sweep per output
+  if (!s.d_dEdG) { real *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
+  const SmemNet sn = smem_net_layout(n);
+  const int TT = s.tileT, rowsD = n.rowsA - n.dims[0];
+  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (TT + 1)) * sizeof(real);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_bwd<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = std::max(1, (int)(200 * 1024 / smem));
+  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
+  LAUNCH(ctx, K_MLP_INGRAD, (k_mlp_bwd<real, 1><<<grid, TT, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr, (real *)s.d_dEdG)));
+  // the force kernel contracts in FP64
+  const double *dEdG64 = nullptr;
+  double *tmp64 = nullptr;
+  const size_t nD = (size_t)s.N * n.nOut * T.F;
+  if (ctx->precision == 64) dEdG64 = (const double *)s.d_dEdG;
+  else {
+    CUDA_TRY(ctx, cudaMalloc((void **)&tmp64, nD * sizeof(double)));
+    LAUNCH(ctx, K_MISC, (k_convert_out<float><<<(int)((nD + 255) / 256), 256, 0, ctx->stream>>>(nD, (const float *)s.d_dEdG, tmp64)));
+    dEdG64 = tmp64;
+  }
+  if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, (size_t)3 * n.nOut * s.N)) return 1; }
+  CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
+  int cap = std::max(32, (s.maxNeigh + 31) & ~31);
+  int wpb = 4;
+  size_t fs = force_warp_smem_bytes(cap, T.F) * wpb;
+  while (fs > 220 * 1024 && wpb > 1) { wpb >>= 1; fs = force_warp_smem_bytes(cap, T.F) * wpb; }
+  if (fs > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+  dim3 g((s.N + wpb - 1) / wpb, n.nOut);
+  LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<<<g, wpb * 32, fs, ctx->stream>>>(s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos, s.d_atnum, s.nExt, s.d_ext, T, cap, dEdG64, n.nOut, s.zscored ? ctx->d_zprec : nullptr, s.d_forces, ctx->d_flags)));
+  int h[8];
+  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  if (forces) CUDA_TRY(ctx, cudaMemcpyAsync(forces, s.d_forces, (size_t)3 * n.nOut * s.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (tmp64) cudaFree(tmp64);
+  if (h[1] != 0) FNET_FAIL(ctx, "neighbour buffer overflow in the force kernel");
+  return 0;
+}
+
+extern "C" int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  cudaSetDevice(ctx->device);
+  Slot &s = ctx->slots[slot];
+  if (ctx->precision == 64) return forces_t<double>(ctx, s, forces);
+  return forces_t<float>(ctx, s, forces);
+}

@@ -1,0 +1,226 @@
+// internal.h -- shared declarations of libfnetgpu (context, device tables, launch macros).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <stdexcept>
+
+#include "../../include/fnetgpu.h"
+
+#define FNET_WARP 32
+#define FNET_MAX_LAYERS 16
+#define FNET_MAX_CODES 14          // distinct atomic numbers referenced by species-resolved functions
+#define FNET_RCHUNK 8              // radial functions per register chunk
+#define FNET_LADDER 8              // angular functions per ladder slot
+#define FNET_SLOTS 4               // ladder slots per angular pass (=> 32 accumulators)
+
+// ------------------------------------------------------------------------------------------
+// kernel ids for launch counting / per-kernel event timing
+// ------------------------------------------------------------------------------------------
+enum KernelId {
+  K_BIN_COUNT = 0, K_BIN_SCAN, K_BIN_FILL, K_BIN_SORT, K_NEIGH_COUNT, K_ACSF, K_ZSTAT, K_ZSTAT_FINAL,
+  K_ZAPPLY, K_EXT_CONCAT, K_MLP_FWD, K_STRUCT_LOSS, K_LOSS_FINAL, K_MLP_GRAD, K_GRAD_REDUCE,
+  K_MLP_INGRAD, K_ACSF_FORCE, K_MISC, K_NUM_KERNELS
+};
+
+struct StructInfo {
+  double lat[9];     // lat[3*k+c]: component c of lattice (or bounding-box) vector k
+  double inv[9];     // fractional s_k = sum_c inv[3*k+c] * (r_c - lo_c)
+  double lo[3];      // origin of the bounding box (0 for periodic cells)
+  int nb[3];         // bins per direction
+  int D[3];          // bin reach per direction (1 unless the cell is thinner than rc)
+  int binBase;       // first global bin of this structure
+  int periodic;
+  int atomBeg, atomEnd;
+};
+
+// Radial group: functions sharing (type, rc, atomId, species list); evaluated in chunks of
+// FNET_RCHUNK functions, nChunksP2 = chunk count padded to a power of two <= 32.
+struct RadialGroup {
+  int type;          // 1..3
+  int code;          // species code of the neighbour list, -1 = all neighbours
+  int atomId;        // 0 or 1-based ext row
+  int fBeg, fCnt;    // slice of the radial function tables
+  int nChunksP2;
+  double rc;
+};
+
+struct LadderSlot {
+  double lam, xi0, dxi;
+  int count;
+  int feat[FNET_LADDER];       // output feature index
+  double pref[FNET_LADDER];    // 2^(1-xi)
+  double xi[FNET_LADDER];      // exponents (used by the derivative kernel)
+};
+
+// Angular pass: up to FNET_SLOTS ladders evaluated in one sweep over the pairs of
+// (list code1) x (list code2) with shared pair geometry (same type, rc, eta, atomId).
+struct AngularPass {
+  int type;          // 4 or 5
+  int code1, code2;  // -1 = all neighbours
+  int same;          // lists identical (unordered pairs incl. diagonal)
+  int atomId;
+  int nSlots;
+  double rc, eta;
+  LadderSlot slot[FNET_SLOTS];
+};
+
+struct AcsfTables {           // device pointers + sizes, passed by value to kernels
+  int F;                      // number of ACSF functions
+  int nRadialGroups, nAngularPasses;
+  const RadialGroup *rgroups;
+  const int *rfeat;           // radial function tables
+  const double *rp1, *rp2;    // (eta, rs) for G2, (kappa, -) for G3
+  const AngularPass *apasses;
+  int nCodes;                 // number of species codes
+  int zcodes[FNET_MAX_CODES]; // atomic number of each code
+  int anyAtomId;
+  double rcMax;
+};
+
+struct NetTables {
+  int nSpecies, L, act, nTot, nOut;
+  int dims[FNET_MAX_LAYERS];
+  int woff[FNET_MAX_LAYERS], boff[FNET_MAX_LAYERS];
+  int aoff[FNET_MAX_LAYERS];  // row offset of layer l activations in the smem tile
+  int rowsA;                  // sum of dims
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Slot {
+  bool used = false;
+  int nStruct = 0, N = 0, nG = 0, nA = 0, nExt = 0;
+  // host copies needed later
+  std::vector<int> h_offsets;
+  std::vector<int> h_globalsp;      // 0-based
+  std::vector<double> h_lat;
+  std::vector<int> h_periodic;
+  // device data
+  int *d_offsets = nullptr, *d_structOf = nullptr, *d_atnum = nullptr, *d_sp = nullptr, *d_periodic = nullptr;
+  double *d_coords = nullptr;       // [N][3] as given
+  double *d_fpos = nullptr;         // [N][3] folded positions (atom order)
+  double *d_cpos = nullptr;         // [N][3] folded positions (cell order)
+  StructInfo *d_sinfo = nullptr;
+  int *d_atomCell = nullptr, *d_cellStart = nullptr, *d_cellCount = nullptr, *d_cellAtoms = nullptr;
+  int totalBins = 0;
+  double cellRc = -1.0;             // cutoff the cell list was built for
+  double *d_dsw = nullptr;          // [nStruct] dataset weights as double
+  double *d_aw = nullptr;           // [N]
+  double *d_gt = nullptr, *d_at = nullptr, *d_ext = nullptr;
+  void *d_feat = nullptr;           // [N][nFeat] real
+  int nFeat = 0;
+  bool featValid = false;
+  bool zscored = false;             // features were standardised with ctx->d_zprec
+  int maxNeigh = -1; double meanNeigh = 0.0;
+  int *d_neighCount = nullptr;
+  // species-sorted processing order
+  int *d_perm = nullptr;            // [N] atom ids sorted by species (stable)
+  std::vector<int> spBeg;           // [nSpecies+1]
+  int *d_tiles = nullptr; int nTiles = 0, tileT = 0; // (start, count, species) triples
+  // work buffers
+  void *d_raw = nullptr;            // [N][nOut] real
+  double *d_gS = nullptr;           // [nStruct][nG] loss gradients of the global targets
+  double *d_Es = nullptr;           // [nStruct][nG]
+  double *d_lossPart = nullptr;     // [nStruct][2]
+  void *d_dEdG = nullptr;           // [N][nG][F] real
+  double *d_forces = nullptr;       // [N][3*nOut]
+};
+
+struct fnetgpu_ctx {
+  int device = 0;
+  int precision = 64;
+  int deterministic = 1;
+  cudaStream_t stream = nullptr;
+  bool ownStream = true;
+  std::string err;
+  int nSM = 148;
+  long long launches = 0;
+  bool profiling = false;
+  double kms[K_NUM_KERNELS];
+  long long klaunch[K_NUM_KERNELS];
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ACSF config
+  bool acsfSet = false;
+  AcsfTables acsf;                  // device pointers inside
+  std::vector<RadialGroup> h_rgroups;
+  std::vector<AngularPass> h_apasses;
+  RadialGroup *d_rgroups = nullptr; int *d_rfeat = nullptr; double *d_rp1 = nullptr, *d_rp2 = nullptr;
+  AngularPass *d_apasses = nullptr;
+  std::vector<int> extIdx;          // 0-based rows of ext appended to the features
+  int *d_extIdx = nullptr;
+  double *d_zprec = nullptr;        // [2F] means, sigmas
+  bool haveZ = false;
+  // network
+  bool netSet = false;
+  NetTables net;
+  void *d_wb = nullptr;             // [nSpecies][nTot] real
+  double *d_wb64 = nullptr;
+  bool paramsSet = false;
+  // gradient work
+  double *d_partials = nullptr; size_t partialsN = 0;
+  double *d_dd = nullptr;           // [nSpecies*nTot + 2] reduced gradient + loss numerator/denominator
+  double *h_pinned = nullptr; size_t pinnedN = 0;
+  int *d_flags = nullptr;           // [4] overflow flag etc.
+  // comm
+  void *nccl = nullptr;             // dlopen handle
+  void *comm = nullptr;             // ncclComm_t
+  int nRanks = 1, rank = 0;
+  Slot slots[FNETGPU_MAX_SLOTS];
+};
+
+#define CUDA_TRY(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define FNET_FAIL(ctx, msg)                                                                  \
+  do { (ctx)->err = (msg); return 1; } while (0)
+
+// Launch wrapper: counts launches and (in profile mode) brackets the kernel with events.
+#define LAUNCH(ctx, kid, ...)                                                                \
+  do {                                                                                       \
+    if ((ctx)->profiling) cudaEventRecord((ctx)->ev0, (ctx)->stream);                        \
+    __VA_ARGS__;                                                                             \
+    (ctx)->launches++; (ctx)->klaunch[kid]++;                                                \
+    if ((ctx)->profiling) {                                                                  \
+      cudaEventRecord((ctx)->ev1, (ctx)->stream);                                            \
+      cudaEventSynchronize((ctx)->ev1);                                                      \
+      float _ms = 0.f; cudaEventElapsedTime(&_ms, (ctx)->ev0, (ctx)->ev1);                   \
+      (ctx)->kms[kid] += _ms;                                                                \
+    }                                                                                        \
+    cudaError_t _le = cudaGetLastError();                                                    \
+    if (_le != cudaSuccess) {                                                                \
+      (ctx)->err = std::string("kernel launch failed (") + fnetgpu_kernel_name(kid) + "): " + \
+                   cudaGetErrorString(_le);                                                  \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+static inline int dev_alloc(fnetgpu_ctx *ctx, T **p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  CUDA_TRY(ctx, cudaMalloc((void **)p, n * sizeof(T)));
+  return 0;
+}
+template <typename T>
+static inline int dev_upload(fnetgpu_ctx *ctx, T **p, const T *h, size_t n) {
+  if (dev_alloc(ctx, p, n)) return 1;
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(*p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}

@@ -1,0 +1,133 @@
+/*
+ * fnetgpu.h -- C ABI of libfnetgpu.so, the B200 (sm_100a) implementation of Fortnet's
+ * data-parallel hot path: ACSF featurisation (+ analytic Cartesian derivatives) and the
+ * per-species Behler-Parrinello subnetwork forward/backward.
+ *
+ * The reference (vanderhe/fortnet v0.7.4, Fortran 2008) has no FFI for this path; its seams
+ * are type-bound procedures called from prg_fnet/fortnet.F90 and lib_nn/bpnn.F90.  Every
+ * entry point below names the reference call site it replaces (paths relative to
+ * /root/reference/prog/fortnet/).  The ISO_C_BINDING shim a maintainer adds on the Fortran
+ * side is shown in INTEGRATION.md (fortnet_b200/host/fnet_gpu.F90).
+ *
+ * Conventions
+ *   - plain C: ints are 32-bit, reals are FP64 regardless of the compute precision, all
+ *     arrays are caller-owned HOST buffers laid out exactly as the Fortran driver holds them
+ *     (column-major, so `array(F, nAtom)` is `feature fastest`); the library copies in/out
+ *     during the call and owns all device memory behind the opaque context;
+ *   - atom/species/feature indices that cross the boundary are 1-based like the reference's;
+ *   - lengths are Bohr; coordinates Cartesian; latvecs[9*s + 3*k + c] = latVecs(c,k) of
+ *     structure s (lib_dftbp/typegeometry.F90:24-59);
+ *   - every function returns 0 on success, non-zero on error (message via
+ *     fnetgpu_last_error); nothing throws, exits or falls back to the CPU.  The shim maps a
+ *     non-zero status to `call error(msg)` (lib_dftbp/message.F90:73-103);
+ *   - one host thread per context, calls are blocking unless stated otherwise.
+ */
+#ifndef FNETGPU_H
+#define FNETGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fnetgpu_ctx fnetgpu_ctx;
+
+/* activation ids (lib_nn/transfer.F90:54-342, lib_nn/layer.F90:88-150) */
+enum {
+  FNETGPU_ACT_GAUSSIAN = 0, FNETGPU_ACT_RELU = 1, FNETGPU_ACT_LRELU = 2, FNETGPU_ACT_SOFTPLUS = 3,
+  FNETGPU_ACT_BENT = 4, FNETGPU_ACT_ATAN = 5, FNETGPU_ACT_SIGMOID = 6, FNETGPU_ACT_HEAVISIDE = 7,
+  FNETGPU_ACT_TANH = 8, FNETGPU_ACT_LINEAR = 9
+};
+/* loss ids (lib_fortnet/initprogram.F90:1195-1226, lib_common/loss.F90:217-281,370-721) */
+enum { FNETGPU_LOSS_MSE = 0, FNETGPU_LOSS_RMS = 1, FNETGPU_LOSS_MAE = 2, FNETGPU_LOSS_MAPE = 3 };
+/* G-function types (lib_descriptors/acsf.F90:225-270) */
+enum { FNETGPU_G1 = 1, FNETGPU_G2 = 2, FNETGPU_G3 = 3, FNETGPU_G4 = 4, FNETGPU_G5 = 5 };
+
+#define FNETGPU_MAX_SLOTS 8        /* dataset slots: 0 = training set, 1 = validation set, ... */
+#define FNETGPU_UNIQUE_ID_BYTES 128
+
+/* ---- lifecycle: replaces TEnv_init / destructGlobalEnv (lib_dftbp/globalenv.F90:88-172) ---- */
+/* device < 0: use $LOCAL_RANK if set, else device 0.  precision: 64 or 32 (compute/storage
+ * type of features and activations; parity guarantees are stated for 64).  deterministic != 0:
+ * fixed-order reductions everywhere (force scatter uses per-atom ordered accumulation). */
+int fnetgpu_init(fnetgpu_ctx **ctx, int device, int precision, int deterministic);
+int fnetgpu_finalize(fnetgpu_ctx *ctx);
+const char *fnetgpu_last_error(const fnetgpu_ctx *ctx);
+int fnetgpu_synchronize(fnetgpu_ctx *ctx);
+
+/* ---- dataset: what calculateMappings / nTrain receive as TDataset
+ *      (prg_fnet/fortnet.F90:883-889, lib_nn/bpnn.F90:438-441) ---- */
+int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct,
+                           const int *natomOffsets /* [nStruct+1], 0-based prefix sums */,
+                           const double *coords /* [3*N] */, const int *periodic /* [nStruct] */,
+                           const double *latvecs /* [9*nStruct] */, const int *atnum /* [N] localAtToAtNum */,
+                           const int *globalsp /* [N] localAtToGlobalSp, 1-based */,
+                           const int *dsWeights /* [nStruct] or NULL (=1) */,
+                           const double *atomicWeights /* [N] or NULL (=1) */,
+                           int nG, const double *gTargets /* [nG*nStruct] */,
+                           int nA, const double *aTargets /* [nA*N] */,
+                           int nExt, const double *ext /* [nExt*N] = extFeatures(e,i) */);
+/* new geometry for the same atoms (socket/MD path, prg_fnet/fortnet.F90:138-165) */
+int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs);
+
+/* ---- ACSF: TAcsf_init / TAcsf%calculate (lib_descriptors/acsf.F90:148-167, 540-639) ---- */
+int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const double *rcut, const double *kappa,
+                     const double *rs, const double *eta, const double *lambda, const double *xi,
+                     const int *atomid, const int *atomicnumbers /* [2*F] */);
+/* external features appended after the ACSF block: TFeatures_collect
+ * (lib_types/features.F90:200-265); extIndices are 1-based rows of ext */
+int fnetgpu_features_config(fnetgpu_ctx *ctx, int nExtSel, const int *extIndices);
+/* standardize != 0: z-score (acsf.F90:626-631).  have_zprec != 0: zprec[0..F) = means,
+ * zprec[F..2F) = "variances" (population sigma) are inputs; else they are computed from this
+ * slot with the dataset weights (acsf.F90:445-486) and returned. */
+int fnetgpu_acsf_calculate(fnetgpu_ctx *ctx, int slot, int standardize, double *zprec, int have_zprec);
+/* parity/debug: the assembled feature matrix array(nFeat, N) of the slot */
+int fnetgpu_features_get(fnetgpu_ctx *ctx, int slot, double *out /* [nFeat*N] */);
+/* bypass ACSF: load precomputed features (TFeatures%trainFeatures) */
+int fnetgpu_features_set(fnetgpu_ctx *ctx, int slot, int nFeat, const double *in /* [nFeat*N] */);
+
+/* ---- network: TBpnn_init + serializedWeightsAndBiases / serialWeightsAndBiasesFillup
+ *      (lib_nn/bpnn.F90:96-143, 782-822; layout lib_nn/network.F90:397-459) ---- */
+int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, const int *dims, int activationId);
+int fnetgpu_ntot(const fnetgpu_ctx *ctx);                       /* nWeights + nBiases per species */
+int fnetgpu_params_set(fnetgpu_ctx *ctx, const double *wb /* [nTot*nSpecies] */);
+
+/* ---- training gradient: TBpnn_updateGradients + loss (bpnn.F90:277-283, 317-323, 394-481)
+ * ddSerial = TDerivs_serialized(resDd) (lib_common/nestedtypes.F90:428-470): un-normalised,
+ * before regularisation -- exactly what TBpnn_update (bpnn.F90:708-778) consumes.
+ * loss = loss(resPredicts, ...) with dataset weights.  globalPred (optional) = per-structure
+ * sums of the first nG outputs.  shuffle is accepted for interface parity; it only permutes
+ * the summation order (bpnn.F90:436-437) and is ignored.  With an initialised communicator
+ * (fnetgpu_comm_init) ddSerial and loss are the sums over all ranks' shards.
+ * ddSerial == NULL && loss == NULL: compute only, results stay on the device. */
+int fnetgpu_grad(fnetgpu_ctx *ctx, int slot, int lossId, const int *shuffle,
+                 double *ddSerial /* [nTot*nSpecies] */, double *loss, double *globalPred /* [nG*nStruct] or NULL */);
+
+/* ---- prediction: TBpnn_predictBatch (bpnn.F90:1001-1058) and validation loss ---- */
+int fnetgpu_predict(fnetgpu_ctx *ctx, int slot, double *raw /* [nOut*N] = predicts(t,i), dataset atom order */);
+int fnetgpu_loss(fnetgpu_ctx *ctx, int slot, int lossId, double *loss);
+
+/* ---- forces: TAcsf%calculatePrime + TBpnn%nJacobian + forceAnalysis_analytical fused
+ *      (acsf.F90:643-717, bpnn.F90:937-997, lib_analysis/forces.F90:317-425).
+ * forces[(3*nOut)*f + 3*t + c] = forces%geos(s)%array(c+3(t-1), f).  The dense
+ * [3,F,N,N] tensor and the Jacobians never exist. */
+int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces /* [3*nOut*N] */);
+
+/* ---- multi-GPU (one process per GPU): replaces the mpifx_allreduce of dw/db
+ *      (bpnn.F90:460-467) by ONE NCCL all-reduce of [ddSerial | loss terms] on the
+ *      library's stream, and the z-score statistics by two small all-reduces. ---- */
+int fnetgpu_comm_unique_id(char *id /* [FNETGPU_UNIQUE_ID_BYTES] */);
+int fnetgpu_comm_init(fnetgpu_ctx *ctx, int nRanks, int rank, const char *id);
+
+/* ---- plumbing for benchmarks / profiling ---- */
+int fnetgpu_set_stream(fnetgpu_ctx *ctx, void *cudaStream);   /* run on the caller's stream */
+long long fnetgpu_launch_count(const fnetgpu_ctx *ctx);       /* kernels launched so far */
+/* per-kernel CUDA-event timing: enable, run, then read (kernel ids: see fnetgpu_kernel_name) */
+int fnetgpu_profile(fnetgpu_ctx *ctx, int enable);
+int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kernelId, double *ms_total, long long *launches);
+const char *fnetgpu_kernel_name(int kernelId);                /* NULL past the last id */
+int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNETGPU_H */

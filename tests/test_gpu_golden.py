@@ -1,0 +1,100 @@
+"""GPU parity (through the C ABI) against the reference's own golden files and the CPU oracle.
+Tolerance: the reference comparator's ATOL 1e-10 / RTOL 1e-9 (FP64 mode)."""
+import numpy as np
+import pytest
+
+import golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fortnet_b200 as fb
+    return fb
+
+
+def _setup(fb, case, precision=64):
+    ctx = fb.Context(precision=precision)
+    ds = case.dataset
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=case.zmeans is not None,
+                   ext_indices=case.ext_indices)
+    zp = np.stack([case.zmeans, case.zsigmas]) if case.zmeans is not None else None
+    acsf.calculate(0, zprec=zp)
+    net = fb.Bpnn(ctx, case.dims, len(case.atomic_numbers), case.activation)
+    net.set_params(case.wb())
+    return ctx, acsf, net
+
+
+PRED = gio.cases(mode=("predict", "validate"), forces=(None, "analytical"))
+
+
+@pytest.mark.parametrize("entry", PRED, ids=[e["case"] for e in PRED])
+def test_predictions_and_forces(fb, entry):
+    case = gio.Case(entry)
+    ctx, acsf, net = _setup(fb, case)
+    ds = case.dataset
+    raw = net.predict_batch(0)
+    assert gio.allclose(raw, case.arr["out_rawpredictions"]), gio.maxdiff(raw, case.arr["out_rawpredictions"])
+    if case.nG and "out_globalpredictions" in case.arr:
+        glob = np.add.reduceat(raw[:, :case.nG], ds.offsets[:-1].astype(int), axis=0)
+        assert gio.allclose(glob, case.arr["out_globalpredictions"])
+    if case.forces == "analytical":
+        f = net.forces(0)
+        assert gio.allclose(f, case.arr["out_forces"]), gio.maxdiff(f, case.arr["out_forces"])
+    ctx.close()
+
+
+SD = gio.cases(mode=("train",), training=("sd",))
+
+
+@pytest.mark.parametrize("entry", SD, ids=[e["case"] for e in SD])
+def test_sd_training_step(fb, entry):
+    from oracle import oracle as orc
+    case = gio.Case(entry)
+    ctx, acsf, net = _setup(fb, case)
+    ds = case.dataset
+    wb0 = case.wb()
+    dd, loss = net.update_gradients(0, loss=case.loss_name())
+    wb1, _ = case.sd_update(wb0, dd)
+    ref = case.wb("ref_")
+    assert gio.allclose(wb1, ref), gio.maxdiff(wb1, ref)
+    # loss value and raw gradient against the oracle on the same features
+    feats = acsf.features(0)
+    dd_o, raw_o = orc.grad(ds.offsets, feats, ds.globalsp, case.dims, case.activation, wb0,
+                           case.loss_name(), ds.weights, ds.atomic_weights, ds.gtargets, ds.atargets)
+    assert np.allclose(dd, dd_o, rtol=1e-9, atol=1e-10), gio.maxdiff(dd, dd_o)
+    loss_o = orc.loss(ds.offsets, raw_o, case.loss_name(), case.nG, case.nA, ds.gtargets, ds.atargets,
+                      ds.atomic_weights, ds.weights)
+    assert abs(loss - loss_o) <= 1e-10 + 1e-9 * abs(loss_o), (loss, loss_o)
+    ctx.close()
+
+
+ZS = [e for e in gio.cases(mode=("train",))]
+
+
+@pytest.mark.parametrize("entry", ZS, ids=[e["case"] for e in ZS])
+def test_features_and_zscore_statistics(fb, entry):
+    """raw ACSF vs oracle, and statistics computed on the GPU vs the stored netstat values."""
+    from oracle import oracle as orc
+    case = gio.Case(entry)
+    if not case.funcs:
+        pytest.skip("no ACSF in this case")
+    ds = case.dataset
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=False)
+    acsf.calculate(0)
+    vals = acsf.features(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, case.funcs, ext=ds.ext)
+    assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), gio.maxdiff(vals, ref)
+    if case.zmeans is not None and case.name != "input/weighting/datapoints/restart/multispecies/globalTargets/acsfPrec":
+        acsf2 = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=True)
+        acsf2.calculate(0)
+        assert gio.allclose(acsf2.zprec[0], case.zmeans), gio.maxdiff(acsf2.zprec[0], case.zmeans)
+        assert gio.allclose(acsf2.zprec[1], case.zsigmas), gio.maxdiff(acsf2.zprec[1], case.zsigmas)
+        z = acsf2.features(0)
+        zo = orc.zscore_apply(ref, *orc.zscore_stats(ds.offsets, ref, ds.weights))
+        assert np.allclose(z, zo, rtol=1e-9, atol=1e-10), gio.maxdiff(z, zo)
+    ctx.close()
