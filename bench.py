@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the Fortnet hot path on B200.
+
+metric : train atoms/s (ACSF featurisation + BPNN forward/backward + gradient reduction)
+step   : one pass of the hot path over one batch of synthetic structures:
+         fnetgpu_acsf_calculate (cell list resident, z-score fused) + fnetgpu_grad
+workload (N = 1): BASELINE.json configs[1] -- single-species Si bulk, 10k structures x 64 atoms,
+         32 ACSF features (Auto{RCut 4.0, NRadial 16, NAngular 16}), subnets [32,20,20,1] tanh,
+         energy (one global target) training with MSE.  N > 1: the same shard per GPU (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, all host
+threads; the Fortran binary cannot be built in this image) on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_atoms_per_s"
+UNIT = "atoms/s"
+
+
+def workload(name, n_struct, seed_shift=0):
+    import fortnet_b200 as fb
+    from fortnet_b200 import synthetic
+    if name == "c2":
+        ds = synthetic.si_bulk(n_struct=n_struct, seed=20260001 + seed_shift)
+        funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+        dims = [32, 20, 20, 1]
+        label = "C2 single-species Si bulk, 10k structures x 64 atoms, 32 ACSF (G2x16+G5x16, rc 4 A), subnets 32-20-20-1 tanh, MSE energy training"
+    elif name == "c3":
+        ds = synthetic.tio2(n_struct=n_struct, seed=20260002 + seed_shift)
+        funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
+        dims = [64, 32, 32, 32, 1]
+        label = "C3 two-species TiO2-like, 20k structures x 192 atoms, 64 species-resolved G2/G5 ACSF, subnets 64-32-32-32-1 tanh"
+    else:
+        raise SystemExit("unknown workload " + name)
+    assert len(funcs) == dims[0]
+    rng = np.random.default_rng(7)
+    n_species = len(ds.atomic_numbers)
+    import oracle.oracle as _o  # only for ntot(); not on any timed product path
+    ntot = _o.ntot(dims)
+    wb = rng.uniform(-0.5, 0.5, size=(n_species, ntot))
+    return ds, funcs, dims, wb, label
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(name, target_seconds=12.0, threads=None):
+    """Times the oracle (C restatement of the reference algorithm, `kind: port`) on a bounded
+    sample of the workload: ACSF once + one training-gradient pass per step."""
+    from oracle import oracle as orc
+    threads = threads or (os.cpu_count() or 1)
+    per_thread = 1
+    ds, funcs, dims, wb, _ = workload(name, max(threads * per_thread, 1))
+    fd = funcs.asdicts()
+
+    def one(dsx):
+        t0 = time.perf_counter()
+        vals = orc.acsf(dsx.offsets, dsx.coords, dsx.periodic, dsx.latvecs, dsx.atnum, fd, nthreads=threads)
+        t1 = time.perf_counter()
+        orc.grad(dsx.offsets, vals, dsx.globalsp, dims, "tanh", wb, "mse", dsx.weights, dsx.atomic_weights,
+                 dsx.gtargets, dsx.atargets, nthreads=threads)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    ta, tg = one(ds)                                  # calibration: one structure per thread
+    scale = max(1, int(target_seconds / max(ta + tg, 1e-3)))
+    scale = min(scale, 64)
+    ds2, _, _, _, _ = workload(name, threads * per_thread * scale)
+    ta, tg = one(ds2)
+    atoms = ds2.n_atoms
+    return {"value": atoms / (ta + tg), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d structures (%d atoms): oracle ACSF %.2f s + fwd/bwd %.3f s, %d OpenMP threads, "
+                      "reference block partition" % (ds2.n_struct, atoms, ta, tg, threads),
+            "acsf_atoms_per_s": atoms / ta, "train_iter_atoms_per_s": atoms / tg}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    threads = os.cpu_count() or 1
+    name = args.workload
+    # size one step to ~3 s
+    ds, funcs, dims, wb, label = workload(name, threads)
+    fd = funcs.asdicts()
+
+    def step(dsx):
+        vals = orc.acsf(dsx.offsets, dsx.coords, dsx.periodic, dsx.latvecs, dsx.atnum, fd, nthreads=threads)
+        orc.grad(dsx.offsets, vals, dsx.globalsp, dims, "tanh", wb, "mse", dsx.weights, dsx.atomic_weights,
+                 dsx.gtargets, dsx.atargets, nthreads=threads)
+
+    t0 = time.perf_counter(); step(ds); t1 = time.perf_counter()
+    scale = min(64, max(1, int(3.0 / max(t1 - t0, 1e-3))))
+    ds, _, _, _, _ = workload(name, threads * scale)
+    for _ in range(args.warmup):
+        step(ds)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(ds)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = ds.n_atoms / dt
+    sample = "%d structures (%d atoms) per step, %d OpenMP threads" % (ds.n_struct, ds.n_atoms, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C restatement of the reference algorithm (oracle/refcpu.c), not the Fortran binary: "
+                "no Fortran compiler / HDF5 / MPI in this image",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--structures", type=int, default=0, help="structures per GPU (default: 10000 c2 / 20000 c3)")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fortnet_b200 as fb
+    from fortnet_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_struct = args.structures or (10000 if args.workload == "c2" else 20000)
+    ds, funcs, dims, wb, label = workload(args.workload, n_struct, seed_shift=1000 * rank)
+    N = ds.n_atoms
+    F = len(funcs)
+
+    stream = torch.cuda.Stream()
+    ctx = fb.Context(device=local, precision=args.precision)
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        sharding.init_comm(ctx, dist)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)                      # first call: statistics of the training set (all ranks)
+    net = fb.Bpnn(ctx, dims, len(ds.atomic_numbers), "tanh")
+    net.set_params(wb)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step_resident():
+        acsf.calculate(0)
+        net.update_gradients(0, "mse", fetch=False)
+
+    coords_pinned = torch.from_numpy(ds.coords.copy()).pin_memory()
+    lat_pinned = torch.from_numpy(ds.latvecs.copy()).pin_memory()
+
+    def step_e2e():
+        ctx.update_coords(0, coords_pinned.numpy(), lat_pinned.numpy())
+        acsf.calculate(0)
+        return net.update_gradients(0, "mse", fetch=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_resident()
+        # ---------------- timed region: device-resident inputs ----------------
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        ctx.profile(True)
+        l0 = ctx.launch_count()
+        for k in range(args.steps):
+            flush.zero_()                                   # L2 flush, outside the event bracket
+            ev[k][0].record(stream)
+            step_resident()
+            ev[k][1].record(stream)
+        barrier()
+        launches = ctx.launch_count() - l0
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        clocks = sampler.stop() if rank == 0 else None
+        ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+        # ---------------- end to end: host buffers in, gradient + loss out ----------------
+        step_e2e()
+        barrier()
+        t_e2e = 0.0
+        for k in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dd, loss = step_e2e()
+            torch.cuda.synchronize()
+            t_e2e += time.perf_counter() - t0
+        barrier()
+        ms_e2e = t_e2e / args.steps * 1e3
+
+    tms = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tms.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tms.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        natoms = torch.tensor([float(N)], dtype=torch.float64, device="cuda"); dist.all_reduce(natoms)
+        ms, ms_e2e, launches, total_atoms = tmax[0].item(), tmax[1].item(), int(tsum[2].item()), natoms.item()
+    else:
+        total_atoms = float(N)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        a = prof.get("acsf", {"ms_total": float("nan"), "launches": 1})
+        acsf_ms = a["ms_total"] / max(a["launches"], 1)
+        sfeat = 8 if args.precision == 64 else 4
+        bytes_per_atom = 3 * 8 + 4 + sfeat * F                   # coords + species + features
+        alg_bytes = bytes_per_atom * N + 72 * ds.n_struct
+        achieved = alg_bytes / (acsf_ms * 1e-3) / 1e9
+        kshare = {k: v["ms_total"] / args.steps for k, v in prof.items()}
+        out = {
+            "metric": METRIC, "value": total_atoms / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
+            "data": "synthetic",
+            "config": {"workload": label, "atoms_per_gpu": N, "structures_per_gpu": ds.n_struct,
+                       "parallelism": "structure-sharded dp%d, one NCCL all-reduce of [ddSerial|loss] per step" % world,
+                       "l2": "flushed between steps (256 MiB memset outside the per-step event brackets); "
+                             "feature matrix %.0f MB > L2" % (N * F * sfeat / 1e6),
+                       "step": "fnetgpu_acsf_calculate (z-score fused, stats from warm-up) + fnetgpu_grad"},
+            "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(ds.coords.nbytes + ds.latvecs.nbytes + 2 * F * 8),
+                    "d2h_bytes_per_step": int((wb.size + 2) * 8 + 2 * 32),
+                    "path": "fnetgpu_coords_update(host pinned) -> cell list -> acsf_calculate -> grad -> ddSerial+loss on host (wall clock)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_acsf", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_atom": bytes_per_atom, "avg_launch_ms": acsf_ms, "peak_source": peak_src,
+                         "note": "FP64 angular ACSF is FP64-issue bound (SURVEY.md 8d); HBM fraction reported as the contract asks"},
+            "kernel_ms_per_step": kshare,
+            "loss": loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

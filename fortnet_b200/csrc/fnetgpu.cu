@@ -46,7 +46,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   if (device >= ndev) { g_err = "device index out of range"; return 1; }
   fnetgpu_ctx *ctx = new fnetgpu_ctx();
   ctx->device = device; ctx->precision = precision; ctx->deterministic = deterministic;
-  memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->klaunch, 0, sizeof(ctx->klaunch));
+  memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->klaunch, 0, sizeof(ctx->klaunch)); memset(ctx->kprof, 0, sizeof(ctx->kprof));
   memset(&ctx->acsf, 0, sizeof(ctx->acsf)); memset(&ctx->net, 0, sizeof(ctx->net));
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; delete ctx; return 1; }
   cudaDeviceProp prop;
@@ -85,6 +85,7 @@ extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
     if (d) d(ctx->comm);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  if (ctx->prof) { for (int i = 0; i < FNET_PROF_RING; i++) { cudaEventDestroy(ctx->prof[i].a); cudaEventDestroy(ctx->prof[i].b); } delete[] ctx->prof; }
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -109,17 +110,44 @@ extern "C" int fnetgpu_set_stream(fnetgpu_ctx *ctx, void *stream) {
 
 extern "C" long long fnetgpu_launch_count(const fnetgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// resolve the recorded event pairs into per-kernel totals
+static void profile_flush(fnetgpu_ctx *ctx) {
+  if (!ctx->prof || ctx->profUsed == 0) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < ctx->profUsed; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof[i].a, ctx->prof[i].b) == cudaSuccess) {
+      ctx->kms[ctx->prof[i].kernel] += ms;
+      ctx->kprof[ctx->prof[i].kernel]++;
+    }
+  }
+  ctx->profUsed = 0;
+}
+
 extern "C" int fnetgpu_profile(fnetgpu_ctx *ctx, int enable) {
   CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  if (enable && !ctx->prof) {
+    ctx->prof = new ProfEvent[FNET_PROF_RING];
+    for (int i = 0; i < FNET_PROF_RING; i++) { cudaEventCreate(&ctx->prof[i].a); cudaEventCreate(&ctx->prof[i].b); ctx->prof[i].kernel = 0; }
+  }
+  if (enable) {
+    ctx->profUsed = 0;
+    memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->kprof, 0, sizeof(ctx->kprof));
+  } else {
+    profile_flush(ctx);
+  }
   ctx->profiling = enable != 0;
-  if (enable) { memset(ctx->kms, 0, sizeof(ctx->kms)); memset(ctx->klaunch, 0, sizeof(ctx->klaunch)); }
   return 0;
 }
+// ms_total / launches: summed CUDA-event durations and number of timed launches of this kernel
+// since profiling was enabled
 extern "C" int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kid, double *ms, long long *launches) {
   CHECK_CTX(ctx);
   if (kid < 0 || kid >= K_NUM_KERNELS) FNET_FAIL(ctx, "kernel id out of range");
+  profile_flush(ctx);
   if (ms) *ms = ctx->kms[kid];
-  if (launches) *launches = ctx->klaunch[kid];
+  if (launches) *launches = ctx->kprof[kid];
   return 0;
 }
 
@@ -184,7 +212,7 @@ extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, c
   if (dev_upload(ctx, &s.d_perm, perm.data(), (size_t)N)) return 1;
   if (dev_upload(ctx, &s.d_dsw, dsw.data(), (size_t)nStruct)) return 1;
   if (dev_upload(ctx, &s.d_aw, aw.data(), (size_t)N)) return 1;
-  if (coords) { if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * N)) return 1; }
+  if (coords) { if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * N)) return 1; s.capCoords = (size_t)3 * N; }
   if (nG > 0) { if (!gTargets) FNET_FAIL(ctx, "gTargets missing"); if (dev_upload(ctx, &s.d_gt, gTargets, (size_t)nG * nStruct)) return 1; }
   if (nA > 0) { if (!aTargets) FNET_FAIL(ctx, "aTargets missing"); if (dev_upload(ctx, &s.d_at, aTargets, (size_t)nA * N)) return 1; }
   if (nExt > 0) { if (!ext) FNET_FAIL(ctx, "ext missing"); if (dev_upload(ctx, &s.d_ext, ext, (size_t)nExt * N)) return 1; }
@@ -197,10 +225,12 @@ extern "C" int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *c
   Slot &s = ctx->slots[slot];
   if (!s.used) FNET_FAIL(ctx, "coords_update: empty slot");
   cudaSetDevice(ctx->device);
-  if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * s.N)) return 1;
+  if (!coords) FNET_FAIL(ctx, "coords_update: coords missing");
+  if (dev_reserve(ctx, &s.d_coords, &s.capCoords, (size_t)3 * s.N)) return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (latvecs) s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
-  s.cellRc = -1.0; s.maxNeigh = -1; s.featValid = false;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  s.cellRc = -1.0; s.neighStale = true; s.featValid = false;   // maxNeigh stays as a capacity hint
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffer on return
   return 0;
 }
 
@@ -434,13 +464,15 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
     if (totalBins > 2000000000LL) FNET_FAIL(ctx, "cell list too large");
   }
   s.totalBins = (int)totalBins;
-  if (dev_upload(ctx, &s.d_sinfo, si.data(), si.size())) return 1;
-  if (dev_alloc(ctx, &s.d_fpos, (size_t)3 * s.N)) return 1;
-  if (dev_alloc(ctx, &s.d_cpos, (size_t)3 * s.N)) return 1;
-  if (dev_alloc(ctx, &s.d_atomCell, (size_t)s.N)) return 1;
-  if (dev_alloc(ctx, &s.d_cellAtoms, (size_t)s.N)) return 1;
-  if (dev_alloc(ctx, &s.d_cellStart, (size_t)s.totalBins + 1)) return 1;
-  if (dev_alloc(ctx, &s.d_cellCount, (size_t)s.totalBins)) return 1;
+  if (dev_reserve(ctx, &s.d_sinfo, &s.capSinfo, si.size())) return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s.d_sinfo, si.data(), si.size() * sizeof(StructInfo), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // si is a stack-lifetime host vector
+  if (dev_reserve(ctx, &s.d_fpos, &s.capFpos, (size_t)3 * s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_cpos, &s.capCpos, (size_t)3 * s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_atomCell, &s.capAtomCell, (size_t)s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_cellAtoms, &s.capCellAtoms, (size_t)s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_cellStart, &s.capCellStart, (size_t)s.totalBins + 1)) return 1;
+  if (dev_reserve(ctx, &s.d_cellCount, &s.capCellCount, (size_t)s.totalBins)) return 1;
   CUDA_TRY(ctx, cudaMemsetAsync(s.d_cellCount, 0, (size_t)s.totalBins * sizeof(int), ctx->stream));
   const int B = 256;
   LAUNCH(ctx, K_BIN_COUNT, (k_bin_count<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_coords, s.d_structOf, s.d_sinfo, s.d_fpos, s.d_atomCell, s.d_cellCount)));
@@ -449,14 +481,14 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
   LAUNCH(ctx, K_BIN_FILL, (k_bin_fill<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_atomCell, s.d_cellStart, s.d_cellCount, s.d_cellAtoms)));
   LAUNCH(ctx, K_BIN_SORT, (k_bin_sort<<<(s.totalBins + B - 1) / B, B, 0, ctx->stream>>>(s.totalBins, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos)));
   s.cellRc = rc;
-  s.maxNeigh = -1;
+  s.neighStale = true;
   return 0;
 }
 
 static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
-  if (s.maxNeigh >= 0) return 0;
+  if (s.maxNeigh >= 0 && !s.neighStale) return 0;
   const double rc = ctx->acsf.rcMax;
-  if (dev_alloc(ctx, &s.d_neighCount, (size_t)s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_neighCount, &s.capNeigh, (size_t)s.N)) return 1;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
   const int B = 128;
   const int grid = (int)(((long long)s.N * 32 + B - 1) / B);
@@ -468,6 +500,7 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
   unsigned long long tot;
   memcpy(&tot, &h[2], sizeof(tot));
   s.meanNeigh = (double)tot / (double)s.N;
+  s.neighStale = false;
   return 0;
 }
 
@@ -563,7 +596,9 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
   }
   if (F > 0) {
     if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
-    if (ensure_neigh_count(ctx, s)) return 1;
+    // neighbour-buffer capacity: counted once per slot; after a geometry update the previous
+    // maximum is reused as a hint and the kernel's overflow flag triggers a retry
+    if (s.maxNeigh < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
     int cap = std::max(32, (s.maxNeigh + 31) & ~31);
     const int WPB = 4;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -583,6 +618,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       if (h[1] == 0) break;
       if (attempt == 1) FNET_FAIL(ctx, "neighbour buffer overflow");
+      s.maxNeigh = h[1];
       cap = (h[1] + 31) & ~31;
     }
   } else {
@@ -922,7 +958,7 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   if (!ctx->acsfSet || T.F == 0) FNET_FAIL(ctx, "forces: need an ACSF configuration");
   if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "forces: not defined with external features (initprogram.F90:1543-1548)");
   if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
-  if (ensure_neigh_count(ctx, s)) return 1;
+  if (ensure_neigh_count(ctx, s)) return 1;   // exact count: the force kernel has no retry loop
   // (1) dE_k/dG for every atom and output: one reverse sweep per output
   if (!s.d_dEdG) { real *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
   const SmemNet sn = smem_net_layout(n);

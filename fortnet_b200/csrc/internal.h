@@ -114,6 +114,8 @@ struct Slot {
   StructInfo *d_sinfo = nullptr;
   int *d_atomCell = nullptr, *d_cellStart = nullptr, *d_cellCount = nullptr, *d_cellAtoms = nullptr;
   int totalBins = 0;
+  size_t capCoords = 0, capFpos = 0, capCpos = 0, capAtomCell = 0, capCellAtoms = 0, capCellStart = 0, capCellCount = 0, capSinfo = 0, capNeigh = 0;
+  bool neighStale = true;           // maxNeigh is only a hint for the current geometry
   double cellRc = -1.0;             // cutoff the cell list was built for
   double *d_dsw = nullptr;          // [nStruct] dataset weights as double
   double *d_aw = nullptr;           // [N]
@@ -149,7 +151,10 @@ struct fnetgpu_ctx {
   bool profiling = false;
   double kms[K_NUM_KERNELS];
   long long klaunch[K_NUM_KERNELS];
+  long long kprof[K_NUM_KERNELS];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  struct ProfEvent *prof = nullptr;   // ring of event pairs (allocated on first use)
+  int profUsed = 0;
   // ACSF config
   bool acsfSet = false;
   AcsfTables acsf;                  // device pointers inside
@@ -191,18 +196,23 @@ struct fnetgpu_ctx {
 #define FNET_FAIL(ctx, msg)                                                                  \
   do { (ctx)->err = (msg); return 1; } while (0)
 
-// Launch wrapper: counts launches and (in profile mode) brackets the kernel with events.
+// Launch wrapper: counts launches and (in profile mode) brackets the kernel with a pair of CUDA
+// events on the launching stream.  Events are resolved lazily (fnetgpu_profile_get), so profiling
+// adds no host synchronisation to the timed region.
+#define FNET_PROF_RING 8192
+struct ProfEvent { cudaEvent_t a, b; int kernel; };
+
 #define LAUNCH(ctx, kid, ...)                                                                \
   do {                                                                                       \
-    if ((ctx)->profiling) cudaEventRecord((ctx)->ev0, (ctx)->stream);                        \
+    ProfEvent *_pe = nullptr;                                                                \
+    if ((ctx)->profiling && (ctx)->profUsed < FNET_PROF_RING) {                              \
+      _pe = &(ctx)->prof[(ctx)->profUsed++];                                                 \
+      _pe->kernel = (kid);                                                                      \
+      cudaEventRecord(_pe->a, (ctx)->stream);                                                \
+    }                                                                                        \
     __VA_ARGS__;                                                                             \
     (ctx)->launches++; (ctx)->klaunch[kid]++;                                                \
-    if ((ctx)->profiling) {                                                                  \
-      cudaEventRecord((ctx)->ev1, (ctx)->stream);                                            \
-      cudaEventSynchronize((ctx)->ev1);                                                      \
-      float _ms = 0.f; cudaEventElapsedTime(&_ms, (ctx)->ev0, (ctx)->ev1);                   \
-      (ctx)->kms[kid] += _ms;                                                                \
-    }                                                                                        \
+    if (_pe) cudaEventRecord(_pe->b, (ctx)->stream);                                         \
     cudaError_t _le = cudaGetLastError();                                                    \
     if (_le != cudaSuccess) {                                                                \
       (ctx)->err = std::string("kernel launch failed (") + fnetgpu_kernel_name(kid) + "): " + \
@@ -216,6 +226,17 @@ static inline int dev_alloc(fnetgpu_ctx *ctx, T **p, size_t n) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   if (n == 0) n = 1;
   CUDA_TRY(ctx, cudaMalloc((void **)p, n * sizeof(T)));
+  return 0;
+}
+// grow-only allocation: keeps the buffer when it is already large enough (hot e2e path)
+template <typename T>
+static inline int dev_reserve(fnetgpu_ctx *ctx, T **p, size_t *cap, size_t n) {
+  if (*p && *cap >= n) return 0;
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  *cap = 0;
+  if (n == 0) n = 1;
+  CUDA_TRY(ctx, cudaMalloc((void **)p, n * sizeof(T)));
+  *cap = n;
   return 0;
 }
 template <typename T>
