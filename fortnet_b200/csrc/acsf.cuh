@@ -1,18 +1,28 @@
-// acsf.cuh -- ACSF values: one warp per central atom.
+// acsf.cuh -- ACSF values: one CTA per cell-list bin, one warp per central atom.
 //
 // Replaces TAcsf_calculate -> iGeoAcsf -> buildGFunctionNeighborlists + g1..g5
 // (lib_descriptors/acsf.F90:540-639, 797-866, 942-1066, 1287-1492).  The reference rebuilds
 // the neighbour list for every (atom, function) and evaluates acos->cos, pow, exp per pair
-// per function; here the list is gathered once per atom from the cell list into shared
-// memory, sorted by species code, and each angular pass shares the pair geometry between all
-// functions with equal (type, rc, eta, species pair): (1+lam*cos)^xi is evaluated for a whole
-// xi-ladder as exp(xi0*L) * exp(dxi*L)^m with L = log(1+lam*cos) (one log + two exp per
-// ladder per pair), unordered pairs are visited once (x2) where the reference walks ordered
-// pairs.  Parity traps kept: neighbour test d2 <= rc^2 (dynneighlist.F90:294), cos(theta)
-// denominator r_j r_k + 1e-13 (acsf.F90:1174), diagonal j==k pairs of identical lists
-// (acsf.F90:1420-1431,1480-1487), periodic images of the central atom belong to EVERY
-// species list (reduceGeometrySpecies keeps iAtom, acsf.F90:754-760), atom-id prefactors
-// q_i q_j in the cutoffs and q_j q_k in G4's third cutoff (acsf.F90:1201,1428-1430).
+// per function; here
+//   * the candidate records of the bin's neighbour cells are staged once per CTA in shared
+//     memory (cells.cuh), each warp filters them into its own neighbour list (sorted by
+//     species code when species-resolved functions exist);
+//   * radial G2 functions on an arithmetic rs-ladder with a common eta (the auto scheme,
+//     acsf.F90:320-336) are evaluated by the Gaussian recurrence
+//       g_{m+1}/g_m = exp(2 eta drs u) * exp(-eta drs^2 (2m+1)),  u = r - rs_first,
+//     i.e. two exp per (neighbour, 8 functions) instead of eight;
+//   * each angular pass shares the pair geometry between all functions with equal (type, rc,
+//     eta, species pair): (1+lam*cos)^xi is evaluated for a whole arithmetic xi-ladder as
+//     b^xi0 * (b^dxi)^m with b^dxi = exp(dxi*log b) (xi0 = 1 needs no exp; consecutive ladder
+//     slots continue the running product), unordered pairs are visited once (x2) where the
+//     reference walks ordered pairs;
+//   * the per-lane partial sums are combined by a transposing butterfly (M values in M-1+log
+//     shuffles instead of 5M).
+// Parity traps kept: neighbour test d2 <= rc^2 (dynneighlist.F90:294), cos(theta) denominator
+// r_j r_k + 1e-13 (acsf.F90:1174), diagonal j==k pairs of identical lists
+// (acsf.F90:1420-1431,1480-1487), periodic images of the central atom belong to EVERY species
+// list (reduceGeometrySpecies keeps iAtom, acsf.F90:754-760), atom-id prefactors q_i q_j in the
+// cutoffs and q_j q_k in G4's third cutoff (acsf.F90:1201,1428-1430).
 #pragma once
 #include "cells.cuh"
 
@@ -28,6 +38,10 @@ __host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F) {
   b = (b + 7) & ~(size_t)7;
   b += (size_t)((F + 1) & ~1) * sizeof(double);
   return (b + 15) & ~(size_t)15;
+}
+// CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates
+__host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC) {
+  return (size_t)capC * sizeof(CRec) + (size_t)(2 * FNET_MAX_NCELLS + 4) * sizeof(int);
 }
 
 __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap, int F) {
@@ -51,40 +65,46 @@ __device__ __forceinline__ int species_code(const AcsfTables &tab, int z) {
   return code;
 }
 
-// Gathers the neighbours of atom i (within rcMax) into the warp's shared memory, sorted by
-// species code [code 0 .. nCodes-1 | other | self-images]; returns n (or -needed on overflow).
-__device__ __forceinline__ int gather_neighbors(int i, const StructInfo &S, const AcsfTables &tab,
-                                                const int *__restrict__ atomCell,
-                                                const int *__restrict__ cellStart,
-                                                const int *__restrict__ cellAtoms,
-                                                const double *__restrict__ fpos,
-                                                const double *__restrict__ cpos,
-                                                const int *__restrict__ atnum, int cap, WarpSmem &w) {
+// Gathers the neighbours of the central atom `me` (within rcMax) into the warp's shared memory,
+// sorted by species code [code 0 .. nCodes-1 | other | self-images]; returns n (or -needed on
+// overflow).
+template <bool STAGED>
+__device__ __forceinline__ int gather_neighbors(const CRec &me, const StructInfo &S, const BinPos &bp,
+                                                const AcsfTables &tab, const int *__restrict__ cellStart,
+                                                const CRec *__restrict__ crec, const CRec *__restrict__ cand,
+                                                int nCand, int cap, WarpSmem &w) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const bool sorted = tab.nCodes > 0;
+  const double rc2 = tab.rcMax * tab.rcMax;
   // unsorted target = final arrays; sorted target = scratch aliased on (fcE, qv, r | rinv)
   double *gx = sorted ? w.fcE : w.dx, *gy = sorted ? w.qv : w.dy, *gz = sorted ? w.r : w.dz;
   int *gj = sorted ? (int *)w.rinv : w.idx;
+  int *gc = (int *)w.rinv + cap;          // species codes (sorted path only)
   int n = 0;
-  for_each_neighbor(i, S, atomCell, cellStart, cellAtoms, fpos, cpos, tab.rcMax * tab.rcMax,
-                    [&](bool ok, double dx, double dy, double dz, double, int j) {
-                      unsigned m = __ballot_sync(0xffffffffu, ok);
-                      int pos = n + __popc(m & lt);
-                      if (ok && pos < cap) { gx[pos] = dx; gy[pos] = dy; gz[pos] = dz; gj[pos] = j; }
-                      n += __popc(m);
-                    });
+  auto take = [&](bool valid, double x, double y, double z, int j, int zs) {
+    const double dx = x - me.x, dy = y - me.y, dz = z - me.z;
+    const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, j, zs, me.idx);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    const int pos = n + __popc(m & lt);
+    if (ok && pos < cap) {
+      gx[pos] = dx; gy[pos] = dy; gz[pos] = dz; gj[pos] = j;
+      if (sorted) gc[pos] = (j == me.idx) ? tab.nCodes + 1 : species_code(tab, zs & ~FNET_SHIFT_FLAG);
+    }
+    n += __popc(m);
+  };
+  if (STAGED) for_each_candidate_staged(cand, nCand, take);
+  else for_each_candidate_direct(S, bp, cellStart, crec, take);
   if (n > cap) return -n;
   __syncwarp();
   if (sorted) {
     const int nc = tab.nCodes + 2;  // + other + self
     int mycount = 0;
     for (int base = 0; base < n; base += 32) {
-      int t = base + lane;
-      int code = -1;
-      if (t < n) { int j = gj[t]; code = (j == i) ? tab.nCodes + 1 : species_code(tab, atnum[j]); }
+      const int t = base + lane;
+      const int code = (t < n) ? gc[t] : -1;
       for (int c = 0; c < nc; c++) {
-        unsigned m = __ballot_sync(0xffffffffu, code == c);
+        const unsigned m = __ballot_sync(0xffffffffu, code == c);
         if (lane == c) mycount += __popc(m);
       }
     }
@@ -94,14 +114,14 @@ __device__ __forceinline__ int gather_neighbors(int i, const StructInfo &S, cons
     int mybase = incl - mycount;
     if (lane <= nc) w.seg[lane] = (lane < nc) ? mybase : n;
     for (int base = 0; base < n; base += 32) {
-      int t = base + lane;
+      const int t = base + lane;
       int code = -1, j = -1;
       double x = 0, y = 0, z = 0;
-      if (t < n) { j = gj[t]; x = gx[t]; y = gy[t]; z = gz[t]; code = (j == i) ? tab.nCodes + 1 : species_code(tab, atnum[j]); }
+      if (t < n) { j = gj[t]; x = gx[t]; y = gy[t]; z = gz[t]; code = gc[t]; }
       int pos = -1;
       for (int c = 0; c < nc; c++) {
-        unsigned m = __ballot_sync(0xffffffffu, code == c);
-        int b = __shfl_sync(0xffffffffu, mybase, c);
+        const unsigned m = __ballot_sync(0xffffffffu, code == c);
+        const int b = __shfl_sync(0xffffffffu, mybase, c);
         if (code == c) pos = b + __popc(m & lt);
         if (lane == c) mybase += __popc(m);
       }
@@ -112,8 +132,8 @@ __device__ __forceinline__ int gather_neighbors(int i, const StructInfo &S, cons
     w.seg[0] = 0; w.seg[1] = n; w.seg[2] = n;  // [other | self] unused
   }
   for (int t = lane; t < n; t += 32) {
-    double d2 = w.dx[t] * w.dx[t] + w.dy[t] * w.dy[t] + w.dz[t] * w.dz[t];
-    double rr = sqrt(d2);                      // dynneighlist.F90:311
+    const double d2 = w.dx[t] * w.dx[t] + w.dy[t] * w.dy[t] + w.dz[t] * w.dz[t];
+    const double rr = sqrt(d2);                      // dynneighlist.F90:311
     w.r[t] = rr;
     w.rinv[t] = 1.0 / rr;
   }
@@ -139,175 +159,254 @@ __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) 
   return 0.5 * qq * (cospi(rr * invrc) + 1.0);   // acsf.F90:1201 (pi*rr/rcut)
 }
 
-// (1 + lam*c)^xi ladder start and ratio from L = log(1 + lam*c), with the pow(0,0)=1 /
-// pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
-__device__ __forceinline__ void ladder_init(double L, double xi0, double dxi, double &p, double &q) {
-  p = (xi0 == 0.0) ? 1.0 : exp(xi0 * L);
+// (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
+// pow(0,0)=1 / pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
+__device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q) {
+  p = (xi0 == 1.0) ? b : ((xi0 == 0.0) ? 1.0 : exp(xi0 * L));
   q = (dxi == 0.0) ? 1.0 : exp(dxi * L);
 }
 
-template <typename real>
-__global__ void __launch_bounds__(128)
-k_acsf(int N, const int *__restrict__ structOf, const StructInfo *__restrict__ sinfo,
-       const int *__restrict__ atomCell, const int *__restrict__ cellStart,
-       const int *__restrict__ cellAtoms, const double *__restrict__ fpos,
-       const double *__restrict__ cpos, const int *__restrict__ atnum, int nExt,
-       const double *__restrict__ ext, AcsfTables tab, int cap, real *__restrict__ feat, int nFeat,
-       const double *__restrict__ zprec, int nExtSel, const int *__restrict__ extIdx,
+// pair index -> (row j, column k) of the flattened pair walk.  same: upper triangle incl. the
+// diagonal of an n1 x n1 matrix (row j holds k = j..n1-1); else the full n1 x n2 rectangle.
+__device__ __forceinline__ void pair_decode(int p, int same, int n1, int n2, float invn2, int &j, int &k) {
+  if (same) {
+    const float fn = (float)(2 * n1 + 1);
+    j = (int)((fn - sqrtf(fmaxf(fn * fn - 8.0f * (float)p, 0.0f))) * 0.5f);
+    j = min(max(j, 0), n1 - 1);
+    int rs = j * n1 - ((j * (j - 1)) >> 1);
+    if (rs > p) { j--; rs = j * n1 - ((j * (j - 1)) >> 1); }
+    else if (rs + (n1 - j) <= p) { rs += n1 - j; j++; }
+    k = j + (p - rs);
+  } else {
+    j = (int)(((float)p + 0.5f) * invn2);
+    if (j * n2 > p) j--;
+    else if ((j + 1) * n2 <= p) j++;
+    k = p - j * n2;
+  }
+}
+
+// Transposing butterfly: every lane holds M partial values; on return the lane holds the sum
+// over all lanes that differ from it in the lane bits {stride, 2*stride, ..., 16} of the value
+// with index (lane / stride) % M.  M-1 + log2(32/(M*stride)) shuffles.
+template <int M>
+__device__ __forceinline__ double reduce_transpose(double (&v)[M], int lane, int stride) {
+#pragma unroll
+  for (int h = M / 2; h >= 1; h >>= 1) {
+    const int off = h * stride;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < h; k++) {
+      const double send = up ? v[k] : v[k + h];
+      const double keep = up ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  double r = v[0];
+  for (int off = M * stride; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// radial groups (acsf.F90:1287-1373): lanes = (neighbour sub-lane, 8-function chunk)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &tab, const WarpSmem &w, int nExt,
+                                              const double *__restrict__ ext) {
+  const int lane = threadIdx.x & 31;
+  for (int g = 0; g < tab.nRadialGroups; g++) {
+    const RadialGroup *__restrict__ G = &tab.rgroups[g];
+    const int type = G->type, atomId = G->atomId, fBeg = G->fBeg, fCnt = G->fCnt, nch = G->nChunksP2;
+    const double rc = G->rc;
+    const NbList l = make_list(tab, w, G->code, n);
+    const int nl = l.n0 + l.n1;
+    const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
+    const double invrc = 1.0 / rc;
+    const int per = 32 / nch;
+    const int mychunk = lane % nch, sub = lane / nch;
+    const int fbase = fBeg + mychunk * FNET_RCHUNK;
+    const int fcnt = min(max(fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
+    double acc[FNET_RCHUNK];
+#pragma unroll
+    for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
+    if (fcnt > 0) {
+      if (type == FNETGPU_G2 && G->ladder) {
+        const double eta = G->eta, drs = G->drs;
+        const double rsf = G->rs0 + (double)(mychunk * FNET_RCHUNK) * drs;
+        double kk[FNET_RCHUNK - 1];
+#pragma unroll
+        for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = G->kk[m];
+        for (int t = sub; t < nl; t += per) {
+          const int a = list_at(l, t);
+          const double rr = w.r[a];
+          if (rr > rc) continue;                       // cutoff1d: rr > rcut -> 0
+          const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[a] + atomId - 1] : 1.0;
+          const double fc = cutoff_fn(rr, qi * qj, invrc);
+          const double u = rr - rsf;
+          const double e0 = eta * u * u, a1 = 2.0 * eta * drs * u;
+          if (e0 < 600.0 && fabs(a1) * (FNET_RCHUNK - 1) < 600.0) {
+            double gv = exp(-e0) * fc;
+            const double A = exp(a1);
+            acc[0] += gv;
+#pragma unroll
+            for (int m = 0; m < FNET_RCHUNK - 1; m++) { gv *= A * kk[m]; acc[m + 1] += gv; }
+          } else {                                      // out of the recurrence's safe range
+#pragma unroll
+            for (int f = 0; f < FNET_RCHUNK; f++) { const double d = u - (double)f * drs; acc[f] += exp(-eta * d * d) * fc; }
+          }
+        }
+      } else {
+        for (int t = sub; t < nl; t += per) {
+          const int a = list_at(l, t);
+          const double rr = w.r[a];
+          if (rr > rc) continue;
+          const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[a] + atomId - 1] : 1.0;
+          const double fc = cutoff_fn(rr, qi * qj, invrc);
+          if (type == FNETGPU_G1) {
+#pragma unroll
+            for (int f = 0; f < FNET_RCHUNK; f++) acc[f] += fc;
+          } else if (type == FNETGPU_G2) {
+#pragma unroll
+            for (int f = 0; f < FNET_RCHUNK; f++)
+              if (f < fcnt) { const double d = rr - tab.rp2[fbase + f]; acc[f] += exp(-tab.rp1[fbase + f] * d * d) * fc; }
+          } else {
+#pragma unroll
+            for (int f = 0; f < FNET_RCHUNK; f++)
+              if (f < fcnt) acc[f] += cos(tab.rp1[fbase + f] * rr) * fc;
+          }
+        }
+      }
+    }
+    // sum over the sub-lanes: lane ends with function (lane / nch) % 8 of chunk lane % nch
+    const double v = reduce_transpose<FNET_RCHUNK>(acc, lane, nch);
+    const int f = (lane / nch) % FNET_RCHUNK;
+    if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[fbase + f]] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// one angular pass (acsf.F90:1377-1492) with up to NS ladder slots
+// ------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab, const AngularPass *__restrict__ P,
+                                             const WarpSmem &w, int nExt, const double *__restrict__ ext) {
+  const int lane = threadIdx.x & 31;
+  const int type = P->type, same = P->same, atomId = P->atomId;
+  const int nSlots = min(P->nSlots, NS);
+  const double rc = P->rc, eta = P->eta, invrc = 1.0 / rc;
+  const NbList l1 = make_list(tab, w, P->code1, n);
+  const NbList l2 = same ? l1 : make_list(tab, w, P->code2, n);
+  const int n1 = l1.n0 + l1.n1, n2 = l2.n0 + l2.n1;
+  const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
+  __syncwarp();
+  for (int t = lane; t < n; t += 32) {   // per-neighbour radial factor fc * exp(-eta r^2)
+    const double rr = w.r[t];
+    const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
+    w.qv[t] = qj;
+    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * exp(-eta * rr * rr);
+  }
+  __syncwarp();
+  double lam[NS], xi0[NS], dxi[NS];
+  bool on[NS], cont[NS];
+  double acc[NS * FNET_LADDER];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    on[s] = s < nSlots;
+    lam[s] = on[s] ? P->slot[s].lam : 0.0;
+    xi0[s] = on[s] ? P->slot[s].xi0 : 0.0;
+    dxi[s] = on[s] ? P->slot[s].dxi : 0.0;
+    cont[s] = on[s] && s > 0 && P->slot[s].cont != 0;
+#pragma unroll
+    for (int f = 0; f < FNET_LADDER; f++) acc[s * FNET_LADDER + f] = 0.0;
+  }
+  const int nPairs = same ? (n1 * (n1 + 1)) >> 1 : n1 * n2;
+  const float invn2 = n2 > 0 ? 1.0f / (float)n2 : 0.0f;
+  for (int p = lane; p < nPairs; p += 32) {
+    int j, k;
+    pair_decode(p, same, n1, n2, invn2, j, k);
+    const int a = list_at(l1, j), b = list_at(l2, k);
+    double base = w.fcE[a] * w.fcE[b];
+    if (same && a != b) base *= 2.0;
+    if (type == FNETGPU_G4 && base != 0.0) {
+      const double ex = w.dx[a] - w.dx[b], ey = w.dy[a] - w.dy[b], ez = w.dz[a] - w.dz[b];
+      const double djk2 = ex * ex + ey * ey + ez * ez;
+      const double djk = sqrt(djk2);
+      base = (djk > rc) ? 0.0 : base * exp(-eta * djk2) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
+    }
+    if (base != 0.0) {
+      const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
+      const double pr = w.rinv[a] * w.rinv[b];
+      const double c = dot * (pr * (1.0 - 1e-13 * pr));   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
+      double L = 0.0, bb = 0.0, pw = 0.0, q = 1.0;
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        if (on[s]) {
+          if (!cont[s]) {
+            if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = log(bb); }
+            ladder_init(bb, L, xi0[s], dxi[s], pw, q);
+            pw *= base;
+          }
+#pragma unroll
+          for (int f = 0; f < FNET_LADDER; f++) { acc[s * FNET_LADDER + f] += pw; pw *= q; }
+        }
+      }
+    }
+  }
+  const double v = reduce_transpose<NS * FNET_LADDER>(acc, lane, 1);
+  {
+    const int e = lane % (NS * FNET_LADDER);
+    const int s = e / FNET_LADDER, f = e % FNET_LADDER;
+    if (lane < NS * FNET_LADDER && s < nSlots && f < P->slot[s].count)
+      w.outv[P->slot[s].feat[f]] = v * P->slot[s].pref[f];
+  }
+}
+
+template <typename real, int NS, bool STAGED>
+__global__ void __launch_bounds__(128, (NS <= 2 ? 4 : 3))
+k_acsf(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restrict__ sinfo,
+       const int *__restrict__ cellStart, const CRec *__restrict__ crec, int nExt,
+       const double *__restrict__ ext, AcsfTables tab, int cap, int capC, real *__restrict__ feat,
+       int nFeat, const double *__restrict__ zprec, int nExtSel, const int *__restrict__ extIdx,
        int *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (i >= N) return;
-  WarpSmem w = carve_warp_smem(smem_raw + (size_t)wib * acsf_warp_smem_bytes(cap, tab.F), cap, tab.F);
-  const StructInfo &S = sinfo[structOf[i]];
-  int n = gather_neighbors(i, S, tab, atomCell, cellStart, cellAtoms, fpos, cpos, atnum, cap, w);
-  if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); return; }
-
-  // ---------------- radial groups (acsf.F90:1287-1373) ----------------
-  for (int g = 0; g < tab.nRadialGroups; g++) {
-    const RadialGroup G = tab.rgroups[g];
-    const NbList l = make_list(tab, w, G.code, n);
-    const int nl = l.n0 + l.n1;
-    const double qi = G.atomId > 0 ? ext[(size_t)nExt * i + G.atomId - 1] : 1.0;
-    const double invrc = 1.0 / G.rc;
-    const int nch = G.nChunksP2, per = 32 / nch;
-    const int mychunk = lane % nch, sub = lane / nch;
-    const int fbase = G.fBeg + mychunk * FNET_RCHUNK;
-    const int fcnt = min(max(G.fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
-    double p1[FNET_RCHUNK], p2[FNET_RCHUNK], acc[FNET_RCHUNK];
-#pragma unroll
-    for (int f = 0; f < FNET_RCHUNK; f++) {
-      acc[f] = 0.0;
-      p1[f] = f < fcnt ? tab.rp1[fbase + f] : 0.0;
-      p2[f] = f < fcnt ? tab.rp2[fbase + f] : 0.0;
-    }
-    if (fcnt > 0)
-      for (int t = sub; t < nl; t += per) {
-        const int a = list_at(l, t);
-        const double rr = w.r[a];
-        if (rr > G.rc) continue;                       // cutoff1d: rr > rcut -> 0
-        const double qj = G.atomId > 0 ? ext[(size_t)nExt * w.idx[a] + G.atomId - 1] : 1.0;
-        const double fc = cutoff_fn(rr, qi * qj, invrc);
-        if (G.type == FNETGPU_G1) {
-#pragma unroll
-          for (int f = 0; f < FNET_RCHUNK; f++) acc[f] += fc;
-        } else if (G.type == FNETGPU_G2) {
-#pragma unroll
-          for (int f = 0; f < FNET_RCHUNK; f++)
-            if (f < fcnt) { double d = rr - p2[f]; acc[f] += exp(-p1[f] * d * d) * fc; }
-        } else {
-#pragma unroll
-          for (int f = 0; f < FNET_RCHUNK; f++)
-            if (f < fcnt) acc[f] += cos(p1[f] * rr) * fc;
-        }
-      }
-#pragma unroll
-    for (int f = 0; f < FNET_RCHUNK; f++)
-      for (int o = 16; o >= nch; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
-    if (sub == 0) {
-#pragma unroll
-      for (int f = 0; f < FNET_RCHUNK; f++)
-        if (f < fcnt) w.outv[tab.rfeat[fbase + f]] = acc[f];
-    }
+  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int bin = blockIdx.x;
+  const int beg = cellStart[bin], end = cellStart[bin + 1];
+  const int per = (end - beg + nSplit - 1) / nSplit;
+  const int a0 = beg + blockIdx.y * per, a1 = min(end, a0 + per);
+  if (a0 >= a1) return;
+  const StructInfo &S = sinfo[binStruct[bin]];
+  const BinPos bp = bin_pos(S, bin);
+  CRec *cand = (CRec *)smem_raw;
+  int nCand = 0;
+  unsigned char *wbase = smem_raw;
+  if (STAGED) {
+    int *tabs = (int *)(smem_raw + (size_t)capC * sizeof(CRec));
+    nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
+    if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
+    wbase += acsf_cta_prefix_bytes(capC);
   }
-
-  // ---------------- angular passes (acsf.F90:1377-1492) ----------------
-  for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) {
-    const AngularPass *__restrict__ P = &tab.apasses[pi_];
-    const int type = P->type, same = P->same, atomId = P->atomId, nSlots = P->nSlots;
-    const double rc = P->rc, eta = P->eta, invrc = 1.0 / rc;
-    const NbList l1 = make_list(tab, w, P->code1, n);
-    const NbList l2 = same ? l1 : make_list(tab, w, P->code2, n);
-    const int n1 = l1.n0 + l1.n1, n2 = l2.n0 + l2.n1;
-    const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
+  WarpSmem w = carve_warp_smem(wbase + (size_t)wib * acsf_warp_smem_bytes(cap, tab.F), cap, tab.F);
+  for (int slot = a0 + wib; slot < a1; slot += nw) {
+    const CRec me = crec[slot];
+    const int i = me.idx;
+    const int n = gather_neighbors<STAGED>(me, S, bp, tab, cellStart, crec, cand, nCand, cap, w);
+    if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
+    radial_groups(i, n, tab, w, nExt, ext);
+    for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) angular_pass<NS>(i, n, tab, &tab.apasses[pi_], w, nExt, ext);
     __syncwarp();
-    for (int t = lane; t < n; t += 32) {   // per-neighbour radial factor fc * exp(-eta r^2)
-      const double rr = w.r[t];
-      const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
-      w.qv[t] = qj;
-      w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * exp(-eta * rr * rr);
+    // ---------------- coalesced feature write (+ z-score, + external features) ----------------
+    real *out = feat + (size_t)nFeat * i;
+    for (int a = lane; a < tab.F; a += 32) {
+      double v = w.outv[a];
+      if (zprec) {
+        const double sg = zprec[tab.F + a];
+        if (!(sg < 1e-08)) v = (v - zprec[a]) / sg;   // acsf.F90:505-507
+      }
+      out[a] = (real)v;
     }
+    for (int e = lane; e < nExtSel; e += 32) out[tab.F + e] = (real)ext[(size_t)nExt * i + extIdx[e]];
     __syncwarp();
-    double lam[FNET_SLOTS], xi0[FNET_SLOTS], dxi[FNET_SLOTS];
-    int cnt[FNET_SLOTS];
-    double acc[FNET_SLOTS][FNET_LADDER];
-#pragma unroll
-    for (int s = 0; s < FNET_SLOTS; s++) {
-      lam[s] = s < nSlots ? P->slot[s].lam : 0.0;
-      xi0[s] = s < nSlots ? P->slot[s].xi0 : 0.0;
-      dxi[s] = s < nSlots ? P->slot[s].dxi : 0.0;
-      cnt[s] = s < nSlots ? P->slot[s].count : 0;
-#pragma unroll
-      for (int f = 0; f < FNET_LADDER; f++) acc[s][f] = 0.0;
-    }
-    if (n1 > 0 && n2 > 0) {
-      // flattened pair walk: row j holds k = k0(j) .. k0(j)+len(j)-1
-      int j = 0, o = lane;
-      while (j < n1) {
-        int len = same ? n1 - j : n2;
-        while (o >= len) { o -= len; j++; if (j >= n1) break; len = same ? n1 - j : n2; }
-        if (j >= n1) break;
-        const int k = (same ? j : 0) + o;
-        const int a = list_at(l1, j), b = list_at(l2, k);
-        double base = w.fcE[a] * w.fcE[b];
-        if (same && a != b) base *= 2.0;
-        if (type == FNETGPU_G4 && base != 0.0) {
-          const double ex = w.dx[a] - w.dx[b], ey = w.dy[a] - w.dy[b], ez = w.dz[a] - w.dz[b];
-          const double djk2 = ex * ex + ey * ey + ez * ez;
-          const double djk = sqrt(djk2);
-          base = (djk > rc) ? 0.0 : base * exp(-eta * djk2) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
-        }
-        if (base != 0.0) {
-          const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
-          const double pr = w.rinv[a] * w.rinv[b];
-          const double c = dot * (pr * (1.0 - 1e-13 * pr));   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
-          double L = 0.0;
-#pragma unroll
-          for (int s = 0; s < FNET_SLOTS; s++) {
-            if (cnt[s] > 0) {
-              if (s == 0 || lam[s] != lam[s - 1]) L = log(fmax(1.0 + lam[s] * c, 0.0));
-              double p, q;
-              ladder_init(L, xi0[s], dxi[s], p, q);
-              p *= base;
-#pragma unroll
-              for (int f = 0; f < FNET_LADDER; f++) {
-                if (f < cnt[s]) acc[s][f] += p;
-                p *= q;
-              }
-            }
-          }
-        }
-        o += 32;
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < FNET_SLOTS; s++) {
-      if (cnt[s] > 0) {
-#pragma unroll
-        for (int f = 0; f < FNET_LADDER; f++) {
-          double v = acc[s][f];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0 && f < cnt[s]) w.outv[P->slot[s].feat[f]] = v * P->slot[s].pref[f];
-        }
-      }
-    }
   }
-  __syncwarp();
-
-  // ---------------- coalesced feature write (+ z-score, + external features) ----------------
-  real *out = feat + (size_t)nFeat * i;
-  for (int a = lane; a < tab.F; a += 32) {
-    double v = w.outv[a];
-    if (zprec) {
-      const double sg = zprec[tab.F + a];
-      if (!(sg < 1e-08)) v = (v - zprec[a]) / sg;   // acsf.F90:505-507
-    }
-    out[a] = (real)v;
-  }
-  for (int e = lane; e < nExtSel; e += 32) out[tab.F + e] = (real)ext[(size_t)nExt * i + extIdx[e]];
 }
 
 // external features only (no ACSF functions configured): features.F90:227-241

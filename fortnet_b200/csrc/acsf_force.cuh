@@ -30,27 +30,42 @@ __device__ __forceinline__ double dcutoff_fn(double rr, double qq, double rc, do
   return -0.5 * qq * (3.14159265358979323846 * invrc) * sinpi(rr * invrc);
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(128)
-k_acsf_force(int N, const int *__restrict__ structOf, const StructInfo *__restrict__ sinfo,
-             const int *__restrict__ atomCell, const int *__restrict__ cellStart,
-             const int *__restrict__ cellAtoms, const double *__restrict__ fpos,
-             const double *__restrict__ cpos, const int *__restrict__ atnum, int nExt,
-             const double *__restrict__ ext, AcsfTables tab, int cap, const double *__restrict__ dEdG,
+k_acsf_force(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restrict__ sinfo,
+             const int *__restrict__ cellStart, const CRec *__restrict__ crec, int nExt,
+             const double *__restrict__ ext, AcsfTables tab, int cap, int capC, const double *__restrict__ dEdG,
              int nOut, const double *__restrict__ zprec, double *__restrict__ forces,
              int *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * (blockDim.x >> 5) + wib;
-  const int kt = blockIdx.y;                        // target index
-  if (i >= N) return;
-  unsigned char *base = smem_raw + (size_t)wib * force_warp_smem_bytes(cap, tab.F);
+  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int kt = blockIdx.z;                        // target index
+  const int bin = blockIdx.x;
+  const int beg = cellStart[bin], end = cellStart[bin + 1];
+  const int per = (end - beg + nSplit - 1) / nSplit;
+  const int a0 = beg + blockIdx.y * per, a1 = min(end, a0 + per);
+  if (a0 >= a1) return;
+  const StructInfo &S = sinfo[binStruct[bin]];
+  const BinPos bp = bin_pos(S, bin);
+  CRec *cand = (CRec *)smem_raw;
+  int nCand = 0;
+  unsigned char *wbase = smem_raw;
+  if (STAGED) {
+    int *tabs = (int *)(smem_raw + (size_t)capC * sizeof(CRec));
+    nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
+    if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
+    wbase += acsf_cta_prefix_bytes(capC);
+  }
+  unsigned char *base = wbase + (size_t)wib * force_warp_smem_bytes(cap, tab.F);
   WarpSmem w = carve_warp_smem(base, cap, tab.F);
   double *extra = (double *)(base + acsf_warp_smem_bytes(cap, tab.F));
   double *dE = extra, *fx = extra + cap, *fy = extra + 2 * cap, *fz = extra + 3 * cap;
-  const StructInfo &S = sinfo[structOf[i]];
-  int n = gather_neighbors(i, S, tab, atomCell, cellStart, cellAtoms, fpos, cpos, atnum, cap, w);
-  if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); return; }
+  for (int slot = a0 + wib; slot < a1; slot += nw) {
+  const CRec me = crec[slot];
+  const int i = me.idx;
+  const int n = gather_neighbors<STAGED>(me, S, bp, tab, cellStart, crec, cand, nCand, cap, w);
+  if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
   for (int t = lane; t < n; t += 32) {
     const double ri = w.rinv[t];
     w.dx[t] *= ri; w.dy[t] *= ri; w.dz[t] *= ri;    // unit vectors (acsf.F90:1565)
@@ -170,7 +185,7 @@ k_acsf_force(int N, const int *__restrict__ structOf, const StructInfo *__restri
             if (cnt[s] > 0) {
               if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = log(bb); }
               double pm, q;
-              ladder_init(L, xi0[s] - 1.0, dxi[s], pm, q);     // b^(xi-1)
+              ladder_init(bb, L, xi0[s] - 1.0, dxi[s], pm, q);     // b^(xi-1)
 #pragma unroll
               for (int f = 0; f < FNET_LADDER; f++) {
                 S1 += c1[s][f] * pm;
@@ -219,4 +234,6 @@ k_acsf_force(int N, const int *__restrict__ structOf, const StructInfo *__restri
     double *ff = forces + (size_t)stride * i + 3 * kt;
     atomicAdd(ff, sx); atomicAdd(ff + 1, sy); atomicAdd(ff + 2, sz);
   }
+  __syncwarp();
+  }   // slot loop
 }

@@ -7,8 +7,22 @@
 // is the same), binned into nb[0] x nb[1] x nb[2] bins whose thickness is >= rc along each
 // reciprocal direction, sorted by (bin, atom index) -> deterministic order.  Clusters use
 // their bounding box without wrap-around.
+//
+// Layout: one 32-byte record per atom in CELL order (position, atom index, atomic number), so a
+// candidate costs two 16-byte loads.  The ACSF kernels run one CTA per bin: all atoms of a bin
+// share the same 27 (or (2D+1)^3) neighbour cells, so the candidate records are staged once per
+// CTA in shared memory (shift applied) and every warp filters them for its own central atom.
 #pragma once
 #include "internal.h"
+
+#define FNET_SHIFT_FLAG 0x40000000   // staged candidate is a periodic image (lattice shift != 0)
+#define FNET_MAX_NCELLS 128          // neighbour cells per bin the staged path can hold
+
+struct __align__(16) CRec {
+  double x, y, z;
+  int idx;          // atom index (dataset order)
+  int zs;           // atomic number (| FNET_SHIFT_FLAG in staged copies)
+};
 
 __device__ __forceinline__ int floor_div(int a, int b) {
   int q = a / b;
@@ -48,16 +62,19 @@ __global__ void k_bin_count(int N, const double *__restrict__ coords, const int 
   atomicAdd(&cellCount[cell], 1);
 }
 
-// single-block exclusive scan (runs once per geometry upload)
-__global__ void k_bin_scan(int n, const int *__restrict__ count, int *__restrict__ start) {
+// single-block exclusive scan (runs once per geometry upload); flags[4] = largest bin population
+__global__ void k_bin_scan(int n, const int *__restrict__ count, int *__restrict__ start, int *__restrict__ flags) {
   __shared__ int wsum[32];
   __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  __shared__ int smax;
+  if (threadIdx.x == 0) { carry = 0; smax = 0; }
   __syncthreads();
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int mymax = 0;
   for (int base = 0; base < n; base += blockDim.x) {
     int i = base + threadIdx.x;
     int v = (i < n) ? count[i] : 0;
+    mymax = max(mymax, v);
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -76,7 +93,9 @@ __global__ void k_bin_scan(int n, const int *__restrict__ count, int *__restrict
     if (threadIdx.x == blockDim.x - 1) carry = off + x;
     __syncthreads();
   }
-  if (threadIdx.x == 0) start[n] = carry;
+  atomicMax(&smax, mymax);
+  __syncthreads();
+  if (threadIdx.x == 0) { start[n] = carry; flags[4] = smax; }
 }
 
 __global__ void k_bin_fill(int N, const int *__restrict__ atomCell, const int *__restrict__ cellStart,
@@ -88,9 +107,10 @@ __global__ void k_bin_fill(int N, const int *__restrict__ atomCell, const int *_
   cellAtoms[slot] = i;
 }
 
-// one thread per bin: order the bin by atom index (deterministic), then gather positions
+// one thread per bin: order the bin by atom index (deterministic), then write the records
 __global__ void k_bin_sort(int nBins, const int *__restrict__ cellStart, int *__restrict__ cellAtoms,
-                           const double *__restrict__ fpos, double *__restrict__ cpos) {
+                           const double *__restrict__ fpos, const int *__restrict__ atnum,
+                           CRec *__restrict__ crec) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nBins) return;
   int b = cellStart[c], e = cellStart[c + 1];
@@ -102,99 +122,179 @@ __global__ void k_bin_sort(int nBins, const int *__restrict__ cellStart, int *__
   }
   for (int a = b; a < e; a++) {
     int j = cellAtoms[a];
-    cpos[3 * a] = fpos[3 * j]; cpos[3 * a + 1] = fpos[3 * j + 1]; cpos[3 * a + 2] = fpos[3 * j + 2];
+    CRec r;
+    r.x = fpos[3 * j]; r.y = fpos[3 * j + 1]; r.z = fpos[3 * j + 2];
+    r.idx = j; r.zs = atnum[j];
+    crec[a] = r;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-cooperative neighbour enumeration around atom i.  Calls visit(ok, dx, dy, dz, d2, j, selfImage)
-// with all 32 lanes converged; `ok` marks lanes that hold a neighbour within rc.
-// Lane l owns neighbour cell (cbase + l) and walks its atoms, so each step tests up to 32
-// candidates from different cells.
+// Neighbour cells of a bin.  The bin's (2D0+1)(2D1+1)(2D2+1) neighbour cells are numbered
+// c = 0..ncells-1; each maps to a global bin (wrapped for periodic cells) plus a lattice shift.
 // ------------------------------------------------------------------------------------------
-template <typename Visit>
-__device__ __forceinline__ void for_each_neighbor(int i, const StructInfo &S, const int *__restrict__ atomCell,
-                                                  const int *__restrict__ cellStart,
-                                                  const int *__restrict__ cellAtoms,
-                                                  const double *__restrict__ fpos,
-                                                  const double *__restrict__ cpos, double rc2, Visit visit) {
-  const int lane = threadIdx.x & 31;
-  const double rix = fpos[3 * i], riy = fpos[3 * i + 1], riz = fpos[3 * i + 2];
-  int cell = atomCell[i] - S.binBase;
-  const int b2 = cell % S.nb[2];
-  const int b1 = (cell / S.nb[2]) % S.nb[1];
-  const int b0 = cell / (S.nb[2] * S.nb[1]);
-  const int w0 = 2 * S.D[0] + 1, w1 = 2 * S.D[1] + 1, w2 = 2 * S.D[2] + 1;
-  const int ncells = w0 * w1 * w2;
-  for (int cbase = 0; cbase < ncells; cbase += 32) {
-    int c = cbase + lane;
-    bool valid = c < ncells;
-    int beg = 0, end = 0;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    bool zeroShift = true;
-    if (valid) {
-      int d2 = c % w2 - S.D[2];
-      int d1 = (c / w2) % w1 - S.D[1];
-      int d0 = c / (w2 * w1) - S.D[0];
-      int g0 = b0 + d0, g1 = b1 + d1, g2 = b2 + d2;
-      int s0 = 0, s1 = 0, s2 = 0;
-      if (S.periodic) {
-        s0 = floor_div(g0, S.nb[0]); g0 -= s0 * S.nb[0];
-        s1 = floor_div(g1, S.nb[1]); g1 -= s1 * S.nb[1];
-        s2 = floor_div(g2, S.nb[2]); g2 -= s2 * S.nb[2];
-      } else {
-        valid = g0 >= 0 && g0 < S.nb[0] && g1 >= 0 && g1 < S.nb[1] && g2 >= 0 && g2 < S.nb[2];
-      }
-      if (valid) {
-        int gc = S.binBase + (g0 * S.nb[1] + g1) * S.nb[2] + g2;
-        beg = cellStart[gc];
-        end = cellStart[gc + 1];
-        sx = s0 * S.lat[0] + s1 * S.lat[3] + s2 * S.lat[6];
-        sy = s0 * S.lat[1] + s1 * S.lat[4] + s2 * S.lat[7];
-        sz = s0 * S.lat[2] + s1 * S.lat[5] + s2 * S.lat[8];
-        zeroShift = (s0 == 0 && s1 == 0 && s2 == 0);
-      }
+struct BinPos { int b0, b1, b2, w0, w1, w2, ncells; };
+
+__device__ __forceinline__ BinPos bin_pos(const StructInfo &S, int bin) {
+  BinPos p;
+  const int cell = bin - S.binBase;
+  p.b2 = cell % S.nb[2];
+  p.b1 = (cell / S.nb[2]) % S.nb[1];
+  p.b0 = cell / (S.nb[2] * S.nb[1]);
+  p.w0 = 2 * S.D[0] + 1; p.w1 = 2 * S.D[1] + 1; p.w2 = 2 * S.D[2] + 1;
+  p.ncells = p.w0 * p.w1 * p.w2;
+  return p;
+}
+
+struct NCell { int beg, len, shifted; double sx, sy, sz; };
+
+__device__ __forceinline__ NCell neighbor_cell(const StructInfo &S, const BinPos &p, int c,
+                                               const int *__restrict__ cellStart) {
+  NCell nc;
+  nc.beg = 0; nc.len = 0; nc.shifted = 0; nc.sx = 0.0; nc.sy = 0.0; nc.sz = 0.0;
+  if (c >= p.ncells) return nc;
+  const int d2 = c % p.w2 - S.D[2];
+  const int d1 = (c / p.w2) % p.w1 - S.D[1];
+  const int d0 = c / (p.w2 * p.w1) - S.D[0];
+  int g0 = p.b0 + d0, g1 = p.b1 + d1, g2 = p.b2 + d2;
+  int s0 = 0, s1 = 0, s2 = 0;
+  if (S.periodic) {
+    s0 = floor_div(g0, S.nb[0]); g0 -= s0 * S.nb[0];
+    s1 = floor_div(g1, S.nb[1]); g1 -= s1 * S.nb[1];
+    s2 = floor_div(g2, S.nb[2]); g2 -= s2 * S.nb[2];
+  } else if (g0 < 0 || g0 >= S.nb[0] || g1 < 0 || g1 >= S.nb[1] || g2 < 0 || g2 >= S.nb[2]) {
+    return nc;
+  }
+  const int gc = S.binBase + (g0 * S.nb[1] + g1) * S.nb[2] + g2;
+  nc.beg = cellStart[gc];
+  nc.len = cellStart[gc + 1] - nc.beg;
+  nc.sx = s0 * S.lat[0] + s1 * S.lat[3] + s2 * S.lat[6];
+  nc.sy = s0 * S.lat[1] + s1 * S.lat[4] + s2 * S.lat[7];
+  nc.sz = s0 * S.lat[2] + s1 * S.lat[5] + s2 * S.lat[8];
+  nc.shifted = (s0 != 0 || s1 != 0 || s2 != 0) ? 1 : 0;
+  return nc;
+}
+
+// CTA-cooperative staging of all candidate records of a bin's neighbour cells (shift applied).
+// Warp w copies cells w, w+nWarps, ...; returns the candidate count (or -needed on overflow, or
+// -1 when the bin has more than FNET_MAX_NCELLS neighbour cells).  tabs: 2*FNET_MAX_NCELLS+1 ints.
+__device__ __forceinline__ int stage_candidates(const StructInfo &S, const BinPos &p,
+                                                const int *__restrict__ cellStart,
+                                                const CRec *__restrict__ crec, CRec *__restrict__ cand,
+                                                int capC, int *__restrict__ tabs) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int *clen = tabs, *cpre = tabs + FNET_MAX_NCELLS;
+  if (p.ncells > FNET_MAX_NCELLS) return -1;
+  for (int c = threadIdx.x; c < FNET_MAX_NCELLS; c += blockDim.x) {
+    int len = 0;
+    if (c < p.ncells) { NCell nc = neighbor_cell(S, p, c, cellStart); len = nc.len; }
+    clen[c] = len;
+  }
+  __syncthreads();
+  if (wib == 0) {   // exclusive scan over FNET_MAX_NCELLS = 4 x 32 entries
+    int carry = 0;
+#pragma unroll
+    for (int q = 0; q < FNET_MAX_NCELLS / 32; q++) {
+      const int v = clen[q * 32 + lane];
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      cpre[q * 32 + lane] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    int len = end - beg;
-    int maxlen = len;
+    if (lane == 0) cpre[FNET_MAX_NCELLS] = carry;
+  }
+  __syncthreads();
+  const int total = cpre[FNET_MAX_NCELLS];
+  if (total > capC) return -total;
+  for (int c = wib; c < p.ncells; c += nw) {
+    const int len = clen[c];
+    if (len == 0) continue;
+    const NCell nc = neighbor_cell(S, p, c, cellStart);
+    const int dst = cpre[c];
+    for (int t = lane; t < len; t += 32) {
+      CRec r = crec[nc.beg + t];
+      r.x += nc.sx; r.y += nc.sy; r.z += nc.sz;
+      if (nc.shifted) r.zs |= FNET_SHIFT_FLAG;
+      cand[dst + t] = r;
+    }
+  }
+  __syncthreads();
+  return total;
+}
+
+// Warp-cooperative enumeration of the candidates around a central atom.  visit(valid, x, y, z,
+// idx, zs) is called with all 32 lanes converged; the candidate position already contains the
+// lattice shift and zs carries FNET_SHIFT_FLAG for periodic images.
+template <typename Visit>
+__device__ __forceinline__ void for_each_candidate_staged(const CRec *__restrict__ cand, int total, Visit visit) {
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < total;
+    CRec r;
+    r.x = 0.0; r.y = 0.0; r.z = 0.0; r.idx = -1; r.zs = 0;
+    if (valid) r = cand[t];
+    visit(valid, r.x, r.y, r.z, r.idx, r.zs);
+  }
+}
+
+// direct variant (no staging): lane l owns neighbour cell (cbase + l) and walks its records
+template <typename Visit>
+__device__ __forceinline__ void for_each_candidate_direct(const StructInfo &S, const BinPos &p,
+                                                          const int *__restrict__ cellStart,
+                                                          const CRec *__restrict__ crec, Visit visit) {
+  const int lane = threadIdx.x & 31;
+  for (int cbase = 0; cbase < p.ncells; cbase += 32) {
+    const NCell nc = neighbor_cell(S, p, cbase + lane, cellStart);
+    int maxlen = nc.len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
     for (int t = 0; t < maxlen; t++) {
-      bool ok = false;
-      double dx = 0, dy = 0, dz = 0, d2 = 0;
-      int j = -1;
-      if (t < len) {
-        int slot = beg + t;
-        j = cellAtoms[slot];
-        dx = (cpos[3 * slot] + sx) - rix;
-        dy = (cpos[3 * slot + 1] + sy) - riy;
-        dz = (cpos[3 * slot + 2] + sz) - riz;
-        d2 = dx * dx + dy * dy + dz * dz;
-        ok = (d2 <= rc2) && !(j == i && zeroShift);   // dynneighlist.F90:271-276,294
+      const bool valid = t < nc.len;
+      CRec r;
+      r.x = 0.0; r.y = 0.0; r.z = 0.0; r.idx = -1; r.zs = 0;
+      if (valid) {
+        r = crec[nc.beg + t];
+        r.x += nc.sx; r.y += nc.sy; r.z += nc.sz;
+        if (nc.shifted) r.zs |= FNET_SHIFT_FLAG;
       }
-      visit(ok, dx, dy, dz, d2, j);
+      visit(valid, r.x, r.y, r.z, r.idx, r.zs);
     }
   }
 }
 
-// neighbour count per atom (one warp per atom) -> sizes the shared-memory neighbour buffers
-__global__ void k_neigh_count(int N, const int *__restrict__ structOf, const StructInfo *__restrict__ sinfo,
-                              const int *__restrict__ atomCell, const int *__restrict__ cellStart,
-                              const int *__restrict__ cellAtoms, const double *__restrict__ fpos,
-                              const double *__restrict__ cpos, double rc2, int *__restrict__ neighCount,
-                              int *__restrict__ flags /* [0]=max, [1..2]=sum lo/hi */) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const StructInfo &S = sinfo[structOf[warp]];
-  int n = 0;
-  for_each_neighbor(warp, S, atomCell, cellStart, cellAtoms, fpos, cpos, rc2,
-                    [&](bool ok, double, double, double, double, int) {
-                      n += __popc(__ballot_sync(0xffffffffu, ok));
-                    });
+// neighbour test of the reference: d2 <= rc2, the central atom itself excluded in the central
+// cell only (dynneighlist.F90:271-276,294)
+__device__ __forceinline__ bool is_neighbor(bool valid, double d2, double rc2, int j, int zs, int i) {
+  return valid && (d2 <= rc2) && !(j == i && !(zs & FNET_SHIFT_FLAG));
+}
+
+// statistics that size the shared-memory buffers (one warp per atom, cell order):
+// flags[0] = max neighbours per atom, flags[2..3] = sum of neighbours (64 bit),
+// flags[5] = max candidates per bin, flags[6] = max neighbour cells per bin
+__global__ void k_neigh_count(int N, const int *__restrict__ binOfSlot_unused, const int *__restrict__ binStruct,
+                              const StructInfo *__restrict__ sinfo, const int *__restrict__ atomCell,
+                              const int *__restrict__ cellStart, const CRec *__restrict__ crec,
+                              double rc2, int *__restrict__ flags) {
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= N) return;
+  const CRec me = crec[slot];
+  const int bin = atomCell[me.idx];
+  const StructInfo &S = sinfo[binStruct[bin]];
+  const BinPos p = bin_pos(S, bin);
+  int n = 0, ncand = 0;
+  for_each_candidate_direct(S, p, cellStart, crec, [&](bool valid, double x, double y, double z, int j, int zs) {
+    const double dx = x - me.x, dy = y - me.y, dz = z - me.z;
+    const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, j, zs, me.idx);
+    n += __popc(__ballot_sync(0xffffffffu, ok));
+    ncand += __popc(__ballot_sync(0xffffffffu, valid));
+  });
   if (lane == 0) {
-    neighCount[warp] = n;
     atomicMax(&flags[0], n);
     atomicAdd((unsigned long long *)(flags + 2), (unsigned long long)n);
+    atomicMax(&flags[5], ncand);
+    atomicMax(&flags[6], p.ncells);
   }
 }

@@ -54,17 +54,17 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   ctx->nSM = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "stream creation failed"; delete ctx; return 1; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-  cudaMalloc((void **)&ctx->d_flags, 8 * sizeof(int));
-  cudaMemset(ctx->d_flags, 0, 8 * sizeof(int));
+  cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
+  cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
   *out = ctx;
   return 0;
 }
 
 static void free_slot(Slot &s) {
   cudaFree(s.d_offsets); cudaFree(s.d_structOf); cudaFree(s.d_atnum); cudaFree(s.d_sp); cudaFree(s.d_periodic);
-  cudaFree(s.d_coords); cudaFree(s.d_fpos); cudaFree(s.d_cpos); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
+  cudaFree(s.d_coords); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
-  cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat); cudaFree(s.d_neighCount);
+  cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
   cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
   cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
   s = Slot();
@@ -247,7 +247,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   AcsfTables &T = ctx->acsf;
   memset(&T, 0, sizeof(T));
   T.F = F;
-  ctx->h_rgroups.clear(); ctx->h_apasses.clear();
+  ctx->h_rgroups.clear(); ctx->h_apasses.clear(); ctx->maxSlots = 1;
   std::vector<int> rfeat; std::vector<double> rp1, rp2;
   // species codes
   std::vector<int> codes;
@@ -290,27 +290,63 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   T.nCodes = (int)codes.size();
   for (size_t c = 0; c < codes.size(); c++) T.zcodes[c] = codes[c];
   T.rcMax = rcMax; T.anyAtomId = anyAtomId;
-  // radial groups (<= 32 chunks of FNET_RCHUNK functions each)
-  for (size_t g = 0; g < rkeys.size(); g++) {
-    const std::vector<int> &m = rmembers[g];
-    for (size_t beg = 0; beg < m.size(); beg += 32 * FNET_RCHUNK) {
-      size_t cnt = std::min(m.size() - beg, (size_t)32 * FNET_RCHUNK);
-      RadialGroup G;
-      G.type = std::get<0>(rkeys[g]); G.rc = std::get<1>(rkeys[g]); G.atomId = std::get<2>(rkeys[g]);
-      G.code = std::get<3>(rkeys[g]);
-      G.fBeg = (int)rfeat.size(); G.fCnt = (int)cnt;
-      int nch = ((int)cnt + FNET_RCHUNK - 1) / FNET_RCHUNK, p2 = 1;
-      while (p2 < nch) p2 <<= 1;
-      G.nChunksP2 = p2;
-      for (size_t q = 0; q < cnt; q++) {
-        int a = m[beg + q];
-        rfeat.push_back(a);
-        if (G.type == FNETGPU_G2) { rp1.push_back(eta[a]); rp2.push_back(rs[a]); }
-        else if (G.type == FNETGPU_G3) { rp1.push_back(kappa[a]); rp2.push_back(0.0); }
-        else { rp1.push_back(0.0); rp2.push_back(0.0); }
-      }
-      ctx->h_rgroups.push_back(G);
+  // radial groups: <= 4 chunks of FNET_RCHUNK functions each.  G2 members that form an arithmetic
+  // rs-ladder with one eta (auto scheme, acsf.F90:320-336) become ladder groups evaluated by the
+  // Gaussian recurrence (acsf.cuh); everything else goes into generic groups.
+  const size_t RG_MAX = 4 * FNET_RCHUNK;
+  auto emit_group = [&](const RKey &key, const std::vector<int> &m, size_t beg, size_t cnt, bool lad) {
+    RadialGroup G; memset(&G, 0, sizeof(G));
+    G.type = std::get<0>(key); G.rc = std::get<1>(key); G.atomId = std::get<2>(key); G.code = std::get<3>(key);
+    G.fBeg = (int)rfeat.size(); G.fCnt = (int)cnt;
+    int nch = ((int)cnt + FNET_RCHUNK - 1) / FNET_RCHUNK, p2 = 1;
+    while (p2 < nch) p2 <<= 1;
+    G.nChunksP2 = p2;
+    if (lad) {
+      const double d = rs[m[beg + 1]] - rs[m[beg]];
+      G.ladder = 1; G.eta = eta[m[beg]]; G.rs0 = rs[m[beg]]; G.drs = d;
+      for (int q = 0; q < FNET_RCHUNK - 1; q++) G.kk[q] = exp(-G.eta * d * d * (2.0 * q + 1.0));
     }
+    for (size_t q = 0; q < cnt; q++) {
+      int a = m[beg + q];
+      rfeat.push_back(a);
+      if (G.type == FNETGPU_G2) { rp1.push_back(eta[a]); rp2.push_back(rs[a]); }
+      else if (G.type == FNETGPU_G3) { rp1.push_back(kappa[a]); rp2.push_back(0.0); }
+      else { rp1.push_back(0.0); rp2.push_back(0.0); }
+    }
+    ctx->h_rgroups.push_back(G);
+  };
+  for (size_t g = 0; g < rkeys.size(); g++) {
+    std::vector<int> m = rmembers[g], rest;
+    if (std::get<0>(rkeys[g]) == FNETGPU_G2) {
+      std::stable_sort(m.begin(), m.end(), [&](int a, int b) { return eta[a] != eta[b] ? eta[a] < eta[b] : rs[a] < rs[b]; });
+      size_t beg = 0;
+      while (beg < m.size()) {
+        size_t run = 1;
+        while (beg + run < m.size() && eta[m[beg + run]] == eta[m[beg]]) run++;
+        bool lad = run >= 3;
+        const double r0 = rs[m[beg]], d = lad ? rs[m[beg + 1]] - r0 : 0.0;
+        lad = lad && d > 0.0;
+        for (size_t q = 0; q < run && lad; q++) {
+          const double expect = r0 + (double)q * d, v = rs[m[beg + q]];
+          if (fabs(v - expect) > 8.0 * 2.220446049250313e-16 * std::max(fabs(v), fabs(d))) lad = false;
+        }
+        if (lad) {
+          // chunks restart the recurrence from a direct exp, so groups may be cut anywhere
+          for (size_t b2 = 0; b2 < run; b2 += RG_MAX) {
+            size_t cnt = std::min(run - b2, RG_MAX);
+            if (cnt >= 2) emit_group(rkeys[g], m, beg + b2, cnt, true);
+            else rest.push_back(m[beg + b2]);
+          }
+        } else {
+          for (size_t q = 0; q < run; q++) rest.push_back(m[beg + q]);
+        }
+        beg += run;
+      }
+    } else {
+      rest = m;
+    }
+    for (size_t beg = 0; beg < rest.size(); beg += RG_MAX)
+      emit_group(rkeys[g], rest, beg, std::min(rest.size() - beg, RG_MAX), false);
   }
   // angular passes: per key, split by lambda, sort by xi, cut into arithmetic ladders
   for (size_t g = 0; g < akeys.size(); g++) {
@@ -347,7 +383,20 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       P.atomId = std::get<3>(akeys[g]); P.code1 = std::get<4>(akeys[g]); P.code2 = std::get<5>(akeys[g]);
       P.same = (P.code1 == P.code2) ? 1 : 0;   // unresolved (-1,-1) or Z1 == Z2 (acsf.F90:1573)
       P.nSlots = (int)std::min(slots.size() - b, (size_t)FNET_SLOTS);
-      for (int q = 0; q < P.nSlots; q++) P.slot[q] = slots[b + q];
+      for (int q = 0; q < P.nSlots; q++) {
+        P.slot[q] = slots[b + q];
+        P.slot[q].cont = 0;
+        if (q > 0) {   // continues the running product of the previous slot (acsf.cuh angular_pass)
+          const LadderSlot &pv = P.slot[q - 1];
+          const LadderSlot &cu = P.slot[q];
+          const double expect = pv.xi0 + FNET_LADDER * pv.dxi;
+          if (pv.count == FNET_LADDER && pv.dxi != 0.0 && cu.lam == pv.lam &&
+              fabs(cu.xi0 - expect) <= 1e-12 * std::max(1.0, fabs(expect)) &&
+              (cu.count == 1 || fabs(cu.dxi - pv.dxi) <= 1e-12 * std::max(1.0, fabs(pv.dxi))))
+            P.slot[q].cont = 1;
+        }
+      }
+      ctx->maxSlots = std::max(ctx->maxSlots, P.nSlots);
       ctx->h_apasses.push_back(P);
     }
   }
@@ -363,7 +412,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   if (dev_alloc(ctx, &ctx->d_zprec, (size_t)2 * std::max(F, 1))) return 1;
   ctx->haveZ = false;
   ctx->acsfSet = true;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; }
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; ctx->slots[i].maxCand = -1; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -421,7 +470,9 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
   }
   (void)h_coords_or_null;
   std::vector<StructInfo> si(s.nStruct);
+  std::vector<int> binStruct;
   long long totalBins = 0;
+  s.maxCells = 1;
   for (int st = 0; st < s.nStruct; st++) {
     StructInfo &S = si[st];
     memset(&S, 0, sizeof(S));
@@ -462,13 +513,17 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
     S.binBase = (int)totalBins;
     totalBins += (long long)S.nb[0] * S.nb[1] * S.nb[2];
     if (totalBins > 2000000000LL) FNET_FAIL(ctx, "cell list too large");
+    binStruct.resize((size_t)totalBins, st);
+    s.maxCells = std::max(s.maxCells, (2 * S.D[0] + 1) * (2 * S.D[1] + 1) * (2 * S.D[2] + 1));
   }
   s.totalBins = (int)totalBins;
   if (dev_reserve(ctx, &s.d_sinfo, &s.capSinfo, si.size())) return 1;
   CUDA_TRY(ctx, cudaMemcpyAsync(s.d_sinfo, si.data(), si.size() * sizeof(StructInfo), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // si is a stack-lifetime host vector
+  if (dev_reserve(ctx, &s.d_binStruct, &s.capBinStruct, binStruct.size())) return 1;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s.d_binStruct, binStruct.data(), binStruct.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // si / binStruct are stack-lifetime host vectors
   if (dev_reserve(ctx, &s.d_fpos, &s.capFpos, (size_t)3 * s.N)) return 1;
-  if (dev_reserve(ctx, &s.d_cpos, &s.capCpos, (size_t)3 * s.N)) return 1;
+  if (dev_reserve(ctx, &s.d_crec, &s.capCrec, (size_t)s.N)) return 1;
   if (dev_reserve(ctx, &s.d_atomCell, &s.capAtomCell, (size_t)s.N)) return 1;
   if (dev_reserve(ctx, &s.d_cellAtoms, &s.capCellAtoms, (size_t)s.N)) return 1;
   if (dev_reserve(ctx, &s.d_cellStart, &s.capCellStart, (size_t)s.totalBins + 1)) return 1;
@@ -476,10 +531,10 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
   CUDA_TRY(ctx, cudaMemsetAsync(s.d_cellCount, 0, (size_t)s.totalBins * sizeof(int), ctx->stream));
   const int B = 256;
   LAUNCH(ctx, K_BIN_COUNT, (k_bin_count<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_coords, s.d_structOf, s.d_sinfo, s.d_fpos, s.d_atomCell, s.d_cellCount)));
-  LAUNCH(ctx, K_BIN_SCAN, (k_bin_scan<<<1, 1024, 0, ctx->stream>>>(s.totalBins, s.d_cellCount, s.d_cellStart)));
+  LAUNCH(ctx, K_BIN_SCAN, (k_bin_scan<<<1, 1024, 0, ctx->stream>>>(s.totalBins, s.d_cellCount, s.d_cellStart, ctx->d_flags + 8)));
   CUDA_TRY(ctx, cudaMemsetAsync(s.d_cellCount, 0, (size_t)s.totalBins * sizeof(int), ctx->stream));
   LAUNCH(ctx, K_BIN_FILL, (k_bin_fill<<<(s.N + B - 1) / B, B, 0, ctx->stream>>>(s.N, s.d_atomCell, s.d_cellStart, s.d_cellCount, s.d_cellAtoms)));
-  LAUNCH(ctx, K_BIN_SORT, (k_bin_sort<<<(s.totalBins + B - 1) / B, B, 0, ctx->stream>>>(s.totalBins, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos)));
+  LAUNCH(ctx, K_BIN_SORT, (k_bin_sort<<<(s.totalBins + B - 1) / B, B, 0, ctx->stream>>>(s.totalBins, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_atnum, s.d_crec)));
   s.cellRc = rc;
   s.neighStale = true;
   return 0;
@@ -488,19 +543,43 @@ static int ensure_cells(fnetgpu_ctx *ctx, Slot &s, double rc, const double *h_co
 static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
   if (s.maxNeigh >= 0 && !s.neighStale) return 0;
   const double rc = ctx->acsf.rcMax;
-  if (dev_reserve(ctx, &s.d_neighCount, &s.capNeigh, (size_t)s.N)) return 1;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
   const int B = 128;
   const int grid = (int)(((long long)s.N * 32 + B - 1) / B);
-  LAUNCH(ctx, K_NEIGH_COUNT, (k_neigh_count<<<grid, B, 0, ctx->stream>>>(s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos, rc * rc, s.d_neighCount, ctx->d_flags)));
-  int h[8];
+  LAUNCH(ctx, K_NEIGH_COUNT, (k_neigh_count<<<grid, B, 0, ctx->stream>>>(s.N, nullptr, s.d_binStruct, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_crec, rc * rc, ctx->d_flags)));
+  int h[16];
   CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   s.maxNeigh = h[0];
   unsigned long long tot;
   memcpy(&tot, &h[2], sizeof(tot));
   s.meanNeigh = (double)tot / (double)s.N;
+  s.maxCand = h[5];
+  s.maxBinPop = h[8 + 4];
   s.neighStale = false;
+  return 0;
+}
+
+// launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; size_t smem; };
+static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
+  L.cap = std::max(32, (s.maxNeigh + 31) & ~31);
+  L.staged = s.maxCells <= FNET_MAX_NCELLS && s.maxCand >= 0 && s.maxCand <= 1536;
+  L.capC = L.staged ? ((s.maxCand + s.maxCand / 8 + 31) & ~31) : 0;
+  L.wpb = 4;
+  const size_t prefix = L.staged ? acsf_cta_prefix_bytes(L.capC) : 0;
+  L.smem = prefix + warpBytes * L.wpb;
+  while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
+  if (L.smem > 220 * 1024 && L.staged) { L.staged = false; L.capC = 0; L.wpb = 4; L.smem = warpBytes * L.wpb;
+    while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = warpBytes * L.wpb; } }
+  if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
+  // atoms of a bin are split over blockIdx.y so that a CTA sees ~4 rounds of its warps and the
+  // grid still fills the GPU when a structure has few, crowded bins
+  const int pop = std::max(1, s.maxBinPop);
+  int nSplit = (pop + 4 * L.wpb - 1) / (4 * L.wpb);
+  const long long want = 8LL * ctx->nSM;
+  if ((long long)s.totalBins * nSplit < want) nSplit = (int)std::min<long long>((pop + L.wpb - 1) / L.wpb, (want + s.totalBins - 1) / s.totalBins);
+  L.nSplit = std::max(1, std::min(nSplit, 65535));
   return 0;
 }
 
@@ -596,30 +675,35 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
   }
   if (F > 0) {
     if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
-    // neighbour-buffer capacity: counted once per slot; after a geometry update the previous
-    // maximum is reused as a hint and the kernel's overflow flag triggers a retry
-    if (s.maxNeigh < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
-    int cap = std::max(32, (s.maxNeigh + 31) & ~31);
-    const int WPB = 4;
-    for (int attempt = 0; attempt < 2; attempt++) {
-      size_t smem = acsf_warp_smem_bytes(cap, F) * WPB;
-      int wpb = WPB;
-      while (smem > 220 * 1024 && wpb > 1) { wpb >>= 1; smem = acsf_warp_smem_bytes(cap, F) * wpb; }
-      if (smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // buffer capacities (neighbours per atom, candidates per bin): counted once per slot; after a
+    // geometry update the previous maxima are reused as hints and the kernel's overflow flags
+    // trigger a retry
+    if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
+    for (int attempt = 0; attempt < 3; attempt++) {
+      AcsfLaunch L;
+      if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-      const int grid = (s.N + wpb - 1) / wpb;
-      LAUNCH(ctx, K_ACSF, (k_acsf<real><<<grid, wpb * 32, smem, ctx->stream>>>(
-                              s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos,
-                              s.d_cpos, s.d_atnum, s.nExt, s.d_ext, T, cap, feat, nFeat,
-                              useGiven ? ctx->d_zprec : nullptr, nExtSel, ctx->d_extIdx, ctx->d_flags)));
-      int h[8];
+      const dim3 grid(s.totalBins, L.nSplit);
+      const double *zp = useGiven ? ctx->d_zprec : nullptr;
+#define FNET_ACSF_LAUNCH(NS, ST)                                                                               \
+      do {                                                                                                     \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+        LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, ST><<<grid, L.wpb * 32, L.smem, ctx->stream>>>(                   \
+                                L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, \
+                                L.capC, feat, nFeat, zp, nExtSel, ctx->d_extIdx, ctx->d_flags)));               \
+      } while (0)
+      const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
+      if (L.staged) { if (ns == 1) FNET_ACSF_LAUNCH(1, true); else if (ns == 2) FNET_ACSF_LAUNCH(2, true); else FNET_ACSF_LAUNCH(4, true); }
+      else { if (ns == 1) FNET_ACSF_LAUNCH(1, false); else if (ns == 2) FNET_ACSF_LAUNCH(2, false); else FNET_ACSF_LAUNCH(4, false); }
+#undef FNET_ACSF_LAUNCH
+      int h[16];
       CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      if (h[1] == 0) break;
-      if (attempt == 1) FNET_FAIL(ctx, "neighbour buffer overflow");
-      s.maxNeigh = h[1];
-      cap = (h[1] + 31) & ~31;
+      s.maxBinPop = h[8 + 4];
+      if (h[1] == 0 && h[7] == 0) break;
+      if (attempt == 2) FNET_FAIL(ctx, "neighbour buffer overflow");
+      if (h[1] != 0) s.maxNeigh = h[1];
+      if (h[7] != 0) s.maxCand = h[7];     // 0x7fffffff: too many neighbour cells -> direct path
     }
   } else {
     const int B = 256;
@@ -980,21 +1064,24 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   }
   if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, (size_t)3 * n.nOut * s.N)) return 1; }
   CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
-  int cap = std::max(32, (s.maxNeigh + 31) & ~31);
-  int wpb = 4;
-  size_t fs = force_warp_smem_bytes(cap, T.F) * wpb;
-  while (fs > 220 * 1024 && wpb > 1) { wpb >>= 1; fs = force_warp_smem_bytes(cap, T.F) * wpb; }
-  if (fs > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+  AcsfLaunch L;
+  if (plan_acsf_launch(ctx, s, force_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F), L)) return 1;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-  dim3 g((s.N + wpb - 1) / wpb, n.nOut);
-  LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<<<g, wpb * 32, fs, ctx->stream>>>(s.N, s.d_structOf, s.d_sinfo, s.d_atomCell, s.d_cellStart, s.d_cellAtoms, s.d_fpos, s.d_cpos, s.d_atnum, s.nExt, s.d_ext, T, cap, dEdG64, n.nOut, s.zscored ? ctx->d_zprec : nullptr, s.d_forces, ctx->d_flags)));
-  int h[8];
+  const dim3 g(s.totalBins, L.nSplit, n.nOut);
+  const double *zp = s.zscored ? ctx->d_zprec : nullptr;
+  if (L.staged) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<true><<<g, L.wpb * 32, L.smem, ctx->stream>>>(L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags)));
+  } else {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<false><<<g, L.wpb * 32, L.smem, ctx->stream>>>(L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags)));
+  }
+  int h[16];
   CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   if (forces) CUDA_TRY(ctx, cudaMemcpyAsync(forces, s.d_forces, (size_t)3 * n.nOut * s.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (tmp64) cudaFree(tmp64);
-  if (h[1] != 0) FNET_FAIL(ctx, "neighbour buffer overflow in the force kernel");
+  if (h[1] != 0 || h[7] != 0) FNET_FAIL(ctx, "neighbour buffer overflow in the force kernel");
   return 0;
 }
 

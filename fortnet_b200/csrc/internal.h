@@ -12,6 +12,7 @@
 
 #include "../../include/fnetgpu.h"
 
+struct CRec;
 #define FNET_WARP 32
 #define FNET_MAX_LAYERS 16
 #define FNET_MAX_CODES 14          // distinct atomic numbers referenced by species-resolved functions
@@ -46,13 +47,18 @@ struct RadialGroup {
   int code;          // species code of the neighbour list, -1 = all neighbours
   int atomId;        // 0 or 1-based ext row
   int fBeg, fCnt;    // slice of the radial function tables
-  int nChunksP2;
+  int nChunksP2;     // 1, 2 or 4 chunks (<= 32 functions per group)
   double rc;
+  // G2 on an arithmetic rs-ladder with one eta (auto scheme): Gaussian recurrence constants
+  int ladder;
+  double eta, rs0, drs;
+  double kk[FNET_RCHUNK - 1];   // kk[m] = exp(-eta drs^2 (2m+1))
 };
 
 struct LadderSlot {
   double lam, xi0, dxi;
   int count;
+  int cont;                    // continues the previous slot's ladder (same lam, dxi; xi0 = prev.xi0 + 8 dxi)
   int feat[FNET_LADDER];       // output feature index
   double pref[FNET_LADDER];    // 2^(1-xi)
   double xi[FNET_LADDER];      // exponents (used by the derivative kernel)
@@ -110,11 +116,12 @@ struct Slot {
   int *d_offsets = nullptr, *d_structOf = nullptr, *d_atnum = nullptr, *d_sp = nullptr, *d_periodic = nullptr;
   double *d_coords = nullptr;       // [N][3] as given
   double *d_fpos = nullptr;         // [N][3] folded positions (atom order)
-  double *d_cpos = nullptr;         // [N][3] folded positions (cell order)
+  CRec *d_crec = nullptr;    // [N] 32-byte records in cell order (position, atom index, atomic number)
+  int *d_binStruct = nullptr;       // [totalBins] structure of each bin
   StructInfo *d_sinfo = nullptr;
   int *d_atomCell = nullptr, *d_cellStart = nullptr, *d_cellCount = nullptr, *d_cellAtoms = nullptr;
   int totalBins = 0;
-  size_t capCoords = 0, capFpos = 0, capCpos = 0, capAtomCell = 0, capCellAtoms = 0, capCellStart = 0, capCellCount = 0, capSinfo = 0, capNeigh = 0;
+  size_t capCoords = 0, capFpos = 0, capCrec = 0, capBinStruct = 0, capAtomCell = 0, capCellAtoms = 0, capCellStart = 0, capCellCount = 0, capSinfo = 0;
   bool neighStale = true;           // maxNeigh is only a hint for the current geometry
   double cellRc = -1.0;             // cutoff the cell list was built for
   double *d_dsw = nullptr;          // [nStruct] dataset weights as double
@@ -125,7 +132,9 @@ struct Slot {
   bool featValid = false;
   bool zscored = false;             // features were standardised with ctx->d_zprec
   int maxNeigh = -1; double meanNeigh = 0.0;
-  int *d_neighCount = nullptr;
+  int maxCand = -1;                 // max candidates (atoms in the neighbour cells) of a bin
+  int maxBinPop = 0;                // largest bin population (hint, from the last cell-list build)
+  int maxCells = 0;                 // max neighbour cells per bin: (2D0+1)(2D1+1)(2D2+1)
   // species-sorted processing order
   int *d_perm = nullptr;            // [N] atom ids sorted by species (stable)
   std::vector<int> spBeg;           // [nSpecies+1]
@@ -160,6 +169,7 @@ struct fnetgpu_ctx {
   AcsfTables acsf;                  // device pointers inside
   std::vector<RadialGroup> h_rgroups;
   std::vector<AngularPass> h_apasses;
+  int maxSlots = 1;                 // largest nSlots of any angular pass (selects the kernel instantiation)
   RadialGroup *d_rgroups = nullptr; int *d_rfeat = nullptr; double *d_rp1 = nullptr, *d_rp2 = nullptr;
   AngularPass *d_apasses = nullptr;
   std::vector<int> extIdx;          // 0-based rows of ext appended to the features
@@ -176,7 +186,7 @@ struct fnetgpu_ctx {
   double *d_partials = nullptr; size_t partialsN = 0;
   double *d_dd = nullptr;           // [nSpecies*nTot + 2] reduced gradient + loss numerator/denominator
   double *h_pinned = nullptr; size_t pinnedN = 0;
-  int *d_flags = nullptr;           // [4] overflow flag etc.
+  int *d_flags = nullptr;           // [8] statistics / overflow flags (cells.cuh, acsf.cuh)
   // comm
   void *nccl = nullptr;             // dlopen handle
   void *comm = nullptr;             // ncclComm_t
