@@ -25,6 +25,7 @@
 // cutoffs and q_j q_k in G4's third cutoff (acsf.F90:1201,1428-1430).
 #pragma once
 #include "cells.cuh"
+#include "fmath.cuh"
 
 struct WarpSmem {
   double *dx, *dy, *dz, *r, *rinv, *qv, *fcE;
@@ -41,7 +42,7 @@ __host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F) {
 }
 // CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates
 __host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC) {
-  return (size_t)capC * sizeof(CRec) + (size_t)(2 * FNET_MAX_NCELLS + 4) * sizeof(int);
+  return (size_t)capC * sizeof(CRec) + ((sizeof(StageTabs) + 15) & ~(size_t)15);
 }
 
 __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap, int F) {
@@ -162,8 +163,8 @@ __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) 
 // (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
 // pow(0,0)=1 / pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
 __device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q) {
-  p = (xi0 == 1.0) ? b : ((xi0 == 0.0) ? 1.0 : exp(xi0 * L));
-  q = (dxi == 0.0) ? 1.0 : exp(dxi * L);
+  p = (xi0 == 1.0) ? b : ((xi0 == 0.0) ? 1.0 : fnet_exp(xi0 * L));
+  q = (dxi == 0.0) ? 1.0 : fnet_exp(dxi * L);
 }
 
 // pair index -> (row j, column k) of the flattened pair walk.  same: upper triangle incl. the
@@ -207,8 +208,19 @@ __device__ __forceinline__ double reduce_transpose(double (&v)[M], int lane, int
 }
 
 // ------------------------------------------------------------------------------------------
-// radial groups (acsf.F90:1287-1373): lanes = (neighbour sub-lane, 8-function chunk)
+// radial groups (acsf.F90:1287-1373)
+//   ladder groups (G2, arithmetic rs, one eta): lanes = (neighbour sub-lane, 8-function chunk),
+//     Gaussian recurrence, transposing butterfly over the sub-lanes;
+//   generic groups (G1, G3, arbitrary G2): lanes = (neighbour sub-lane, function), one
+//     accumulator per lane, xor-shuffle over the sub-lanes.  Kept small on purpose: this path
+//     only has to be correct, the instruction cache belongs to the hot loops.
 // ------------------------------------------------------------------------------------------
+__device__ __noinline__ double radial_term_generic(int type, double p1, double p2, double rr) {
+  if (type == FNETGPU_G1) return 1.0;
+  if (type == FNETGPU_G2) { const double d = rr - p2; return exp(-p1 * d * d); }
+  return cos(p1 * rr);
+}
+
 __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &tab, const WarpSmem &w, int nExt,
                                               const double *__restrict__ ext) {
   const int lane = threadIdx.x & 31;
@@ -220,20 +232,20 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
     const int nl = l.n0 + l.n1;
     const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
     const double invrc = 1.0 / rc;
-    const int per = 32 / nch;
-    const int mychunk = lane % nch, sub = lane / nch;
-    const int fbase = fBeg + mychunk * FNET_RCHUNK;
-    const int fcnt = min(max(fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
-    double acc[FNET_RCHUNK];
+    if (G->ladder) {
+      const int per = 32 / nch;
+      const int mychunk = lane % nch, sub = lane / nch;
+      const int fbase = fBeg + mychunk * FNET_RCHUNK;
+      const int fcnt = min(max(fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
+      double acc[FNET_RCHUNK];
 #pragma unroll
-    for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
-    if (fcnt > 0) {
-      if (type == FNETGPU_G2 && G->ladder) {
-        const double eta = G->eta, drs = G->drs;
-        const double rsf = G->rs0 + (double)(mychunk * FNET_RCHUNK) * drs;
-        double kk[FNET_RCHUNK - 1];
+      for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
+      const double eta = G->eta, drs = G->drs;
+      const double rsf = G->rs0 + (double)(mychunk * FNET_RCHUNK) * drs;
+      double kk[FNET_RCHUNK - 1];
 #pragma unroll
-        for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = G->kk[m];
+      for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = G->kk[m];
+      if (fcnt > 0)
         for (int t = sub; t < nl; t += per) {
           const int a = list_at(l, t);
           const double rr = w.r[a];
@@ -242,43 +254,46 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
           const double fc = cutoff_fn(rr, qi * qj, invrc);
           const double u = rr - rsf;
           const double e0 = eta * u * u, a1 = 2.0 * eta * drs * u;
-          if (e0 < 600.0 && fabs(a1) * (FNET_RCHUNK - 1) < 600.0) {
-            double gv = exp(-e0) * fc;
-            const double A = exp(a1);
+          if (e0 < 690.0 && fabs(a1) < 690.0) {         // g_0 and the ratio stay normal numbers
+            double gv = fnet_exp(-e0) * fc;
+            const double A = fnet_exp(a1);
             acc[0] += gv;
 #pragma unroll
             for (int m = 0; m < FNET_RCHUNK - 1; m++) { gv *= A * kk[m]; acc[m + 1] += gv; }
-          } else {                                      // out of the recurrence's safe range
+          } else {                                      // out of the recurrence's safe range (rare)
+#pragma unroll 1
+            for (int m = 0; m < FNET_RCHUNK; m++) {
+              const double d = u - (double)m * drs;
+              const double v = radial_term_generic(FNETGPU_G2, eta, 0.0, d) * fc;
 #pragma unroll
-            for (int f = 0; f < FNET_RCHUNK; f++) { const double d = u - (double)f * drs; acc[f] += exp(-eta * d * d) * fc; }
+              for (int f = 0; f < FNET_RCHUNK; f++) acc[f] += (f == m) ? v : 0.0;
+            }
           }
         }
-      } else {
+      // sum over the sub-lanes: lane ends with function (lane / nch) % 8 of chunk lane % nch
+      const double v = reduce_transpose<FNET_RCHUNK>(acc, lane, nch);
+      const int f = (lane / nch) % FNET_RCHUNK;
+      if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[fbase + f]] = v;
+    } else {
+      int nfP2 = 1;
+      while (nfP2 < fCnt) nfP2 <<= 1;                  // fCnt <= 32
+      const int per = 32 / nfP2;
+      const int f = lane % nfP2, sub = lane / nfP2;
+      double acc = 0.0;
+      if (f < fCnt) {
+        const double p1 = tab.rp1[fBeg + f], p2 = tab.rp2[fBeg + f];
+#pragma unroll 1
         for (int t = sub; t < nl; t += per) {
           const int a = list_at(l, t);
           const double rr = w.r[a];
           if (rr > rc) continue;
           const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[a] + atomId - 1] : 1.0;
-          const double fc = cutoff_fn(rr, qi * qj, invrc);
-          if (type == FNETGPU_G1) {
-#pragma unroll
-            for (int f = 0; f < FNET_RCHUNK; f++) acc[f] += fc;
-          } else if (type == FNETGPU_G2) {
-#pragma unroll
-            for (int f = 0; f < FNET_RCHUNK; f++)
-              if (f < fcnt) { const double d = rr - tab.rp2[fbase + f]; acc[f] += exp(-tab.rp1[fbase + f] * d * d) * fc; }
-          } else {
-#pragma unroll
-            for (int f = 0; f < FNET_RCHUNK; f++)
-              if (f < fcnt) acc[f] += cos(tab.rp1[fbase + f] * rr) * fc;
-          }
+          acc += radial_term_generic(type, p1, p2, rr) * cutoff_fn(rr, qi * qj, invrc);
         }
       }
+      for (int off = nfP2; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane < nfP2 && f < fCnt) w.outv[tab.rfeat[fBeg + f]] = acc;
     }
-    // sum over the sub-lanes: lane ends with function (lane / nch) % 8 of chunk lane % nch
-    const double v = reduce_transpose<FNET_RCHUNK>(acc, lane, nch);
-    const int f = (lane / nch) % FNET_RCHUNK;
-    if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[fbase + f]] = v;
   }
 }
 
@@ -301,7 +316,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
     const double rr = w.r[t];
     const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
     w.qv[t] = qj;
-    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * exp(-eta * rr * rr);
+    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * fnet_exp(-eta * rr * rr);
   }
   __syncwarp();
   double lam[NS], xi0[NS], dxi[NS];
@@ -329,7 +344,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       const double ex = w.dx[a] - w.dx[b], ey = w.dy[a] - w.dy[b], ez = w.dz[a] - w.dz[b];
       const double djk2 = ex * ex + ey * ey + ez * ez;
       const double djk = sqrt(djk2);
-      base = (djk > rc) ? 0.0 : base * exp(-eta * djk2) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
+      base = (djk > rc) ? 0.0 : base * fnet_exp(-eta * djk2) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
     }
     if (base != 0.0) {
       const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
@@ -340,7 +355,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       for (int s = 0; s < NS; s++) {
         if (on[s]) {
           if (!cont[s]) {
-            if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = log(bb); }
+            if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log(bb); }
             ladder_init(bb, L, xi0[s], dxi[s], pw, q);
             pw *= base;
           }
@@ -380,7 +395,7 @@ k_acsf(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restri
   int nCand = 0;
   unsigned char *wbase = smem_raw;
   if (STAGED) {
-    int *tabs = (int *)(smem_raw + (size_t)capC * sizeof(CRec));
+    StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
     nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
     if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
     wbase += acsf_cta_prefix_bytes(capC);

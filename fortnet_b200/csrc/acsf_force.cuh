@@ -52,7 +52,7 @@ k_acsf_force(int nSplit, const int *__restrict__ binStruct, const StructInfo *__
   int nCand = 0;
   unsigned char *wbase = smem_raw;
   if (STAGED) {
-    int *tabs = (int *)(smem_raw + (size_t)capC * sizeof(CRec));
+    StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
     nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
     if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
     wbase += acsf_cta_prefix_bytes(capC);

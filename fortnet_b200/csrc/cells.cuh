@@ -176,46 +176,60 @@ __device__ __forceinline__ NCell neighbor_cell(const StructInfo &S, const BinPos
 }
 
 // CTA-cooperative staging of all candidate records of a bin's neighbour cells (shift applied).
-// Warp w copies cells w, w+nWarps, ...; returns the candidate count (or -needed on overflow, or
-// -1 when the bin has more than FNET_MAX_NCELLS neighbour cells).  tabs: 2*FNET_MAX_NCELLS+1 ints.
+// Each neighbour cell is resolved once (thread c < ncells) into the shared tables; warp w then
+// copies cells w, w+nWarps, ...  Returns the candidate count (or -needed on overflow, or -1 when
+// the bin has more than FNET_MAX_NCELLS neighbour cells).
+struct StageTabs {                       // lives in shared memory behind the candidate records
+  double sh[FNET_MAX_NCELLS][3];
+  int beg[FNET_MAX_NCELLS];              // first record; bit 31 set when the lattice shift is non-zero
+  int len[FNET_MAX_NCELLS];
+  int pre[FNET_MAX_NCELLS + 4];
+};
+
 __device__ __forceinline__ int stage_candidates(const StructInfo &S, const BinPos &p,
                                                 const int *__restrict__ cellStart,
                                                 const CRec *__restrict__ crec, CRec *__restrict__ cand,
-                                                int capC, int *__restrict__ tabs) {
+                                                int capC, StageTabs *__restrict__ tb) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  int *clen = tabs, *cpre = tabs + FNET_MAX_NCELLS;
   if (p.ncells > FNET_MAX_NCELLS) return -1;
   for (int c = threadIdx.x; c < FNET_MAX_NCELLS; c += blockDim.x) {
     int len = 0;
-    if (c < p.ncells) { NCell nc = neighbor_cell(S, p, c, cellStart); len = nc.len; }
-    clen[c] = len;
+    if (c < p.ncells) {
+      const NCell nc = neighbor_cell(S, p, c, cellStart);
+      len = nc.len;
+      tb->beg[c] = nc.beg | (nc.shifted ? 0x80000000 : 0);
+      tb->sh[c][0] = nc.sx; tb->sh[c][1] = nc.sy; tb->sh[c][2] = nc.sz;
+    }
+    tb->len[c] = len;
   }
   __syncthreads();
   if (wib == 0) {   // exclusive scan over FNET_MAX_NCELLS = 4 x 32 entries
     int carry = 0;
 #pragma unroll
     for (int q = 0; q < FNET_MAX_NCELLS / 32; q++) {
-      const int v = clen[q * 32 + lane];
+      const int v = tb->len[q * 32 + lane];
       int x = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      cpre[q * 32 + lane] = carry + x - v;
+      tb->pre[q * 32 + lane] = carry + x - v;
       carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane == 0) cpre[FNET_MAX_NCELLS] = carry;
+    if (lane == 0) tb->pre[FNET_MAX_NCELLS] = carry;
   }
   __syncthreads();
-  const int total = cpre[FNET_MAX_NCELLS];
+  const int total = tb->pre[FNET_MAX_NCELLS];
   if (total > capC) return -total;
   for (int c = wib; c < p.ncells; c += nw) {
-    const int len = clen[c];
+    const int len = tb->len[c];
     if (len == 0) continue;
-    const NCell nc = neighbor_cell(S, p, c, cellStart);
-    const int dst = cpre[c];
+    const int begf = tb->beg[c], beg = begf & 0x7fffffff;
+    const int flag = (begf < 0) ? FNET_SHIFT_FLAG : 0;
+    const double sx = tb->sh[c][0], sy = tb->sh[c][1], sz = tb->sh[c][2];
+    const int dst = tb->pre[c];
     for (int t = lane; t < len; t += 32) {
-      CRec r = crec[nc.beg + t];
-      r.x += nc.sx; r.y += nc.sy; r.z += nc.sz;
-      if (nc.shifted) r.zs |= FNET_SHIFT_FLAG;
+      CRec r = crec[beg + t];
+      r.x += sx; r.y += sy; r.z += sz;
+      r.zs |= flag;
       cand[dst + t] = r;
     }
   }
