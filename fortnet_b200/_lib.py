@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfnetgpu.so")
+LIB_PATH = os.environ.get("FNETGPU_LIB") or os.path.join(_HERE, "libfnetgpu.so")   # override: A/B builds
 _lib = None
 
 SYMBOLS = [

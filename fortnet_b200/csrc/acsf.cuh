@@ -27,6 +27,11 @@
 #include "cells.cuh"
 #include "fmath.cuh"
 
+#ifndef FNET_ACSF_MINB
+#define FNET_ACSF_MINB 5          // resident CTAs per SM the value kernel is compiled for (NS <= 2)
+#endif
+static_assert(FNET_LADDER == 8, "ladder_accumulate is written for 8-function ladders");
+
 struct WarpSmem {
   double *dx, *dy, *dz, *r, *rinv, *qv, *fcE;
   int *idx, *seg;
@@ -162,9 +167,22 @@ __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) 
 
 // (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
 // pow(0,0)=1 / pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
+__device__ __noinline__ double fnet_exp_call(double x) { return fnet_exp(x); }   // keeps rare paths out of line
 __device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q) {
-  p = (xi0 == 1.0) ? b : ((xi0 == 0.0) ? 1.0 : fnet_exp(xi0 * L));
+  if (xi0 == 1.0) p = b;                       // auto scheme: every ladder starts at xi = 1 (acsf.F90:341)
+  else if (xi0 == 0.0) p = 1.0;
+  else p = fnet_exp_call(xi0 * L);
   q = (dxi == 0.0) ? 1.0 : fnet_exp(dxi * L);
+}
+// acc[m] += pw q^m (m = 0..7) with the powers built by doubling (dependency depth 3 instead of
+// 8); returns pw q^8 for a continuing ladder slot
+__device__ __forceinline__ double ladder_accumulate(double *acc, double pw, double q) {
+  const double q2 = q * q, q4 = q2 * q2;
+  const double p1 = pw * q, p2 = pw * q2, p3 = p1 * q2;
+  acc[0] += pw; acc[1] += p1; acc[2] += p2; acc[3] += p3;
+  const double p4 = pw * q4, p5 = p1 * q4, p6 = p2 * q4, p7 = p3 * q4;
+  acc[4] += p4; acc[5] += p5; acc[6] += p6; acc[7] += p7;
+  return p4 * q4;
 }
 
 // pair index -> (row j, column k) of the flattened pair walk.  same: upper triangle incl. the
@@ -359,8 +377,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
             ladder_init(bb, L, xi0[s], dxi[s], pw, q);
             pw *= base;
           }
-#pragma unroll
-          for (int f = 0; f < FNET_LADDER; f++) { acc[s * FNET_LADDER + f] += pw; pw *= q; }
+          pw = ladder_accumulate(&acc[s * FNET_LADDER], pw, q);
         }
       }
     }
@@ -375,7 +392,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
 }
 
 template <typename real, int NS, bool STAGED>
-__global__ void __launch_bounds__(128, (NS <= 2 ? 4 : 3))
+__global__ void __launch_bounds__(128, (NS <= 2 ? FNET_ACSF_MINB : 3))
 k_acsf(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restrict__ sinfo,
        const int *__restrict__ cellStart, const CRec *__restrict__ crec, int nExt,
        const double *__restrict__ ext, AcsfTables tab, int cap, int capC, real *__restrict__ feat,

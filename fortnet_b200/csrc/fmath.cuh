@@ -18,6 +18,37 @@
 #else
 #define FNET_HD static inline
 #endif
+#ifdef __CUDA_ARCH__
+#define FNET_UNROLL _Pragma("unroll")
+#else
+#define FNET_UNROLL
+#endif
+
+
+// Polynomial coefficients live in constant memory on the device: a DFMA then takes the
+// coefficient straight from the constant bank (one issue slot per Horner step) instead of two
+// UMOVs that rebuild a 64-bit immediate in a uniform register.
+#define FNET_EXP_COEFFS { 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, \
+  2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, \
+  1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, \
+  1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10 }
+#define FNET_LOG_COEFFS { 4.7619047619047616e-02, 5.2631578947368418e-02, 5.8823529411764705e-02, \
+  6.6666666666666666e-02, 7.6923076923076927e-02, 9.0909090909090912e-02, 1.1111111111111110e-01, \
+  1.4285714285714285e-01, 2.0000000000000001e-01, 3.3333333333333331e-01, \
+  1.90821492927058770002e-10, 6.93147180369123816490e-01 }
+#ifdef __CUDACC__
+__constant__ double fnet_exp_cd[14] = FNET_EXP_COEFFS;
+__constant__ double fnet_log_cd[12] = FNET_LOG_COEFFS;
+#endif
+static const double fnet_exp_ch[14] = FNET_EXP_COEFFS;
+static const double fnet_log_ch[12] = FNET_LOG_COEFFS;
+#ifdef __CUDA_ARCH__
+#define FNET_EC(i) fnet_exp_cd[i]
+#define FNET_LC(i) fnet_log_cd[i]
+#else
+#define FNET_EC(i) fnet_exp_ch[i]
+#define FNET_LC(i) fnet_log_ch[i]
+#endif
 
 FNET_HD double fnet_mk_double(int hi, int lo) {
 #ifdef __CUDA_ARCH__
@@ -46,22 +77,14 @@ FNET_HD int fnet_lo(double x) {
 // Taylor polynomial on |r| <= 0.3466 (truncation 4e-18 relative).
 FNET_HD double fnet_exp(double x) {
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52: rint() through the adder
-  const double tk = fma(x, 1.4426950408889634074, magic);
+  const double tk = fma(x, FNET_EC(11), magic);
   const int k = fnet_lo(tk);
   const double kd = tk - magic;
-  double r = fma(kd, -6.93147180369123816490e-01, x);      // ln2 high part: 32 significant bits
-  r = fma(kd, -1.90821492927058770002e-10, r);             // ln2 low part
-  double p = 1.6059043836821613e-10;                        // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);                      // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);                     // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);                     // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);                    // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);                      // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);                     // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);                     // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);                     // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);                    // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);                    // 1/3!
+  double r = fma(kd, FNET_EC(12), x);                      // ln2 high part: 32 significant bits
+  r = fma(kd, FNET_EC(13), r);                             // ln2 low part
+  double p = FNET_EC(0);                                   // 1/13!
+FNET_UNROLL
+  for (int i = 1; i <= 10; i++) p = fma(p, r, FNET_EC(i)); // 1/12! ... 1/3!
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
@@ -93,21 +116,14 @@ FNET_HD double fnet_log(double x) {
   const double s = f / d;
 #endif
   const double z = s * s;
-  double q = 4.7619047619047616e-02;                        // 1/21
-  q = fma(q, z, 5.2631578947368418e-02);                    // 1/19
-  q = fma(q, z, 5.8823529411764705e-02);                    // 1/17
-  q = fma(q, z, 6.6666666666666666e-02);                    // 1/15
-  q = fma(q, z, 7.6923076923076927e-02);                    // 1/13
-  q = fma(q, z, 9.0909090909090912e-02);                    // 1/11
-  q = fma(q, z, 1.1111111111111110e-01);                    // 1/9
-  q = fma(q, z, 1.4285714285714285e-01);                    // 1/7
-  q = fma(q, z, 2.0000000000000001e-01);                    // 1/5
-  q = fma(q, z, 3.3333333333333331e-01);                    // 1/3
+  double q = FNET_LC(0);                                   // 1/21
+FNET_UNROLL
+  for (int i = 1; i <= 9; i++) q = fma(q, z, FNET_LC(i));  // 1/19 ... 1/3
   const double s2 = s + s;
   const double ed = (double)e;
   // e*ln2_hi is exact (ln2_hi has 32 significant bits, |e| < 2^11)
-  double res = fma(ed, 1.90821492927058770002e-10, (s2 * z) * q);
+  double res = fma(ed, FNET_LC(10), (s2 * z) * q);
   res = res + s2;
-  res = fma(ed, 6.93147180369123816490e-01, res);
+  res = fma(ed, FNET_LC(11), res);
   return tiny ? -INFINITY : res;
 }
