@@ -881,21 +881,17 @@ extern "C" int fnetgpu_params_set(fnetgpu_ctx *ctx, const double *wb) {
   return 0;
 }
 
-// tile table of the species-sorted atom order; T = threads (= atoms) per CTA
+// tile table of the species-sorted atom order; T = atoms per tile (k_bpnn, mlp.cuh)
 template <typename real>
 static int ensure_tiles(fnetgpu_ctx *ctx, Slot &s) {
   if (s.nTiles > 0) return 0;
   const NetTables &n = ctx->net;
   if ((int)s.spBeg.size() - 1 > n.nSpecies) FNET_FAIL(ctx, "dataset references more species than the network has sub-networks");
-  const SmemNet sn = smem_net_layout(n);
-  const int rowsD = n.rowsA - n.dims[0];
-  int T = 32;
-  const int cand[4] = {128, 96, 64, 32};
-  for (int c = 0; c < 4; c++) {
-    size_t sm = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (cand[c] + 1)) * sizeof(real);
-    if (sm <= 100 * 1024 || (cand[c] == 32 && sm <= 220 * 1024)) { T = cand[c]; break; }
-    if (cand[c] == 32) FNET_FAIL(ctx, "network too large for the shared-memory tile (layer widths sum too big)");
-  }
+  int T = 0;
+  const int cand[3] = {64, 32, 16};
+  for (int c = 0; c < 3 && !T; c++)
+    if (bpnn_smem_bytes<real>(n, cand[c], 0, false) <= 220 * 1024) T = cand[c];
+  if (!T) FNET_FAIL(ctx, "network too large for the shared-memory tile (layer widths sum too big)");
   std::vector<int> tiles;
   for (int sp = 0; sp + 1 < (int)s.spBeg.size(); sp++)
     for (int b = s.spBeg[sp]; b < s.spBeg[sp + 1]; b += T) {
@@ -912,6 +908,24 @@ static int ensure_tiles(fnetgpu_ctx *ctx, Slot &s) {
   return 0;
 }
 
+// launch geometry of k_bpnn: threads = largest per-layer item count (4-atom x 4-output register
+// tiles), persistent grid sized by the shared-memory footprint
+struct BpnnLaunch { int threads, grid, gInSmem; size_t smem; };
+template <typename real>
+static BpnnLaunch plan_bpnn(fnetgpu_ctx *ctx, const Slot &s, int mode) {
+  const NetTables &n = ctx->net;
+  BpnnLaunch B;
+  const int RG = s.tileT / 4;
+  int items = 32;
+  for (int l = 0; l < n.L; l++) items = std::max(items, RG * ((n.dims[l] + 3) / 4));
+  B.threads = std::min(256, (items + 31) & ~31);
+  B.gInSmem = (mode == 0 && bpnn_smem_bytes<real>(n, s.tileT, 0, true) <= 220 * 1024) ? 1 : 0;
+  B.smem = bpnn_smem_bytes<real>(n, s.tileT, mode, B.gInSmem != 0);
+  const int perSM = std::max(1, std::min((int)(225 * 1024 / (B.smem + 1024)), 2048 / B.threads));
+  B.grid = std::max(1, std::min(s.nTiles, ctx->nSM * std::min(perSM, 8)));
+  return B;
+}
+
 template <typename real>
 static int check_ready(fnetgpu_ctx *ctx, Slot &s, bool needTargets) {
   if (!s.used) FNET_FAIL(ctx, "empty dataset slot");
@@ -925,15 +939,12 @@ static int check_ready(fnetgpu_ctx *ctx, Slot &s, bool needTargets) {
 template <typename real>
 static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
   const NetTables &n = ctx->net;
-  const SmemNet sn = smem_net_layout(n);
-  int dmax = 1;
-  for (int l = 0; l < n.L; l++) dmax = std::max(dmax, n.dims[l]);
-  const int T = s.tileT;
-  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)2 * dmax * (T + 1)) * sizeof(real);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_fwd<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = std::max(1, (int)(200 * 1024 / smem));
-  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
-  LAUNCH(ctx, K_MLP_FWD, (k_mlp_fwd<real><<<grid, T, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, dmax, (real *)s.d_raw)));
+  const BpnnLaunch B = plan_bpnn<real>(ctx, s, 2);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  LAUNCH(ctx, K_MLP_FWD, (k_bpnn<real, 2><<<B.grid, B.threads, B.smem, ctx->stream>>>(
+                             s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
+                             s.tileT, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr,
+                             (real *)nullptr, (real *)s.d_raw)));
   return 0;
 }
 
@@ -955,16 +966,16 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
   const size_t nDD = (size_t)n.nTot * n.nSpecies;
   if (run_forward<real>(ctx, s)) return 1;
   if (run_struct_loss<real>(ctx, s, lossId)) return 1;
-  const SmemNet sn = smem_net_layout(n);
-  const int T = s.tileT, rowsD = n.rowsA - n.dims[0];
-  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (T + 1)) * sizeof(real);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_bwd<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = std::max(1, (int)(200 * 1024 / smem));
-  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
+  const BpnnLaunch B = plan_bpnn<real>(ctx, s, 0);
+  const int grid = B.grid;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
   size_t need = (size_t)grid * nDD;
   if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_partials, 0, need * sizeof(double), ctx->stream));
-  LAUNCH(ctx, K_MLP_GRAD, (k_mlp_bwd<real, 0><<<grid, T, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (real *)nullptr)));
+  LAUNCH(ctx, K_MLP_GRAD, (k_bpnn<real, 0><<<grid, B.threads, B.smem, ctx->stream>>>(
+                              s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
+                              s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
+                              lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
   LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
   if (allreduce_sum(ctx, ctx->d_dd, nDD + 2)) return 1;   // gradient | loss numerator | denominator
   if (ddSerial || loss) {
@@ -1045,13 +1056,14 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   if (ensure_neigh_count(ctx, s)) return 1;   // exact count: the force kernel has no retry loop
   // (1) dE_k/dG for every atom and output: one reverse sweep per output
   if (!s.d_dEdG) { real *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
-  const SmemNet sn = smem_net_layout(n);
-  const int TT = s.tileT, rowsD = n.rowsA - n.dims[0];
-  size_t smem = ((size_t)((sn.total + 1) & ~1) + (size_t)(n.rowsA + rowsD) * (TT + 1)) * sizeof(real);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_bwd<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = std::max(1, (int)(200 * 1024 / smem));
-  int grid = std::min(s.nTiles, ctx->nSM * std::min(perSM, 8));
-  LAUNCH(ctx, K_MLP_INGRAD, (k_mlp_bwd<real, 1><<<grid, TT, smem, ctx->stream>>>(s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr, (real *)s.d_dEdG)));
+  {
+    const BpnnLaunch B = plan_bpnn<real>(ctx, s, 1);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<real, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
+                                  s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
+                                  s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
+                                  nullptr, (real *)s.d_dEdG, (real *)nullptr)));
+  }
   // the force kernel contracts in FP64
   const double *dEdG64 = nullptr;
   double *tmp64 = nullptr;

@@ -39,6 +39,16 @@ int main() {
     if (re > ml) ml = re;
   }
   if (fnet_log(0.0) != -INFINITY || fnet_log(1.0) != 0.0) { printf("log edge cases failed\n"); return 1; }
-  printf("FMATH_OK %.3e %.3e\n", me, ml);
-  return (me < 1e-14 && ml < 1e-14) ? 0 : 2;
+  double mt = 0.0;
+  for (int i = 0; i < 2000000; i++) {
+    double u = urand(seed);
+    double x = (i % 3 == 0) ? 40.0 * (u - 0.5) : (i % 3 == 1 ? 2.0 * (u - 0.5) : 0.01 * (u - 0.5));
+    if (i % 1000 == 7) x = 800.0 * (u - 0.5);
+    double a = fnet_tanh(x), b = tanh(x);
+    double re = (b == 0.0) ? fabs(a) : fabs(a - b) / fabs(b);
+    if (re > mt) mt = re;
+  }
+  if (fnet_tanh(0.0) != 0.0 || fnet_tanh(1e3) != 1.0 || fnet_tanh(-1e3) != -1.0) { printf("tanh edge cases failed\n"); return 1; }
+  printf("FMATH_OK %.3e %.3e %.3e\n", me, ml, mt);
+  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13) ? 0 : 2;
 }
