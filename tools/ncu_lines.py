@@ -54,7 +54,14 @@ def main():
             blocks.append((r[1], cur_rows))
         elif cur_rows is not None:
             cur_rows.append(r)
-    name, rs = blocks[0]
+    # pick the report block whose instruction count matches the disassembly (or env NCU_BLOCK)
+    bi = int(os.environ.get("NCU_BLOCK", "-1"))
+    if bi < 0:
+        bi = 0
+        for k, (nm, rr) in enumerate(blocks):
+            if len(rr) - 1 == len(inst_lines):
+                bi = k; break
+    name, rs = blocks[bi]
     hdr = rs[0]
     ci, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
     data = rs[1:]
