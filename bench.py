@@ -49,8 +49,8 @@ def workload(name, n_struct, seed_shift=0):
     assert len(funcs) == dims[0]
     rng = np.random.default_rng(7)
     n_species = len(ds.atomic_numbers)
-    import oracle.oracle as _o  # only for ntot(); not on any timed product path
-    ntot = _o.ntot(dims)
+    # serialised length per species (network.F90:397-427): all weights incl. the dummy ww(d_L,1), all biases
+    ntot = sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1] + sum(dims)
     wb = rng.uniform(-0.5, 0.5, size=(n_species, ntot))
     return ds, funcs, dims, wb, label
 

@@ -1,0 +1,393 @@
+"""GPU parity (through the C ABI) against the CPU oracle on synthetic inputs of the BASELINE.json
+shapes, the edge cases the reference handles (clusters, single atoms, ragged batches, thin and
+triclinic cells, unfolded coordinates), and size-independent properties at full configuration size.
+
+FP64 mode: the reference comparator's RTOL 1e-9 / ATOL 1e-10 (bin/testwithworkdir.py:24-25), raw
+ACSF values at RTOL 1e-10.  FP32 mode: the bound documented in DESIGN.md section 4.5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-10
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fortnet_b200 as fb
+    return fb
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _nthreads():
+    import os
+    return os.cpu_count() or 1
+
+
+def _ntot(dims):
+    return sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1] + sum(dims)
+
+
+def _md(a, b):
+    return "max abs diff %.3e (scale %.3e)" % (np.abs(a - b).max(), np.abs(b).max())
+
+
+def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3):
+    """features (raw + z-scored), statistics, predictions, loss, gradient and forces vs the oracle"""
+    fd = funcs.asdicts()
+    nt = _nthreads()
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    a_raw = fb.Acsf(ctx, funcs, standardize=False)
+    a_raw.calculate(0)
+    vals = a_raw.features(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, ext=ds.ext, nthreads=nt)
+    assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    mu, sg = orc.zscore_stats(ds.offsets, ref, ds.weights)
+    assert np.allclose(acsf.zprec[0], mu, rtol=RTOL, atol=ATOL), _md(acsf.zprec[0], mu)
+    assert np.allclose(acsf.zprec[1], sg, rtol=RTOL, atol=ATOL), _md(acsf.zprec[1], sg)
+    zref = orc.zscore_apply(ref, mu, sg)
+    z = acsf.features(0)
+    assert np.allclose(z, zref, rtol=RTOL, atol=ATOL), _md(z, zref)
+    nsp = len(ds.atomic_numbers)
+    net = fb.Bpnn(ctx, dims, nsp, act)
+    wb = np.random.default_rng(seed).uniform(-0.5, 0.5, size=(nsp, _ntot(dims)))
+    net.set_params(wb)
+    raw = net.predict_batch(0)
+    raw_o = orc.predict(zref, ds.globalsp, dims, act, wb, nthreads=nt)
+    assert np.allclose(raw, raw_o, rtol=RTOL, atol=ATOL), _md(raw, raw_o)
+    dd, lossv = net.update_gradients(0, loss)
+    dd_o, raw_o2 = orc.grad(ds.offsets, zref, ds.globalsp, dims, act, wb, loss, ds.weights, ds.atomic_weights,
+                            ds.gtargets, ds.atargets, nthreads=nt)
+    assert np.allclose(dd, dd_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(dd_o).max())), _md(dd, dd_o)
+    loss_o = orc.loss(ds.offsets, raw_o2, loss, ds.n_global_targets, ds.n_atomic_targets, ds.gtargets, ds.atargets,
+                      ds.atomic_weights, ds.weights)
+    assert abs(lossv - loss_o) <= ATOL + RTOL * abs(loss_o), (lossv, loss_o)
+    assert abs(net.loss(0, loss) - loss_o) <= ATOL + RTOL * abs(loss_o)
+    if forces:
+        f = net.forces(0)
+        f_o = orc.forces(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, zref, ds.globalsp, dims, act,
+                         wb, ext=ds.ext, sigmas=sg, nthreads=nt)
+        assert np.allclose(f, f_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(f_o).max())), _md(f, f_o)
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs at oracle-sized samples
+# ---------------------------------------------------------------------------------------------
+def test_c2_si_bulk(fb, orc):
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=12, seed=20260001)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1])
+
+
+def test_c3_tio2(fb, orc):
+    from fortnet_b200 import synthetic
+    ds = synthetic.tio2(n_struct=3, seed=20260002)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
+    assert len(funcs) == 64
+    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1])
+
+
+def test_c5_dense_liquid_values(fb, orc):
+    """C5 shape at oracle size: rc = 8 A, ~150 neighbours, 128 G5 on the auto ladder; box edge
+    (15.4 A) < 2 rc, so atoms see several periodic images of the same neighbour."""
+    from fortnet_b200 import synthetic
+    ds = synthetic.dense_liquid(n_atoms=256, density_aa3=0.070, seed=99, n_struct=2)
+    funcs = fb.GFunctions.from_auto_scheme(8.0 * fb.BOHR_PER_AA, 2, 128)
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False)
+    acsf.calculate(0)
+    vals = acsf.features(0)
+    mx, mean = ctx.max_neighbors(0)
+    assert 120 < mean < 180, mean
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
+    assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("act", ["gaussian", "relu", "lrelu", "softplus", "bent", "atan", "sigmoid", "tanh", "linear"])
+@pytest.mark.parametrize("loss", ["mse", "rms", "mae", "mape"])
+def test_activations_and_losses(fb, orc, act, loss):
+    """every transfer function (transfer.F90) x every loss (loss.F90:217-281) on one small batch"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=3, seed=11)
+    ds.gtargets[:] = np.random.default_rng(5).uniform(1.0, 2.0, size=ds.gtargets.shape)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 5, 4)
+    _full_check(fb, orc, ds, funcs, [9, 7, 5, 1], act=act, loss=loss, forces=(loss == "mse"))
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def _mixed_functions(fb, rc, zs=None):
+    G = fb.GFunction
+    fs = [G("g1", rc), G("g2", rc, eta=0.3, rs=1.1), G("g2", 0.8 * rc, eta=1.7, rs=0.0), G("g3", rc, kappa=0.9),
+          G("g4", rc, xi=1.0, eta=0.05, lam=1.0), G("g4", rc, xi=2.5, eta=0.05, lam=-1.0),
+          G("g5", rc, xi=4.0, eta=0.02, lam=1.0), G("g5", 0.7 * rc, xi=1.5, eta=0.1, lam=-1.0),
+          G("g5", rc, xi=0.0, eta=0.02, lam=1.0)]
+    out = fb.GFunctions(fs)
+    if zs is not None:
+        out = out.resolve_species(zs)
+    return out
+
+
+def test_ragged_clusters_and_single_atoms(fb, orc):
+    """non-periodic structures of 1..40 atoms in one batch (prediction/** goldens are clusters);
+    a single atom has no neighbours -> all ACSF are 0 (before the z-score)"""
+    rng = np.random.default_rng(21)
+    natoms = [1, 2, 3, 17, 1, 40, 5, 33]
+    coords = np.concatenate([rng.uniform(0.0, 3.0 + 1.2 * n ** (1 / 3), size=(n, 3)) * fb.BOHR_PER_AA for n in natoms])
+    N = sum(natoms)
+    atnum = rng.choice([1, 8], size=N).astype(np.int32)
+    atnum[0] = 1
+    atnum[1] = 8
+    ds = fb.Dataset.build(natoms, coords, np.zeros(len(natoms), np.int32), np.zeros((len(natoms), 3, 3)), atnum,
+                          gtargets=rng.normal(size=(len(natoms), 1)), weights=rng.integers(1, 4, size=len(natoms)),
+                          atomic_weights=rng.uniform(0.5, 1.5, size=N), atomic_numbers=[1, 8])
+    funcs = _mixed_functions(fb, 3.0 * fb.BOHR_PER_AA, [1, 8])
+    _full_check(fb, orc, ds, funcs, [len(funcs), 6, 4, 1], act="sigmoid")
+
+
+def test_atomic_and_multiple_targets(fb, orc):
+    """two global + two atomic targets (bothTargets goldens): nOut = 4, forces have 3*nOut columns"""
+    rng = np.random.default_rng(22)
+    natoms = [9, 14, 6]
+    N = sum(natoms)
+    L = 9.0 * fb.BOHR_PER_AA
+    lat = np.stack([np.eye(3) * L] * 3)
+    coords = np.concatenate([rng.uniform(0, L, size=(n, 3)) for n in natoms])
+    atnum = rng.choice([14, 6], size=N).astype(np.int32)
+    ds = fb.Dataset.build(natoms, coords, np.ones(3, np.int32), lat, atnum, gtargets=rng.normal(size=(3, 2)),
+                          atargets=rng.normal(size=(N, 2)), atomic_weights=rng.uniform(0.5, 1.5, size=N),
+                          atomic_numbers=[14, 6])
+    funcs = _mixed_functions(fb, 4.0 * fb.BOHR_PER_AA)
+    _full_check(fb, orc, ds, funcs, [len(funcs), 5, 4], act="tanh")
+
+
+def test_thin_triclinic_and_unfolded_cells(fb, orc):
+    """cell edges < rc (an atom sees several images of a neighbour and of itself), triclinic
+    lattices, and coordinates outside the unit cell (the reference does not fold them).  Values
+    only: the reference's dense derivative overwrites image contributions when an edge < 2 rc
+    (acsf.F90:918), so forces parity is undefined here."""
+    rng = np.random.default_rng(23)
+    rc = 4.0 * fb.BOHR_PER_AA
+    lats = np.array([
+        [[0.6 * rc, 0, 0], [0, 2.3 * rc, 0], [0, 0, 1.1 * rc]],
+        [[2.1 * rc, 0, 0], [0.7 * rc, 1.9 * rc, 0], [-0.4 * rc, 0.5 * rc, 2.2 * rc]],
+        [[0.9 * rc, 0.2 * rc, 0], [0, 0.8 * rc, 0.1 * rc], [0.3 * rc, 0, 0.7 * rc]],
+        [[3.0 * rc, 0, 0], [0, 3.0 * rc, 0], [0, 0, 3.0 * rc]],
+    ])
+    natoms = [3, 20, 1, 30]
+    coords = []
+    for s, n in enumerate(natoms):
+        frac = rng.uniform(-1.5, 2.5, size=(n, 3)) if s != 3 else rng.uniform(0.0, 1.0, size=(n, 3))
+        if s == 3:
+            frac[0] = [1.0, 0.0, 1.0]          # fractional coordinate exactly 1.0 stays unfolded in the reference
+        coords.append(frac @ lats[s])
+    coords = np.concatenate(coords)
+    N = sum(natoms)
+    atnum = rng.choice([22, 8], size=N).astype(np.int32)
+    ds = fb.Dataset.build(natoms, coords, np.ones(4, np.int32), lats, atnum, gtargets=rng.normal(size=(4, 1)),
+                          atomic_numbers=[22, 8])
+    funcs = _mixed_functions(fb, rc, [22, 8])
+    _full_check(fb, orc, ds, funcs, [len(funcs), 4, 1], forces=False)
+
+
+def test_atom_id_scaling_and_external_features(fb, orc):
+    """q_i q_j prefactors from an external-feature row (acsf.F90:836-840,1003-1052) and external
+    columns appended to the ACSF block (features.F90:227-241)"""
+    from fortnet_b200 import synthetic
+    rng = np.random.default_rng(24)
+    base = synthetic.si_bulk(n_struct=2, seed=5)
+    ext = rng.uniform(0.5, 1.5, size=(base.n_atoms, 3))
+    ds = fb.Dataset.build(np.diff(base.offsets), base.coords, base.periodic, base.latvecs, base.atnum,
+                          gtargets=base.gtargets, ext=ext, atomic_numbers=[14])
+    rc = 4.0 * fb.BOHR_PER_AA
+    G = fb.GFunction
+    funcs = fb.GFunctions.from_auto_scheme(rc, 4, 4, atomid=2)
+    funcs.append(fb.GFunctions([G("g4", rc, xi=2.0, eta=0.03, lam=1.0, atomid=1), G("g1", rc, atomid=3), G("g3", rc, kappa=0.5)]))
+    fd = funcs.asdicts()
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False, ext_indices=[2, 0])
+    acsf.calculate(0)
+    vals = acsf.features(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, ext=ds.ext)
+    assert vals.shape == (ds.n_atoms, len(funcs) + 2)
+    assert np.allclose(vals[:, :len(funcs)], ref, rtol=1e-10, atol=1e-12), _md(vals[:, :len(funcs)], ref)
+    assert np.array_equal(vals[:, len(funcs):], ext[:, [2, 0]])
+    ctx.close()
+
+
+def test_empty_and_unconfigured_calls_fail_loudly(fb):
+    """error convention of the boundary: non-zero return + message, never a silent fallback"""
+    from fortnet_b200 import synthetic
+    ctx = fb.Context()
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 4, 4)
+    acsf = fb.Acsf(ctx, funcs)
+    with pytest.raises(fb.FnetGpuError):
+        acsf.calculate(3)                      # empty slot
+    with pytest.raises(fb.FnetGpuError):
+        fb.Bpnn(ctx, [8, 4, 1], 1, "nope")
+    ds = synthetic.si_bulk(n_struct=1, seed=2)
+    ctx.upload(0, ds)
+    acsf.calculate(0)
+    net = fb.Bpnn(ctx, [9, 4, 1], 1, "tanh")     # input width != number of features
+    net.set_params(np.zeros((1, _ntot([9, 4, 1]))))
+    with pytest.raises(fb.FnetGpuError):
+        net.predict_batch(0)
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the full C2 size (640k atoms) -- no oracle involved
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_full(fb):
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=10000, seed=20260001)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+    return ds, funcs
+
+
+def test_full_size_invariances(fb, c2_full):
+    """ACSF are invariant under rigid translation (incl. across the cell boundary) and atom
+    permutation within a structure; the gradient is invariant under both as well."""
+    ds, funcs = c2_full
+    dims = [32, 20, 20, 1]
+    wb = np.random.default_rng(7).uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False)
+    acsf.calculate(0)
+    f0 = acsf.features(0)
+    assert np.isfinite(f0).all() and f0.min() >= 0.0            # G2/G5 sums of non-negative terms
+    z = fb.Acsf(ctx, funcs, standardize=True)
+    z.calculate(0)
+    zf = z.features(0)
+    assert np.allclose(zf.mean(0), 0.0, atol=1e-9) and np.allclose(zf.std(0), 1.0, atol=1e-9)
+    net = fb.Bpnn(ctx, dims, 1, "tanh")
+    net.set_params(wb)
+    dd0, loss0 = net.update_gradients(0, "mse")
+    # translate every structure by its own vector, permute atoms within each structure
+    rng = np.random.default_rng(31)
+    n = 64
+    shift = rng.uniform(-20.0, 20.0, size=(ds.n_struct, 1, 3))
+    perm = np.argsort(rng.random((ds.n_struct, n)), axis=1)
+    c = ds.coords.reshape(ds.n_struct, n, 3) + shift
+    c = np.take_along_axis(c, perm[:, :, None], axis=1)
+    ctx.update_coords(0, c.reshape(-1, 3), ds.latvecs)
+    acsf.calculate(0)
+    f1 = acsf.features(0).reshape(ds.n_struct, n, -1)
+    f0p = np.take_along_axis(f0.reshape(ds.n_struct, n, -1), perm[:, :, None], axis=1)
+    assert np.allclose(f1, f0p, rtol=1e-9, atol=1e-10), _md(f1, f0p)
+    z.calculate(0)
+    dd1, loss1 = net.update_gradients(0, "mse")
+    assert np.allclose(dd1, dd0, rtol=1e-8, atol=1e-9 * np.abs(dd0).max()), _md(dd1, dd0)
+    assert abs(loss1 - loss0) <= 1e-9 * abs(loss0)
+    ctx.close()
+
+
+def test_full_size_gradient_linearity_and_determinism(fb, c2_full):
+    """dd is linear in the datapoint weights (bpnn.F90:443-450): dd(w) + dd(w') = dd(w + w');
+    two runs on the same input are bit-identical (fixed-order reductions, no float atomics)."""
+    ds, funcs = c2_full
+    dims = [32, 20, 20, 1]
+    wb = np.random.default_rng(7).uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    rng = np.random.default_rng(32)
+    w1 = rng.integers(1, 5, size=ds.n_struct).astype(np.int32)
+    w2 = rng.integers(1, 5, size=ds.n_struct).astype(np.int32)
+    zp = None
+    out = []
+    for w in (w1, w2, w1 + w2, w1 + w2):
+        ctx = fb.Context()
+        d = fb.Dataset.build(np.diff(ds.offsets), ds.coords, ds.periodic, ds.latvecs, ds.atnum, weights=w,
+                             gtargets=ds.gtargets, atomic_numbers=[14])
+        ctx.upload(0, d)
+        acsf = fb.Acsf(ctx, funcs, standardize=True)
+        acsf.calculate(0, zprec=zp)
+        if zp is None:
+            zp = acsf.zprec.copy()
+        net = fb.Bpnn(ctx, dims, 1, "tanh")
+        net.set_params(wb)
+        out.append(net.update_gradients(0, "mse")[0])
+        ctx.close()
+    assert np.array_equal(out[2], out[3])
+    assert np.allclose(out[0] + out[1], out[2], rtol=1e-10, atol=1e-12 * np.abs(out[2]).max()), _md(out[0] + out[1], out[2])
+
+
+def test_full_size_forces_sum_rule_and_finite_difference(fb):
+    """C4 shape (TiO2-like 192-atom cells, forces on): the forces of every structure sum to zero
+    (translation invariance), and F = -dE/dR against a central finite difference of the predicted
+    energy for a few displaced atoms."""
+    from fortnet_b200 import synthetic
+    ds = synthetic.tio2(n_struct=600, seed=20260004)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
+    dims = [64, 32, 32, 32, 1]
+    wb = np.random.default_rng(7).uniform(-0.5, 0.5, size=(2, _ntot(dims)))
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    net = fb.Bpnn(ctx, dims, 2, "tanh")
+    net.set_params(wb)
+    f = net.forces(0)
+    fs = f.reshape(ds.n_struct, 192, 3).sum(1)
+    assert np.abs(fs).max() <= 1e-9 * np.abs(f).max(), np.abs(fs).max()
+    h = 1e-4
+    rng = np.random.default_rng(33)
+    for _ in range(3):
+        s = int(rng.integers(ds.n_struct))
+        i = int(ds.offsets[s] + rng.integers(192))
+        c = int(rng.integers(3))
+        e = []
+        for sgn in (+1, -1):
+            cc = ds.coords.copy()
+            cc[i, c] += sgn * h
+            ctx.update_coords(0, cc, ds.latvecs)
+            acsf.calculate(0)
+            raw = net.predict_batch(0)
+            e.append(raw[ds.offsets[s]:ds.offsets[s + 1], 0].sum())
+        fd = -(e[0] - e[1]) / (2 * h)
+        assert abs(fd - f[i, c]) <= 1e-6 * max(1.0, abs(f[i, c])), (fd, f[i, c])
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# FP32 mode: documented bound
+# ---------------------------------------------------------------------------------------------
+def test_fp32_mode_bound(fb, orc):
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=16, seed=20260001)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+    dims = [32, 20, 20, 1]
+    wb = np.random.default_rng(7).uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
+    mu, sg = orc.zscore_stats(ds.offsets, ref, ds.weights)
+    zref = orc.zscore_apply(ref, mu, sg)
+    dd_o, raw_o = orc.grad(ds.offsets, zref, ds.globalsp, dims, "tanh", wb, "mse", ds.weights, ds.atomic_weights,
+                           ds.gtargets, ds.atargets)
+    ctx = fb.Context(precision=32)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    z = acsf.features(0)
+    # features are computed in FP64 and stored as FP32: half an ulp of the stored value
+    assert np.allclose(z, zref, rtol=1e-6, atol=1e-6), _md(z, zref)
+    net = fb.Bpnn(ctx, dims, 1, "tanh")
+    net.set_params(wb)
+    raw = net.predict_batch(0)
+    assert np.abs(raw - raw_o).max() <= 2e-5 * max(1.0, np.abs(raw_o).max()), _md(raw, raw_o)
+    dd, lossv = net.update_gradients(0, "mse")
+    assert np.abs(dd - dd_o).max() <= 1e-4 * np.abs(dd_o).max(), _md(dd, dd_o)
+    ctx.close()
