@@ -206,7 +206,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_struct = args.structures or (10000 if args.workload == "c2" else 20000)
     ds, funcs, dims, wb, label = workload(args.workload, n_struct, seed_shift=1000 * rank)

@@ -99,9 +99,9 @@ def test_c3_tio2(fb, orc):
 
 def test_c5_dense_liquid_values(fb, orc):
     """C5 shape at oracle size: rc = 8 A, ~150 neighbours, 128 G5 on the auto ladder; box edge
-    (15.4 A) < 2 rc, so atoms see several periodic images of the same neighbour."""
+    (12.2 A) < 2 rc, so atoms see several periodic images of the same neighbour."""
     from fortnet_b200 import synthetic
-    ds = synthetic.dense_liquid(n_atoms=256, density_aa3=0.070, seed=99, n_struct=2)
+    ds = synthetic.dense_liquid(n_atoms=128, density_aa3=0.070, seed=99, n_struct=1)
     funcs = fb.GFunctions.from_auto_scheme(8.0 * fb.BOHR_PER_AA, 2, 128)
     ctx = fb.Context()
     ctx.upload(0, ds)
@@ -176,7 +176,7 @@ def test_atomic_and_multiple_targets(fb, orc):
 
 def test_thin_triclinic_and_unfolded_cells(fb, orc):
     """cell edges < rc (an atom sees several images of a neighbour and of itself), triclinic
-    lattices, and coordinates outside the unit cell (the reference does not fold them).  Values
+    lattices, and coordinates outside the unit cell (the reference does not fold them; we do).  Values
     only: the reference's dense derivative overwrites image contributions when an edge < 2 rc
     (acsf.F90:918), so forces parity is undefined here."""
     rng = np.random.default_rng(23)
@@ -190,8 +190,14 @@ def test_thin_triclinic_and_unfolded_cells(fb, orc):
     natoms = [3, 20, 1, 30]
     coords = []
     for s, n in enumerate(natoms):
-        frac = rng.uniform(-1.5, 2.5, size=(n, 3)) if s != 3 else rng.uniform(0.0, 1.0, size=(n, 3))
-        if s == 3:
+        # The reference never folds coordinates and searches images in +-(floor(rc |b_k|) + 1)
+        # (latpointiter.F90:204-253), which finds every image only while the fractional coordinates of
+        # two atoms differ by less than 1 per axis (any reader output with 0 <= frac <= 1 does).  That is
+        # the parity domain: a window of width 1 anywhere in space, here shifted by whole lattice vectors.
+        if s != 3:
+            frac = rng.uniform(0.3, 1.3, size=(n, 3)) + np.array([3.0, -2.0, 5.0])
+        else:
+            frac = rng.uniform(0.0, 1.0, size=(n, 3))
             frac[0] = [1.0, 0.0, 1.0]          # fractional coordinate exactly 1.0 stays unfolded in the reference
         coords.append(frac @ lats[s])
     coords = np.concatenate(coords)
@@ -219,7 +225,7 @@ def test_atom_id_scaling_and_external_features(fb, orc):
     fd = funcs.asdicts()
     ctx = fb.Context()
     ctx.upload(0, ds)
-    acsf = fb.Acsf(ctx, funcs, standardize=False, ext_indices=[2, 0])
+    acsf = fb.Acsf(ctx, funcs, standardize=False, ext_indices=[3, 1])      # 1-based rows of extFeatures (features.F90:227-241)
     acsf.calculate(0)
     vals = acsf.features(0)
     ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, ext=ds.ext)
@@ -275,7 +281,10 @@ def test_full_size_invariances(fb, c2_full):
     z = fb.Acsf(ctx, funcs, standardize=True)
     z.calculate(0)
     zf = z.features(0)
-    assert np.allclose(zf.mean(0), 0.0, atol=1e-9) and np.allclose(zf.std(0), 1.0, atol=1e-9)
+    on = z.zprec[1] >= 1e-8                                      # sigma < 1e-8: feature left as it is (acsf.F90:505)
+    assert on.sum() >= 24
+    assert np.allclose(zf[:, on].mean(0), 0.0, atol=1e-9) and np.allclose(zf[:, on].std(0), 1.0, atol=1e-9)
+    assert np.array_equal(zf[:, ~on], f0[:, ~on])
     net = fb.Bpnn(ctx, dims, 1, "tanh")
     net.set_params(wb)
     dd0, loss0 = net.update_gradients(0, "mse")
