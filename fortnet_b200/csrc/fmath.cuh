@@ -74,27 +74,48 @@ FNET_HD int fnet_lo(double x) {
 }
 
 // exp(x) = 2^k * e^r, k = rint(x log2 e), r = x - k ln2 (two-part ln2), e^r by its degree-13
-// Taylor polynomial on |r| <= 0.3466 (truncation 4e-18 relative).
-FNET_HD double fnet_exp(double x) {
+// Taylor polynomial on |r| <= 0.3466 (truncation 4e-18 relative).  The polynomial is evaluated by
+// Estrin's scheme: 13 FMA + 3 MUL with a dependency depth of 4 instead of Horner's 13 -- the pair
+// loops run at ~5 warps per scheduler, so the length of the dependent DFMA chain, not the DFMA
+// count, decides how many issue slots stay empty (ncu: stall_wait 2.8 per issued instruction).
+template <bool ESTRIN>
+FNET_HD double fnet_exp_t(double x) {
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52: rint() through the adder
   const double tk = fma(x, FNET_EC(11), magic);
   const int k = fnet_lo(tk);
   const double kd = tk - magic;
   double r = fma(kd, FNET_EC(12), x);                      // ln2 high part: 32 significant bits
   r = fma(kd, FNET_EC(13), r);                             // ln2 low part
-  double p = FNET_EC(0);                                   // 1/13!
+  double p;
+  if (!ESTRIN) {
+    p = FNET_EC(0);                                        // 1/13!
 FNET_UNROLL
-  for (int i = 1; i <= 10; i++) p = fma(p, r, FNET_EC(i)); // 1/12! ... 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+    for (int i = 1; i <= 10; i++) p = fma(p, r, FNET_EC(i)); // 1/12! ... 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+  } else {
+  // c_k = 1/k!: c_k = FNET_EC(13 - k) for k = 3..13
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = 1.0 + r;
+  const double a1 = fma(FNET_EC(10), r, 0.5);
+  const double a2 = fma(FNET_EC(8), r, FNET_EC(9));
+  const double a3 = fma(FNET_EC(6), r, FNET_EC(7));
+  const double a4 = fma(FNET_EC(4), r, FNET_EC(5));
+  const double a5 = fma(FNET_EC(2), r, FNET_EC(3));
+  const double a6 = fma(FNET_EC(0), r, FNET_EC(1));
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
+  p = fma(c1, r8, c0);
+  }
   const double s = fnet_mk_double((k + 1023) << 20, 0);    // 2^k, k in [-1021, 1010]
   return (x < -708.0) ? 0.0 : p * s;
 }
 
 // log(x) = e ln2 + 2 atanh(s), x = 2^e m, m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1),
 // 2 atanh(s) = 2s (1 + z/3 + z^2/5 + ... + z^10/21), z = s^2 <= 0.02944 (truncation 6e-19 rel.).
-FNET_HD double fnet_log(double x) {
+template <bool ESTRIN>
+FNET_HD double fnet_log_t(double x) {
   int hi = fnet_hi(x);
   const int lo = fnet_lo(x);
   int e = (hi >> 20) - 1023;
@@ -105,20 +126,31 @@ FNET_HD double fnet_log(double x) {
   const double f = m - 1.0, d = m + 1.0;
 #ifdef __CUDA_ARCH__
   double rc;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));   // ~2^-23
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));   // relative error e0 ~ 2^-20
   double er = fma(-d, rc, 1.0);
-  rc = fma(rc, er, rc);
-  er = fma(-d, rc, 1.0);
-  rc = fma(rc, er, rc);                                     // ~2^-92
+  rc = fma(rc, er, rc);                                     // e1 = e0^2
   double s = f * rc;
-  s = fma(fma(-d, s, f), rc, s);                            // correctly rounded up to the last bit or so
+  s = fma(fma(-d, s, f), rc, s);                            // residual step: (f/d)(1 - e1^2), last bit or so
 #else
   const double s = f / d;
 #endif
   const double z = s * s;
-  double q = FNET_LC(0);                                   // 1/21
+  double q;
+  if (!ESTRIN) {
+    q = FNET_LC(0);                                        // 1/21
 FNET_UNROLL
-  for (int i = 1; i <= 9; i++) q = fma(q, z, FNET_LC(i));  // 1/19 ... 1/3
+    for (int i = 1; i <= 9; i++) q = fma(q, z, FNET_LC(i)); // 1/19 ... 1/3
+  } else {
+  // d_k = 1/(2k+3) = FNET_LC(9 - k), Estrin: depth 4 instead of 9
+  const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  const double a0 = fma(FNET_LC(8), z, FNET_LC(9));
+  const double a1 = fma(FNET_LC(6), z, FNET_LC(7));
+  const double a2 = fma(FNET_LC(4), z, FNET_LC(5));
+  const double a3 = fma(FNET_LC(2), z, FNET_LC(3));
+  const double a4 = fma(FNET_LC(0), z, FNET_LC(1));
+  const double b0 = fma(a1, z2, a0), b1 = fma(a3, z2, a2);
+  q = fma(a4, z8, fma(b1, z4, b0));
+  }
   const double s2 = s + s;
   const double ed = (double)e;
   // e*ln2_hi is exact (ln2_hi has 32 significant bits, |e| < 2^11)
@@ -127,6 +159,16 @@ FNET_UNROLL
   res = fma(ed, FNET_LC(11), res);
   return tiny ? -INFINITY : res;
 }
+
+// Default entry points: Horner where registers are the scarce resource (the ACSF pair loops run at
+// 96 registers / 5 CTAs per SM: Estrin's extra live values spill there and cost 14 %), Estrin
+// where latency is (the subnetwork kernels: tanh / sigmoid epilogues, -22 % on the gradient kernel).
+#ifndef FNET_ACSF_ESTRIN
+#define FNET_ACSF_ESTRIN 0
+#endif
+FNET_HD double fnet_exp(double x) { return fnet_exp_t<FNET_ACSF_ESTRIN != 0>(x); }
+FNET_HD double fnet_log(double x) { return fnet_log_t<FNET_ACSF_ESTRIN != 0>(x); }
+FNET_HD double fnet_exp_lat(double x) { return fnet_exp_t<true>(x); }
 
 // 1/d for d >= 1 (no zero / inf / denormal handling): hardware seed + two Newton steps + a
 // residual correction; within 1 ulp.
@@ -148,7 +190,7 @@ FNET_HD double fnet_rcp(double d) {
 // tanh(x) = 1 - 2 / (exp(2x) + 1); |x| < 2^-9 uses x - x^3/3 (relative error < 2e-12 at the
 // switch-over from the truncation, ~1e-13 from the cancellation in the closed form above it).
 FNET_HD double fnet_tanh(double x) {
-  const double e2 = fnet_exp(fmin(x + x, 700.0));
+  const double e2 = fnet_exp_lat(fmin(x + x, 700.0));
   const double big = 1.0 - 2.0 * fnet_rcp(e2 + 1.0);
   const double x2 = x * x;
   const double small = fma(x * x2, fma(x2, 0.13333333333333333, -0.33333333333333331), x);

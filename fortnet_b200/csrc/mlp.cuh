@@ -29,13 +29,13 @@ template <typename real> __device__ __forceinline__ real act_d(int id, real x, r
 // lib_nn/transfer.F90:54-342.  act_d receives both the argument x and the activation a = f(x).
 template <> __device__ __forceinline__ double act_f<double>(int id, double x) {
   switch (id) {
-    case FNETGPU_ACT_GAUSSIAN: return fnet_exp(-x * x);
+    case FNETGPU_ACT_GAUSSIAN: return fnet_exp_lat(-x * x);
     case FNETGPU_ACT_RELU: return fmax(0.0, x);
     case FNETGPU_ACT_LRELU: return fmax(0.01 * x, x);
     case FNETGPU_ACT_SOFTPLUS: return log(1.0 + exp(x));
     case FNETGPU_ACT_BENT: return (sqrt(x * x + 1.0) - 1.0) / 2.0 + x;
     case FNETGPU_ACT_ATAN: return atan(x);
-    case FNETGPU_ACT_SIGMOID: return fnet_rcp(1.0 + fnet_exp(fmin(-x, 700.0)));
+    case FNETGPU_ACT_SIGMOID: return fnet_rcp(1.0 + fnet_exp_lat(fmin(-x, 700.0)));
     case FNETGPU_ACT_HEAVISIDE: return x > 0.0 ? 1.0 : 0.0;
     case FNETGPU_ACT_TANH: return fnet_tanh(x);
     default: return x;
