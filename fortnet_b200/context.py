@@ -35,9 +35,10 @@ def _i(a):
 
 
 class Context:
-    """One GPU.  precision 64 (parity mode, default) or 32."""
+    """One GPU.  precision 64 (parity mode, default) or 32.  acsf_path "auto" (small structures:
+    whole-structure / minimum-image neighbour search, else the cell list) or "cells"."""
 
-    def __init__(self, device=-1, precision=64, deterministic=True):
+    def __init__(self, device=-1, precision=64, deterministic=True, acsf_path="auto"):
         self._lib = lib()
         h = C.c_void_p()
         rc = self._lib.fnetgpu_init(C.byref(h), C.c_int(device), C.c_int(precision), C.c_int(int(deterministic)))
@@ -45,6 +46,10 @@ class Context:
             raise FnetGpuError(self._lib.fnetgpu_last_error(None).decode())
         self._h = h
         self.precision = precision
+        if acsf_path not in ("auto", "cells"):
+            raise ValueError("acsf_path must be 'auto' or 'cells'")
+        if acsf_path == "cells":
+            self._check(self._lib.fnetgpu_acsf_path_set(self._h, C.c_int(1)))
         self.n_feat = {}
         self.n_atoms = {}
         self.n_struct = {}
@@ -107,6 +112,10 @@ class Context:
                 out[name.decode()] = dict(ms_total=ms.value, launches=int(n.value))
             k += 1
         return out
+
+    def acsf_path(self, slot):
+        """path of the last ACSF launch: 0/1 cell list (direct/staged), 2 whole structure, -1 none"""
+        return int(self._lib.fnetgpu_acsf_path_get(self._h, C.c_int(slot)))
 
     def max_neighbors(self, slot):
         m, mean = C.c_int(), C.c_double()

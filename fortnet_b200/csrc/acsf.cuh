@@ -45,9 +45,69 @@ __host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F) {
   b += (size_t)((F + 1) & ~1) * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
-// CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates
-__host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC) {
-  return (size_t)capC * sizeof(CRec) + ((sizeof(StageTabs) + 15) & ~(size_t)15);
+// CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates (PATH 1) or the
+// structure's lattice (PATH 2)
+__host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC, int path = 1) {
+  const size_t tail = path == 2 ? sizeof(StructGeom) : sizeof(StageTabs);
+  return (size_t)capC * sizeof(CRec) + ((tail + 15) & ~(size_t)15);
+}
+
+// Where the central atoms and their candidates come from.  PATH 0: cell list, candidates read
+// from global memory; PATH 1: cell list, candidates of the bin staged per CTA; PATH 2: whole
+// structure staged per CTA, minimum image (cells.cuh).
+#define FNET_PATH_DIRECT 0
+#define FNET_PATH_STAGED 1
+#define FNET_PATH_STRUCT 2
+struct GeomArgs {                     // device pointers, passed by value to the kernels
+  const int *binStruct; const StructInfo *sinfo; const int *cellStart; const CRec *crec;      // PATH 0 / 1
+  const int *offsets; const double *coords; const double *lat; const int *periodic; const int *atnum;   // PATH 2
+};
+struct CtaGeom {                      // per-CTA view produced by acsf_cta_prologue
+  const StructInfo *S; BinPos bp; const int *cellStart; const CRec *crec;
+  const CRec *cand; int nCand; const StructGeom *sg;
+  int a0, a1, first;                  // central atoms [a0, a1): slots of crec (PATH 0/1) or atoms (PATH 2, first = atomBeg)
+};
+
+// Splits the CTA's bin (or structure) over blockIdx.y and stages the candidates.  Returns false
+// when this CTA has nothing to do (or on overflow, flagged for the host).
+template <int PATH>
+__device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit, double rcMax, int capC,
+                                                  unsigned char *smem_raw, int *__restrict__ flags, CtaGeom &c,
+                                                  unsigned char *&wbase) {
+  c.S = nullptr; c.cellStart = G.cellStart; c.crec = G.crec; c.cand = (const CRec *)smem_raw; c.nCand = 0; c.sg = nullptr;
+  c.first = 0;
+  wbase = smem_raw;
+  if (PATH == FNET_PATH_STRUCT) {
+    const int st = blockIdx.x;
+    const int beg = G.offsets[st], end = G.offsets[st + 1];
+    const int per = (end - beg + nSplit - 1) / nSplit;
+    c.a0 = beg + blockIdx.y * per; c.a1 = min(end, c.a0 + per); c.first = beg;
+    if (c.a0 >= c.a1) return false;
+    StructGeom *sg = (StructGeom *)(smem_raw + (size_t)capC * sizeof(CRec));
+    c.nCand = stage_structure(st, beg, end - beg, G.coords, G.atnum, G.lat, G.periodic, rcMax, (CRec *)smem_raw, capC, sg, flags);
+    c.sg = sg;
+    if (c.nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], -c.nCand); return false; }
+    wbase += acsf_cta_prefix_bytes(capC, 2);
+    return true;
+  }
+  const int bin = blockIdx.x;
+  const int beg = G.cellStart[bin], end = G.cellStart[bin + 1];
+  const int per = (end - beg + nSplit - 1) / nSplit;
+  c.a0 = beg + blockIdx.y * per; c.a1 = min(end, c.a0 + per);
+  if (c.a0 >= c.a1) return false;
+  c.S = &G.sinfo[G.binStruct[bin]];
+  c.bp = bin_pos(*c.S, bin);
+  if (PATH == FNET_PATH_STAGED) {
+    StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
+    c.nCand = stage_candidates(*c.S, c.bp, G.cellStart, G.crec, (CRec *)smem_raw, capC, tabs);
+    if (c.nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], c.nCand == -1 ? 0x7fffffff : -c.nCand); return false; }
+    wbase += acsf_cta_prefix_bytes(capC, 1);
+  }
+  return true;
+}
+template <int PATH>
+__device__ __forceinline__ CRec central_atom(const CtaGeom &c, int slot) {
+  return PATH == FNET_PATH_STRUCT ? c.cand[slot - c.first] : c.crec[slot];
 }
 
 __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap, int F) {
@@ -74,11 +134,9 @@ __device__ __forceinline__ int species_code(const AcsfTables &tab, int z) {
 // Gathers the neighbours of the central atom `me` (within rcMax) into the warp's shared memory,
 // sorted by species code [code 0 .. nCodes-1 | other | self-images]; returns n (or -needed on
 // overflow).
-template <bool STAGED>
-__device__ __forceinline__ int gather_neighbors(const CRec &me, const StructInfo &S, const BinPos &bp,
-                                                const AcsfTables &tab, const int *__restrict__ cellStart,
-                                                const CRec *__restrict__ crec, const CRec *__restrict__ cand,
-                                                int nCand, int cap, WarpSmem &w) {
+template <int PATH>
+__device__ __forceinline__ int gather_neighbors(const CRec &me, const CtaGeom &cg, const AcsfTables &tab, int cap,
+                                                WarpSmem &w) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const bool sorted = tab.nCodes > 0;
@@ -88,8 +146,7 @@ __device__ __forceinline__ int gather_neighbors(const CRec &me, const StructInfo
   int *gj = sorted ? (int *)w.rinv : w.idx;
   int *gc = (int *)w.rinv + cap;          // species codes (sorted path only)
   int n = 0;
-  auto take = [&](bool valid, double x, double y, double z, int j, int zs) {
-    const double dx = x - me.x, dy = y - me.y, dz = z - me.z;
+  auto take = [&](bool valid, double dx, double dy, double dz, int j, int zs) {
     const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, j, zs, me.idx);
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     const int pos = n + __popc(m & lt);
@@ -99,8 +156,9 @@ __device__ __forceinline__ int gather_neighbors(const CRec &me, const StructInfo
     }
     n += __popc(m);
   };
-  if (STAGED) for_each_candidate_staged(cand, nCand, take);
-  else for_each_candidate_direct(S, bp, cellStart, crec, take);
+  if (PATH == FNET_PATH_STRUCT) for_each_candidate_struct(cg.cand, cg.nCand, cg.sg, me, take);
+  else if (PATH == FNET_PATH_STAGED) for_each_candidate_staged(cg.cand, cg.nCand, me, take);
+  else for_each_candidate_direct(*cg.S, cg.bp, cg.cellStart, cg.crec, me, take);
   if (n > cap) return -n;
   __syncwarp();
   if (sorted) {
@@ -391,37 +449,23 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
   }
 }
 
-template <typename real, int NS, bool STAGED>
+template <typename real, int NS, int PATH>
 __global__ void __launch_bounds__(128, (NS <= 2 ? FNET_ACSF_MINB : 3))
-k_acsf(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restrict__ sinfo,
-       const int *__restrict__ cellStart, const CRec *__restrict__ crec, int nExt,
-       const double *__restrict__ ext, AcsfTables tab, int cap, int capC, real *__restrict__ feat,
-       int nFeat, const double *__restrict__ zprec, int nExtSel, const int *__restrict__ extIdx,
-       int *__restrict__ flags) {
+k_acsf(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, int cap, int capC,
+       real *__restrict__ feat, int nFeat, const double *__restrict__ zprec, int nExtSel,
+       const int *__restrict__ extIdx, int *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int bin = blockIdx.x;
-  const int beg = cellStart[bin], end = cellStart[bin + 1];
-  const int per = (end - beg + nSplit - 1) / nSplit;
-  const int a0 = beg + blockIdx.y * per, a1 = min(end, a0 + per);
-  if (a0 >= a1) return;
-  const StructInfo &S = sinfo[binStruct[bin]];
-  const BinPos bp = bin_pos(S, bin);
-  CRec *cand = (CRec *)smem_raw;
-  int nCand = 0;
-  unsigned char *wbase = smem_raw;
-  if (STAGED) {
-    StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
-    nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
-    if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
-    wbase += acsf_cta_prefix_bytes(capC);
-  }
+  CtaGeom cg;
+  unsigned char *wbase;
+  if (!acsf_cta_prologue<PATH>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;
+  const int a0 = cg.a0, a1 = cg.a1;
   WarpSmem w = carve_warp_smem(wbase + (size_t)wib * acsf_warp_smem_bytes(cap, tab.F), cap, tab.F);
   for (int slot = a0 + wib; slot < a1; slot += nw) {
-    const CRec me = crec[slot];
+    const CRec me = central_atom<PATH>(cg, slot);
     const int i = me.idx;
-    const int n = gather_neighbors<STAGED>(me, S, bp, tab, cellStart, crec, cand, nCand, cap, w);
+    const int n = gather_neighbors<PATH>(me, cg, tab, cap, w);
     if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
     radial_groups(i, n, tab, w, nExt, ext);
     for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) angular_pass<NS>(i, n, tab, &tab.apasses[pi_], w, nExt, ext);

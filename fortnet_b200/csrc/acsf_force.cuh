@@ -30,41 +30,27 @@ __device__ __forceinline__ double dcutoff_fn(double rr, double qq, double rc, do
   return -0.5 * qq * (3.14159265358979323846 * invrc) * sinpi(rr * invrc);
 }
 
-template <bool STAGED>
+template <int PATH>
 __global__ void __launch_bounds__(128)
-k_acsf_force(int nSplit, const int *__restrict__ binStruct, const StructInfo *__restrict__ sinfo,
-             const int *__restrict__ cellStart, const CRec *__restrict__ crec, int nExt,
-             const double *__restrict__ ext, AcsfTables tab, int cap, int capC, const double *__restrict__ dEdG,
-             int nOut, const double *__restrict__ zprec, double *__restrict__ forces,
-             int *__restrict__ flags) {
+k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, int cap, int capC,
+             const double *__restrict__ dEdG, int nOut, const double *__restrict__ zprec,
+             double *__restrict__ forces, int *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int kt = blockIdx.z;                        // target index
-  const int bin = blockIdx.x;
-  const int beg = cellStart[bin], end = cellStart[bin + 1];
-  const int per = (end - beg + nSplit - 1) / nSplit;
-  const int a0 = beg + blockIdx.y * per, a1 = min(end, a0 + per);
-  if (a0 >= a1) return;
-  const StructInfo &S = sinfo[binStruct[bin]];
-  const BinPos bp = bin_pos(S, bin);
-  CRec *cand = (CRec *)smem_raw;
-  int nCand = 0;
-  unsigned char *wbase = smem_raw;
-  if (STAGED) {
-    StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
-    nCand = stage_candidates(S, bp, cellStart, crec, cand, capC, tabs);
-    if (nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], nCand == -1 ? 0x7fffffff : -nCand); return; }
-    wbase += acsf_cta_prefix_bytes(capC);
-  }
+  CtaGeom cg;
+  unsigned char *wbase;
+  if (!acsf_cta_prologue<PATH>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;
+  const int a0 = cg.a0, a1 = cg.a1;
   unsigned char *base = wbase + (size_t)wib * force_warp_smem_bytes(cap, tab.F);
   WarpSmem w = carve_warp_smem(base, cap, tab.F);
   double *extra = (double *)(base + acsf_warp_smem_bytes(cap, tab.F));
   double *dE = extra, *fx = extra + cap, *fy = extra + 2 * cap, *fz = extra + 3 * cap;
   for (int slot = a0 + wib; slot < a1; slot += nw) {
-  const CRec me = crec[slot];
+  const CRec me = central_atom<PATH>(cg, slot);
   const int i = me.idx;
-  const int n = gather_neighbors<STAGED>(me, S, bp, tab, cellStart, crec, cand, nCand, cap, w);
+  const int n = gather_neighbors<PATH>(me, cg, tab, cap, w);
   if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
   for (int t = lane; t < n; t += 32) {
     const double ri = w.rinv[t];

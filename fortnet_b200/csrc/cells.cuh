@@ -237,11 +237,12 @@ __device__ __forceinline__ int stage_candidates(const StructInfo &S, const BinPo
   return total;
 }
 
-// Warp-cooperative enumeration of the candidates around a central atom.  visit(valid, x, y, z,
-// idx, zs) is called with all 32 lanes converged; the candidate position already contains the
-// lattice shift and zs carries FNET_SHIFT_FLAG for periodic images.
+// Warp-cooperative enumeration of the candidates around the central atom `me`.  visit(valid, dx,
+// dy, dz, idx, zs) is called with all 32 lanes converged; (dx, dy, dz) is the displacement from
+// the central atom to the candidate image and zs carries FNET_SHIFT_FLAG for periodic images.
 template <typename Visit>
-__device__ __forceinline__ void for_each_candidate_staged(const CRec *__restrict__ cand, int total, Visit visit) {
+__device__ __forceinline__ void for_each_candidate_staged(const CRec *__restrict__ cand, int total, const CRec &me,
+                                                          Visit visit) {
   const int lane = threadIdx.x & 31;
   for (int base = 0; base < total; base += 32) {
     const int t = base + lane;
@@ -249,7 +250,7 @@ __device__ __forceinline__ void for_each_candidate_staged(const CRec *__restrict
     CRec r;
     r.x = 0.0; r.y = 0.0; r.z = 0.0; r.idx = -1; r.zs = 0;
     if (valid) r = cand[t];
-    visit(valid, r.x, r.y, r.z, r.idx, r.zs);
+    visit(valid, r.x - me.x, r.y - me.y, r.z - me.z, r.idx, r.zs);
   }
 }
 
@@ -257,7 +258,8 @@ __device__ __forceinline__ void for_each_candidate_staged(const CRec *__restrict
 template <typename Visit>
 __device__ __forceinline__ void for_each_candidate_direct(const StructInfo &S, const BinPos &p,
                                                           const int *__restrict__ cellStart,
-                                                          const CRec *__restrict__ crec, Visit visit) {
+                                                          const CRec *__restrict__ crec, const CRec &me,
+                                                          Visit visit) {
   const int lane = threadIdx.x & 31;
   for (int cbase = 0; cbase < p.ncells; cbase += 32) {
     const NCell nc = neighbor_cell(S, p, cbase + lane, cellStart);
@@ -273,8 +275,93 @@ __device__ __forceinline__ void for_each_candidate_direct(const StructInfo &S, c
         r.x += nc.sx; r.y += nc.sy; r.z += nc.sz;
         if (nc.shifted) r.zs |= FNET_SHIFT_FLAG;
       }
-      visit(valid, r.x, r.y, r.z, r.idx, r.zs);
+      visit(valid, r.x - me.x, r.y - me.y, r.z - me.z, r.idx, r.zs);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole-structure path for small structures (the usual training-set shape: tens to a few
+// hundred atoms): no cell list at all.  One CTA stages every atom of its structure in shared
+// memory; each central atom tests all of them and picks the periodic image by the minimum-image
+// convention  d <- d - lat * rint(inv * d).  That is exact (the unique image within rc) when every
+// lattice-plane spacing h_k >= 2 rc: an image with |d| <= rc has |inv_k . d| <= rc / h_k <= 1/2.
+// The same bound excludes periodic images of the central atom itself.  stage_structure checks it
+// and raises flags[4] otherwise (the host then falls back to the cell list).  Clusters: no wrap.
+// ------------------------------------------------------------------------------------------
+#define FNET_STRUCT_MAX_ATOMS 256    // candidates per central atom grow with the structure: beyond this the cell list wins
+
+struct __align__(16) StructGeom {
+  double lat[9];     // lat[3*k+c]: component c of lattice vector k
+  double inv[9];     // fractional s_k = sum_c inv[3*k+c] * d_c
+  int periodic, pad;
+};
+
+__device__ __forceinline__ int stage_structure(int st, int beg, int nAt, const double *__restrict__ coords,
+                                               const int *__restrict__ atnum, const double *__restrict__ lat,
+                                               const int *__restrict__ periodic, double rc, CRec *__restrict__ cand,
+                                               int capC, StructGeom *__restrict__ g, int *__restrict__ flags) {
+  if (nAt > capC) return -nAt;
+  for (int t = threadIdx.x; t < nAt; t += blockDim.x) {
+    const size_t j = (size_t)beg + t;
+    CRec r;
+    r.x = coords[3 * j]; r.y = coords[3 * j + 1]; r.z = coords[3 * j + 2];
+    r.idx = (int)j; r.zs = atnum[j];
+    cand[t] = r;
+  }
+  if (threadIdx.x == blockDim.x - 1) {
+    const int per = periodic[st];
+    g->periodic = per;
+    if (per) {
+      double m[3][3];                                  // m[c][k] = component c of lattice vector k
+      for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) { m[c][k] = lat[(size_t)9 * st + 3 * k + c]; g->lat[3 * k + c] = m[c][k]; }
+      const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1], c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2],
+                   c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+      const double det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+      bool ok = fabs(det) >= 1e-12;
+      const double id = ok ? 1.0 / det : 0.0;
+      double r[3][3];                                  // r = m^-1: s_k = sum_c r[k][c] d_c
+      r[0][0] = c00 * id; r[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id; r[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+      r[1][0] = c01 * id; r[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id; r[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+      r[2][0] = c02 * id; r[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id; r[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+      for (int k = 0; k < 3; k++) {
+        g->inv[3 * k] = r[k][0]; g->inv[3 * k + 1] = r[k][1]; g->inv[3 * k + 2] = r[k][2];
+        // plane spacing h_k = 1 / |row k of m^-1|;  need h_k >= 2 rc (with a little slack)
+        const double bn2 = r[k][0] * r[k][0] + r[k][1] * r[k][1] + r[k][2] * r[k][2];
+        if (!(bn2 * (4.0 * rc * rc) * (1.0 + 1e-9) <= 1.0)) ok = false;
+      }
+      if (!ok) atomicOr(&flags[4], 1);
+    } else {
+      for (int e = 0; e < 9; e++) { g->lat[e] = 0.0; g->inv[e] = 0.0; }
+    }
+  }
+  __syncthreads();
+  return nAt;
+}
+
+template <typename Visit>
+__device__ __forceinline__ void for_each_candidate_struct(const CRec *__restrict__ cand, int total,
+                                                          const StructGeom *__restrict__ g, const CRec &me,
+                                                          Visit visit) {
+  const int lane = threadIdx.x & 31;
+  const bool per = g->periodic != 0;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < total;
+    CRec r;
+    r.x = me.x; r.y = me.y; r.z = me.z; r.idx = -1; r.zs = 0;
+    if (valid) r = cand[t];
+    double dx = r.x - me.x, dy = r.y - me.y, dz = r.z - me.z;
+    if (per) {
+      const double magic = 6755399441055744.0;         // 1.5 * 2^52: rint() through the adder
+      const double n0 = (g->inv[0] * dx + g->inv[1] * dy + g->inv[2] * dz + magic) - magic;
+      const double n1 = (g->inv[3] * dx + g->inv[4] * dy + g->inv[5] * dz + magic) - magic;
+      const double n2 = (g->inv[6] * dx + g->inv[7] * dy + g->inv[8] * dz + magic) - magic;
+      dx -= n0 * g->lat[0] + n1 * g->lat[3] + n2 * g->lat[6];
+      dy -= n0 * g->lat[1] + n1 * g->lat[4] + n2 * g->lat[7];
+      dz -= n0 * g->lat[2] + n1 * g->lat[5] + n2 * g->lat[8];
+    }
+    visit(valid, dx, dy, dz, r.idx, r.zs);             // no shift flag: j == i is the central atom itself
   }
 }
 
@@ -299,8 +386,7 @@ __global__ void k_neigh_count(int N, const int *__restrict__ binOfSlot_unused, c
   const StructInfo &S = sinfo[binStruct[bin]];
   const BinPos p = bin_pos(S, bin);
   int n = 0, ncand = 0;
-  for_each_candidate_direct(S, p, cellStart, crec, [&](bool valid, double x, double y, double z, int j, int zs) {
-    const double dx = x - me.x, dy = y - me.y, dz = z - me.z;
+  for_each_candidate_direct(S, p, cellStart, crec, me, [&](bool valid, double dx, double dy, double dz, int j, int zs) {
     const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, j, zs, me.idx);
     n += __popc(__ballot_sync(0xffffffffu, ok));
     ncand += __popc(__ballot_sync(0xffffffffu, valid));

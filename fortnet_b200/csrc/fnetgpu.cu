@@ -56,13 +56,14 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
   cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
+  { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
   return 0;
 }
 
 static void free_slot(Slot &s) {
   cudaFree(s.d_offsets); cudaFree(s.d_structOf); cudaFree(s.d_atnum); cudaFree(s.d_sp); cudaFree(s.d_periodic);
-  cudaFree(s.d_coords); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
+  cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
   cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
   cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
@@ -184,6 +185,7 @@ extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, c
   std::vector<int> structOf(N);
   for (int st = 0; st < nStruct; st++) {
     if (offsets[st + 1] <= offsets[st]) FNET_FAIL(ctx, "dataset_upload: empty structure");
+    s.maxAtoms = std::max(s.maxAtoms, offsets[st + 1] - offsets[st]);
     for (int i = offsets[st]; i < offsets[st + 1]; i++) structOf[i] = st;
   }
   int maxSp = 0;
@@ -213,6 +215,8 @@ extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, c
   if (dev_upload(ctx, &s.d_dsw, dsw.data(), (size_t)nStruct)) return 1;
   if (dev_upload(ctx, &s.d_aw, aw.data(), (size_t)N)) return 1;
   if (coords) { if (dev_upload(ctx, &s.d_coords, coords, (size_t)3 * N)) return 1; s.capCoords = (size_t)3 * N; }
+  if (dev_upload(ctx, &s.d_lat, s.h_lat.data(), (size_t)9 * nStruct)) return 1;
+  if (dev_upload(ctx, &s.d_periodic, s.h_periodic.data(), (size_t)nStruct)) return 1;
   if (nG > 0) { if (!gTargets) FNET_FAIL(ctx, "gTargets missing"); if (dev_upload(ctx, &s.d_gt, gTargets, (size_t)nG * nStruct)) return 1; }
   if (nA > 0) { if (!aTargets) FNET_FAIL(ctx, "aTargets missing"); if (dev_upload(ctx, &s.d_at, aTargets, (size_t)nA * N)) return 1; }
   if (nExt > 0) { if (!ext) FNET_FAIL(ctx, "ext missing"); if (dev_upload(ctx, &s.d_ext, ext, (size_t)nExt * N)) return 1; }
@@ -228,7 +232,11 @@ extern "C" int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *c
   if (!coords) FNET_FAIL(ctx, "coords_update: coords missing");
   if (dev_reserve(ctx, &s.d_coords, &s.capCoords, (size_t)3 * s.N)) return 1;
   CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (latvecs) s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
+  if (latvecs) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);   // overlaps the copies above
+    s.structPath = 1;
+  }
   s.cellRc = -1.0; s.neighStale = true; s.featValid = false;   // maxNeigh stays as a capacity hint
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffer on return
   return 0;
@@ -561,7 +569,39 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
 }
 
 // launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
-struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; size_t smem; };
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; };
+// the whole-structure path (cells.cuh): small structures, lattice check passed so far
+static bool use_struct_path(const fnetgpu_ctx *ctx, const Slot &s) {
+  return !ctx->acsfPathCells && s.structPath && s.maxAtoms <= FNET_STRUCT_MAX_ATOMS && s.d_coords && s.d_lat;
+}
+static inline int struct_cap(const Slot &s) {   // neighbours per atom <= atoms - 1 under the minimum-image convention
+  const int hint = s.maxNeigh > 0 ? s.maxNeigh : 32;
+  return std::max(32, (std::min(hint, std::max(s.maxAtoms - 1, 1)) + 31) & ~31);
+}
+static GeomArgs geom_args(const Slot &s) {
+  GeomArgs g;
+  g.binStruct = s.d_binStruct; g.sinfo = s.d_sinfo; g.cellStart = s.d_cellStart; g.crec = s.d_crec;
+  g.offsets = s.d_offsets; g.coords = s.d_coords; g.lat = s.d_lat; g.periodic = s.d_periodic; g.atnum = s.d_atnum;
+  return g;
+}
+static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
+  L.path = FNET_PATH_STRUCT; L.staged = false;
+  L.cap = struct_cap(s);
+  L.capC = (s.maxAtoms + 31) & ~31;
+  L.wpb = 4;
+  const size_t prefix = acsf_cta_prefix_bytes(L.capC, 2);
+  L.smem = prefix + warpBytes * L.wpb;
+  while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
+  if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
+  // ~4 central atoms per warp; more splits when there are too few structures to fill the GPU
+  int nSplit = (s.maxAtoms + 4 * L.wpb - 1) / (4 * L.wpb);
+  const long long want = 8LL * ctx->nSM;
+  if ((long long)s.nStruct * nSplit < want)
+    nSplit = (int)std::min<long long>((s.maxAtoms + L.wpb - 1) / L.wpb, (want + s.nStruct - 1) / s.nStruct);
+  L.nSplit = std::max(1, std::min(nSplit, 65535));
+  L.grid = dim3(s.nStruct, L.nSplit);
+  return 0;
+}
 static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
   L.cap = std::max(32, (s.maxNeigh + 31) & ~31);
   L.staged = s.maxCells <= FNET_MAX_NCELLS && s.maxCand >= 0 && s.maxCand <= 1536;
@@ -580,7 +620,20 @@ static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, A
   const long long want = 8LL * ctx->nSM;
   if ((long long)s.totalBins * nSplit < want) nSplit = (int)std::min<long long>((pop + L.wpb - 1) / L.wpb, (want + s.totalBins - 1) / s.totalBins);
   L.nSplit = std::max(1, std::min(nSplit, 65535));
+  L.path = L.staged ? FNET_PATH_STAGED : FNET_PATH_DIRECT;
+  L.grid = dim3(s.totalBins, L.nSplit);
   return 0;
+}
+
+extern "C" int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode) {
+  CHECK_CTX(ctx);
+  if (mode != 0 && mode != 1) FNET_FAIL(ctx, "acsf_path_set: mode must be 0 (auto) or 1 (cell list)");
+  ctx->acsfPathCells = mode;
+  return 0;
+}
+extern "C" int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used) return -1;
+  return ctx->slots[slot].lastPath;
 }
 
 extern "C" int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh) {
@@ -674,36 +727,54 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     ctx->haveZ = true;
   }
   if (F > 0) {
-    if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
     // buffer capacities (neighbours per atom, candidates per bin): counted once per slot; after a
     // geometry update the previous maxima are reused as hints and the kernel's overflow flags
-    // trigger a retry
-    if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
-    for (int attempt = 0; attempt < 3; attempt++) {
+    // trigger a retry.  Small structures take the whole-structure path (no cell list); its lattice
+    // check (flags[4]) sends the slot back to the cell list.
+    for (int attempt = 0; attempt < 4; attempt++) {
       AcsfLaunch L;
-      if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
+      const bool sp = use_struct_path(ctx, s);
+      if (sp) {
+        if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), F), L)) return 1;
+      } else {
+        if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
+        if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
+        if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
+      }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-      const dim3 grid(s.totalBins, L.nSplit);
+      const GeomArgs geo = geom_args(s);
       const double *zp = useGiven ? ctx->d_zprec : nullptr;
-#define FNET_ACSF_LAUNCH(NS, ST)                                                                               \
+#define FNET_ACSF_LAUNCH(NS, PATH)                                                                             \
       do {                                                                                                     \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
-        LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, ST><<<grid, L.wpb * 32, L.smem, ctx->stream>>>(                   \
-                                L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, \
-                                L.capC, feat, nFeat, zp, nExtSel, ctx->d_extIdx, ctx->d_flags)));               \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+        LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, PATH><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(               \
+                                L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, feat, nFeat, zp, nExtSel,    \
+                                ctx->d_extIdx, ctx->d_flags)));                                                \
       } while (0)
+#define FNET_ACSF_LAUNCH_NS(PATH)                                                                              \
+      do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
       const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
-      if (L.staged) { if (ns == 1) FNET_ACSF_LAUNCH(1, true); else if (ns == 2) FNET_ACSF_LAUNCH(2, true); else FNET_ACSF_LAUNCH(4, true); }
-      else { if (ns == 1) FNET_ACSF_LAUNCH(1, false); else if (ns == 2) FNET_ACSF_LAUNCH(2, false); else FNET_ACSF_LAUNCH(4, false); }
+      if (L.path == FNET_PATH_STRUCT) FNET_ACSF_LAUNCH_NS(FNET_PATH_STRUCT);
+      else if (L.path == FNET_PATH_STAGED) FNET_ACSF_LAUNCH_NS(FNET_PATH_STAGED);
+      else FNET_ACSF_LAUNCH_NS(FNET_PATH_DIRECT);
+#undef FNET_ACSF_LAUNCH_NS
 #undef FNET_ACSF_LAUNCH
       int h[16];
       CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      s.maxBinPop = h[8 + 4];
-      if (h[1] == 0 && h[7] == 0) break;
-      if (attempt == 2) FNET_FAIL(ctx, "neighbour buffer overflow");
-      if (h[1] != 0) s.maxNeigh = h[1];
-      if (h[7] != 0) s.maxCand = h[7];     // 0x7fffffff: too many neighbour cells -> direct path
+      s.lastPath = L.path;
+      if (sp) {
+        if (h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; continue; }   // a lattice is too small for the minimum image: cell list
+        if (h[1] == 0 && h[7] == 0) break;
+        if (h[1] != 0) s.maxNeigh = h[1];
+        if (h[7] != 0) FNET_FAIL(ctx, "structure larger than the staged-structure buffer");
+      } else {
+        s.maxBinPop = h[8 + 4];
+        if (h[1] == 0 && h[7] == 0) break;
+        if (h[1] != 0) s.maxNeigh = h[1];
+        if (h[7] != 0) s.maxCand = h[7];     // 0x7fffffff: too many neighbour cells -> direct path
+      }
+      if (attempt == 3) FNET_FAIL(ctx, "neighbour buffer overflow");
     }
   } else {
     const int B = 256;
@@ -1052,8 +1123,6 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   const NetTables &n = ctx->net;
   if (!ctx->acsfSet || T.F == 0) FNET_FAIL(ctx, "forces: need an ACSF configuration");
   if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "forces: not defined with external features (initprogram.F90:1543-1548)");
-  if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
-  if (ensure_neigh_count(ctx, s)) return 1;   // exact count: the force kernel has no retry loop
   // (1) dE_k/dG for every atom and output: one reverse sweep per output
   if (!s.d_dEdG) { real *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
   {
@@ -1075,23 +1144,47 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
     dEdG64 = tmp64;
   }
   if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, (size_t)3 * n.nOut * s.N)) return 1; }
-  CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
-  AcsfLaunch L;
-  if (plan_acsf_launch(ctx, s, force_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F), L)) return 1;
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-  const dim3 g(s.totalBins, L.nSplit, n.nOut);
   const double *zp = s.zscored ? ctx->d_zprec : nullptr;
-  if (L.staged) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<true><<<g, L.wpb * 32, L.smem, ctx->stream>>>(L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags)));
-  } else {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<false><<<g, L.wpb * 32, L.smem, ctx->stream>>>(L.nSplit, s.d_binStruct, s.d_sinfo, s.d_cellStart, s.d_crec, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags)));
-  }
   int h[16];
-  CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  if (forces) CUDA_TRY(ctx, cudaMemcpyAsync(forces, s.d_forces, (size_t)3 * n.nOut * s.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int attempt = 0; attempt < 4; attempt++) {
+    // same path selection as the value kernel; the forces are accumulated with atomics, so a retry
+    // (neighbour-buffer overflow, lattice too small for the whole-structure path) starts from zero
+    AcsfLaunch L;
+    const bool sp = use_struct_path(ctx, s);
+    if (sp) {
+      if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), L)) return 1;
+    } else {
+      if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
+      if (ensure_neigh_count(ctx, s)) return 1;
+      if (plan_acsf_launch(ctx, s, force_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F), L)) return 1;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+    const dim3 g(L.grid.x, L.grid.y, n.nOut);
+    const GeomArgs geo = geom_args(s);
+#define FNET_FORCE_LAUNCH(PATH)                                                                                 \
+    do {                                                                                                        \
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+      LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<PATH><<<g, L.wpb * 32, L.smem, ctx->stream>>>(                    \
+                                    L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp,       \
+                                    s.d_forces, ctx->d_flags)));                                                \
+    } while (0)
+    if (L.path == FNET_PATH_STRUCT) FNET_FORCE_LAUNCH(FNET_PATH_STRUCT);
+    else if (L.path == FNET_PATH_STAGED) FNET_FORCE_LAUNCH(FNET_PATH_STAGED);
+    else FNET_FORCE_LAUNCH(FNET_PATH_DIRECT);
+#undef FNET_FORCE_LAUNCH
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    s.lastPath = L.path;
+    if (sp && h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; continue; }
+    if (h[1] == 0 && h[7] == 0) break;
+    if (!sp || attempt == 3) break;            // cell-list path: capacities were counted exactly
+    if (h[1] != 0) s.maxNeigh = h[1];
+  }
+  if (forces && h[1] == 0 && h[7] == 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(forces, s.d_forces, (size_t)3 * n.nOut * s.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (tmp64) cudaFree(tmp64);
   if (h[1] != 0 || h[7] != 0) FNET_FAIL(ctx, "neighbour buffer overflow in the force kernel");
   return 0;

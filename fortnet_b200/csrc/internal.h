@@ -115,6 +115,10 @@ struct Slot {
   // device data
   int *d_offsets = nullptr, *d_structOf = nullptr, *d_atnum = nullptr, *d_sp = nullptr, *d_periodic = nullptr;
   double *d_coords = nullptr;       // [N][3] as given
+  double *d_lat = nullptr;          // [nStruct][9] lattice vectors (whole-structure ACSF path)
+  int maxAtoms = 0;                 // largest structure
+  int lastPath = -1;                // path of the last ACSF launch (fnetgpu_acsf_path_get)
+  int structPath = 1;               // whole-structure path allowed for the current lattices (reset by coords_update)
   double *d_fpos = nullptr;         // [N][3] folded positions (atom order)
   CRec *d_crec = nullptr;    // [N] 32-byte records in cell order (position, atom index, atomic number)
   int *d_binStruct = nullptr;       // [totalBins] structure of each bin
@@ -187,6 +191,7 @@ struct fnetgpu_ctx {
   double *d_dd = nullptr;           // [nSpecies*nTot + 2] reduced gradient + loss numerator/denominator
   double *h_pinned = nullptr; size_t pinnedN = 0;
   int *d_flags = nullptr;           // [8] statistics / overflow flags (cells.cuh, acsf.cuh)
+  int acsfPathCells = 0;            // FNETGPU_ACSF_PATH=cells: never use the whole-structure path (tests, A/B)
   // comm
   void *nccl = nullptr;             // dlopen handle
   void *comm = nullptr;             // ncclComm_t

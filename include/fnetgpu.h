@@ -126,6 +126,15 @@ int fnetgpu_profile(fnetgpu_ctx *ctx, int enable);
 int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kernelId, double *ms_total, long long *launches);
 const char *fnetgpu_kernel_name(int kernelId);                /* NULL past the last id */
 int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh);
+/* Neighbour search of the ACSF kernels.  mode 0 (default): automatic -- datasets whose structures
+ * all have <= 256 atoms and lattice-plane spacings >= 2 rc (or are clusters) take the
+ * whole-structure / minimum-image path, everything else the cell list (what replaces
+ * dynneighlist.F90:233-320 either way); mode 1: always the cell list (tests, A/B).  The
+ * environment variable FNETGPU_ACSF_PATH=cells selects mode 1 at fnetgpu_init. */
+int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode);
+/* path the last ACSF value / force launch of this slot took: 0 cell list (direct), 1 cell list
+ * (candidates staged per bin), 2 whole structure; -1 before the first launch */
+int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot);
 
 #ifdef __cplusplus
 }

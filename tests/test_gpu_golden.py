@@ -14,8 +14,11 @@ def fb():
     return fb
 
 
-def _setup(fb, case, precision=64):
-    ctx = fb.Context(precision=precision)
+PATHS = ["auto", "cells"]   # whole-structure neighbour search (all fixtures are small structures) and the cell list
+
+
+def _setup(fb, case, precision=64, acsf_path="auto"):
+    ctx = fb.Context(precision=precision, acsf_path=acsf_path)
     ds = case.dataset
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=case.zmeans is not None,
@@ -30,10 +33,13 @@ def _setup(fb, case, precision=64):
 PRED = gio.cases(mode=("predict", "validate"), forces=(None, "analytical"))
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("entry", PRED, ids=[e["case"] for e in PRED])
-def test_predictions_and_forces(fb, entry):
+def test_predictions_and_forces(fb, entry, path):
     case = gio.Case(entry)
-    ctx, acsf, net = _setup(fb, case)
+    ctx, acsf, net = _setup(fb, case, acsf_path=path)
+    if case.funcs:
+        assert ctx.acsf_path(0) in ((2,) if path == "auto" else (0, 1)), ctx.acsf_path(0)
     ds = case.dataset
     raw = net.predict_batch(0)
     assert gio.allclose(raw, case.arr["out_rawpredictions"]), gio.maxdiff(raw, case.arr["out_rawpredictions"])
@@ -74,15 +80,16 @@ def test_sd_training_step(fb, entry):
 ZS = [e for e in gio.cases(mode=("train",))]
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("entry", ZS, ids=[e["case"] for e in ZS])
-def test_features_and_zscore_statistics(fb, entry):
+def test_features_and_zscore_statistics(fb, entry, path):
     """raw ACSF vs oracle, and statistics computed on the GPU vs the stored netstat values."""
     from oracle import oracle as orc
     case = gio.Case(entry)
     if not case.funcs:
         pytest.skip("no ACSF in this case")
     ds = case.dataset
-    ctx = fb.Context()
+    ctx = fb.Context(acsf_path=path)
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=False)
     acsf.calculate(0)

@@ -37,14 +37,23 @@ def _md(a, b):
     return "max abs diff %.3e (scale %.3e)" % (np.abs(a - b).max(), np.abs(b).max())
 
 
-def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3):
+PATHS = ["auto", "cells"]      # neighbour search: whole-structure / minimum image where valid, or always the cell list
+STRUCT, CELLS = (2,), (0, 1)   # values of Context.acsf_path()
+
+
+def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3, acsf_path="auto",
+                expect_path=None):
     """features (raw + z-scored), statistics, predictions, loss, gradient and forces vs the oracle"""
     fd = funcs.asdicts()
     nt = _nthreads()
-    ctx = fb.Context()
+    ctx = fb.Context(acsf_path=acsf_path)
     ctx.upload(0, ds)
     a_raw = fb.Acsf(ctx, funcs, standardize=False)
     a_raw.calculate(0)
+    if acsf_path == "cells":
+        expect_path = CELLS
+    if expect_path is not None:
+        assert ctx.acsf_path(0) in expect_path, ctx.acsf_path(0)
     vals = a_raw.features(0)
     ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, ext=ds.ext, nthreads=nt)
     assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
@@ -76,25 +85,29 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
         f_o = orc.forces(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, zref, ds.globalsp, dims, act,
                          wb, ext=ds.ext, sigmas=sg, nthreads=nt)
         assert np.allclose(f, f_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(f_o).max())), _md(f, f_o)
+        if expect_path is not None:
+            assert ctx.acsf_path(0) in expect_path, ctx.acsf_path(0)
     ctx.close()
 
 
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json configs at oracle-sized samples
 # ---------------------------------------------------------------------------------------------
-def test_c2_si_bulk(fb, orc):
+@pytest.mark.parametrize("path", PATHS)
+def test_c2_si_bulk(fb, orc, path):
     from fortnet_b200 import synthetic
     ds = synthetic.si_bulk(n_struct=12, seed=20260001)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
-    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1])
+    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT)
 
 
-def test_c3_tio2(fb, orc):
+@pytest.mark.parametrize("path", PATHS)
+def test_c3_tio2(fb, orc, path):
     from fortnet_b200 import synthetic
     ds = synthetic.tio2(n_struct=3, seed=20260002)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
     assert len(funcs) == 64
-    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1])
+    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT)
 
 
 def test_c5_dense_liquid_values(fb, orc):
@@ -108,6 +121,7 @@ def test_c5_dense_liquid_values(fb, orc):
     acsf = fb.Acsf(ctx, funcs, standardize=False)
     acsf.calculate(0)
     vals = acsf.features(0)
+    assert ctx.acsf_path(0) in CELLS       # edge < 2 rc: the whole-structure path must have handed over to the cell list
     mx, mean = ctx.max_neighbors(0)
     assert 120 < mean < 180, mean
     ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
@@ -141,7 +155,8 @@ def _mixed_functions(fb, rc, zs=None):
     return out
 
 
-def test_ragged_clusters_and_single_atoms(fb, orc):
+@pytest.mark.parametrize("path", PATHS)
+def test_ragged_clusters_and_single_atoms(fb, orc, path):
     """non-periodic structures of 1..40 atoms in one batch (prediction/** goldens are clusters);
     a single atom has no neighbours -> all ACSF are 0 (before the z-score)"""
     rng = np.random.default_rng(21)
@@ -155,10 +170,11 @@ def test_ragged_clusters_and_single_atoms(fb, orc):
                           gtargets=rng.normal(size=(len(natoms), 1)), weights=rng.integers(1, 4, size=len(natoms)),
                           atomic_weights=rng.uniform(0.5, 1.5, size=N), atomic_numbers=[1, 8])
     funcs = _mixed_functions(fb, 3.0 * fb.BOHR_PER_AA, [1, 8])
-    _full_check(fb, orc, ds, funcs, [len(funcs), 6, 4, 1], act="sigmoid")
+    _full_check(fb, orc, ds, funcs, [len(funcs), 6, 4, 1], act="sigmoid", acsf_path=path, expect_path=STRUCT)
 
 
-def test_atomic_and_multiple_targets(fb, orc):
+@pytest.mark.parametrize("path", PATHS)
+def test_atomic_and_multiple_targets(fb, orc, path):
     """two global + two atomic targets (bothTargets goldens): nOut = 4, forces have 3*nOut columns"""
     rng = np.random.default_rng(22)
     natoms = [9, 14, 6]
@@ -171,7 +187,7 @@ def test_atomic_and_multiple_targets(fb, orc):
                           atargets=rng.normal(size=(N, 2)), atomic_weights=rng.uniform(0.5, 1.5, size=N),
                           atomic_numbers=[14, 6])
     funcs = _mixed_functions(fb, 4.0 * fb.BOHR_PER_AA)
-    _full_check(fb, orc, ds, funcs, [len(funcs), 5, 4], act="tanh")
+    _full_check(fb, orc, ds, funcs, [len(funcs), 5, 4], act="tanh", acsf_path=path, expect_path=STRUCT)
 
 
 def test_thin_triclinic_and_unfolded_cells(fb, orc):
@@ -206,10 +222,74 @@ def test_thin_triclinic_and_unfolded_cells(fb, orc):
     ds = fb.Dataset.build(natoms, coords, np.ones(4, np.int32), lats, atnum, gtargets=rng.normal(size=(4, 1)),
                           atomic_numbers=[22, 8])
     funcs = _mixed_functions(fb, rc, [22, 8])
-    _full_check(fb, orc, ds, funcs, [len(funcs), 4, 1], forces=False)
+    # auto mode: the in-kernel lattice check rejects the thin cells and the call falls back to the cell list
+    _full_check(fb, orc, ds, funcs, [len(funcs), 4, 1], forces=False, expect_path=CELLS)
 
 
-def test_atom_id_scaling_and_external_features(fb, orc):
+def test_whole_structure_path_triclinic_unfolded_mixed(fb, orc):
+    """the whole-structure / minimum-image path on its own ground: skewed triclinic cells whose plane
+    spacings are just above 2 rc, coordinates far outside the unit cell, fractional coordinate exactly
+    1.0, clusters and periodic structures in one batch, 1..200 atoms; values, gradient AND forces
+    (every edge >= 2 rc, so the reference's derivative is well defined)"""
+    rng = np.random.default_rng(31)
+    rc = 4.0 * fb.BOHR_PER_AA
+    lats = np.array([
+        [[2.05 * rc, 0, 0], [0.9 * rc, 2.02 * rc, 0], [-0.7 * rc, 0.8 * rc, 2.01 * rc]],     # rescaled below: min spacing 2.01 rc
+        [[3.0 * rc, 0, 0], [0, 2.4 * rc, 0], [0, 0, 2.000001 * rc]],
+        [[0, 0, 0], [0, 0, 0], [0, 0, 0]],                                                  # cluster
+        [[2.6 * rc, 0.3 * rc, 0.2 * rc], [-0.2 * rc, 2.7 * rc, 0.4 * rc], [0.1 * rc, -0.3 * rc, 2.5 * rc]],
+        [[0, 0, 0], [0, 0, 0], [0, 0, 0]],                                                  # single atom
+    ])
+    per = np.array([1, 1, 0, 1, 0], np.int32)
+    for k in (0, 3):     # skewed cells: scale so that the smallest lattice-plane spacing is 2.01 rc
+        h = 1.0 / np.linalg.norm(np.linalg.inv(lats[k]), axis=0)
+        lats[k] *= 2.01 * rc / h.min()
+    natoms = [40, 33, 25, 200, 1]
+    coords = []
+    for s, n in enumerate(natoms):
+        if per[s]:
+            frac = rng.uniform(0.2, 1.2, size=(n, 3)) + np.array([-4.0, 7.0, 2.0])
+            if s == 1:
+                frac = rng.uniform(0.0, 1.0, size=(n, 3))
+                frac[0] = [1.0, 0.0, 1.0]
+            coords.append(frac @ lats[s])
+        else:
+            coords.append(rng.uniform(0.0, 2.2 * rc, size=(n, 3)) + 50.0)
+    coords = np.concatenate(coords)
+    N = sum(natoms)
+    atnum = rng.choice([22, 8], size=N).astype(np.int32)
+    ds = fb.Dataset.build(natoms, coords, per, lats, atnum, gtargets=rng.normal(size=(5, 1)),
+                          weights=rng.integers(1, 3, size=5), atomic_numbers=[22, 8])
+    funcs = _mixed_functions(fb, rc, [22, 8])
+    _full_check(fb, orc, ds, funcs, [len(funcs), 5, 1], expect_path=STRUCT)
+    _full_check(fb, orc, ds, funcs, [len(funcs), 5, 1], acsf_path="cells")
+
+
+def test_whole_structure_path_hands_over_after_lattice_update(fb, orc):
+    """coords_update with a lattice that shrinks below 2 rc: the slot must switch to the cell list on
+    its own (and back to the whole-structure path when the lattice grows again)"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=3, seed=8)
+    rc = 4.0 * fb.BOHR_PER_AA
+    funcs = fb.GFunctions.from_auto_scheme(rc, 6, 6)
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False)
+    acsf.calculate(0)
+    assert ctx.acsf_path(0) in STRUCT
+    for scale, expect in ((0.7, CELLS), (1.0, STRUCT)):
+        c2, l2 = ds.coords * scale, ds.latvecs * scale
+        ctx.update_coords(0, c2, l2)
+        acsf.calculate(0)
+        assert ctx.acsf_path(0) in expect, (scale, ctx.acsf_path(0))
+        ref = orc.acsf(ds.offsets, c2, ds.periodic, l2, ds.atnum, funcs.asdicts())
+        vals = acsf.features(0)
+        assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_atom_id_scaling_and_external_features(fb, orc, path):
     """q_i q_j prefactors from an external-feature row (acsf.F90:836-840,1003-1052) and external
     columns appended to the ACSF block (features.F90:227-241)"""
     from fortnet_b200 import synthetic
@@ -223,7 +303,7 @@ def test_atom_id_scaling_and_external_features(fb, orc):
     funcs = fb.GFunctions.from_auto_scheme(rc, 4, 4, atomid=2)
     funcs.append(fb.GFunctions([G("g4", rc, xi=2.0, eta=0.03, lam=1.0, atomid=1), G("g1", rc, atomid=3), G("g3", rc, kappa=0.5)]))
     fd = funcs.asdicts()
-    ctx = fb.Context()
+    ctx = fb.Context(acsf_path=path)
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, funcs, standardize=False, ext_indices=[3, 1])      # 1-based rows of extFeatures (features.F90:227-241)
     acsf.calculate(0)
