@@ -36,9 +36,10 @@ def _i(a):
 
 class Context:
     """One GPU.  precision 64 (parity mode, default) or 32.  acsf_path "auto" (small structures:
-    whole-structure / minimum-image neighbour search, else the cell list) or "cells"."""
+    whole-structure / minimum-image neighbour search, else the cell list) or "cells"; mlp "auto"
+    (precision 64: DMMA kernels when the network fits) or "legacy" (register-tiled FMA kernels)."""
 
-    def __init__(self, device=-1, precision=64, deterministic=True, acsf_path="auto"):
+    def __init__(self, device=-1, precision=64, deterministic=True, acsf_path="auto", mlp="auto"):
         self._lib = lib()
         h = C.c_void_p()
         rc = self._lib.fnetgpu_init(C.byref(h), C.c_int(device), C.c_int(precision), C.c_int(int(deterministic)))
@@ -50,6 +51,10 @@ class Context:
             raise ValueError("acsf_path must be 'auto' or 'cells'")
         if acsf_path == "cells":
             self._check(self._lib.fnetgpu_acsf_path_set(self._h, C.c_int(1)))
+        if mlp not in ("auto", "legacy"):
+            raise ValueError("mlp must be 'auto' or 'legacy'")
+        if mlp == "legacy":
+            self._check(self._lib.fnetgpu_mlp_path_set(self._h, C.c_int(1)))
         self.n_feat = {}
         self.n_atoms = {}
         self.n_struct = {}
@@ -112,6 +117,10 @@ class Context:
                 out[name.decode()] = dict(ms_total=ms.value, launches=int(n.value))
             k += 1
         return out
+
+    def mlp_path(self):
+        """1: FP64 tensor-core (DMMA) subnetwork kernels, 0: register-tiled FMA kernels, -1: no network set"""
+        return int(self._lib.fnetgpu_mlp_path_get(self._h))
 
     def acsf_path(self, slot):
         """path of the last ACSF launch: 0/1 cell list (direct/staged), 2 whole structure, -1 none"""

@@ -6,10 +6,12 @@
 #include "acsf.cuh"
 #include "acsf_force.cuh"
 #include "mlp.cuh"
+#include "mlp_mma.cuh"
 
 #include <dlfcn.h>
 #include <map>
 #include <tuple>
+#include <type_traits>
 
 static const char *kKernelNames[K_NUM_KERNELS] = {
     "bin_count", "bin_scan", "bin_fill", "bin_sort", "neigh_count", "acsf", "zstat", "zstat_final",
@@ -56,6 +58,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
   cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
+  { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
   return 0;
@@ -66,7 +69,7 @@ static void free_slot(Slot &s) {
   cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
   cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
-  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
+  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
   cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
   s = Slot();
 }
@@ -631,6 +634,16 @@ extern "C" int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode) {
   ctx->acsfPathCells = mode;
   return 0;
 }
+extern "C" int fnetgpu_mlp_path_set(fnetgpu_ctx *ctx, int mode) {
+  CHECK_CTX(ctx);
+  if (mode != 0 && mode != 1) FNET_FAIL(ctx, "mlp_path_set: mode must be 0 (auto) or 1 (register-tiled kernels)");
+  ctx->mlpLegacy = mode;
+  return 0;
+}
+extern "C" int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx) {
+  if (!ctx || !ctx->netSet) return -1;
+  return (ctx->precision == 64 && !ctx->mlpLegacy && bpnn_mma_fits(ctx->net)) ? 1 : 0;
+}
 extern "C" int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot) {
   if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used) return -1;
   return ctx->slots[slot].lastPath;
@@ -930,7 +943,7 @@ extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, cons
   if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
   if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
   ctx->netSet = true; ctx->paramsSet = false;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) ctx->slots[i].nTiles = 0;
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; }
   return 0;
 }
 
@@ -970,6 +983,16 @@ static int ensure_tiles(fnetgpu_ctx *ctx, Slot &s) {
     }
   s.nTiles = (int)tiles.size() / 3; s.tileT = T;
   if (dev_upload(ctx, &s.d_tiles, tiles.data(), tiles.size())) return 1;
+  {   // rounds of the FP64 tensor-core path: 4 warps x 16 atoms of one species
+    std::vector<int> t16;
+    const int R = FNET_MMA_TA * FNET_MMA_WARPS;
+    for (int sp = 0; sp + 1 < (int)s.spBeg.size(); sp++)
+      for (int b = s.spBeg[sp]; b < s.spBeg[sp + 1]; b += R) {
+        t16.push_back(b); t16.push_back(std::min(R, s.spBeg[sp + 1] - b)); t16.push_back(sp);
+      }
+    s.nTiles16 = (int)t16.size() / 3;
+    if (dev_upload(ctx, &s.d_tiles16, t16.data(), t16.size())) return 1;
+  }
   real *raw = nullptr;
   if (dev_alloc(ctx, &raw, (size_t)s.N * n.nOut)) return 1;
   cudaFree(s.d_raw); s.d_raw = raw;
@@ -1007,9 +1030,33 @@ static int check_ready(fnetgpu_ctx *ctx, Slot &s, bool needTargets) {
   return ensure_tiles<real>(ctx, s);
 }
 
+// precision 64: DMMA kernels (mlp_mma.cuh) whenever the network fits their limits
+template <typename real>
+static bool use_mma(const fnetgpu_ctx *ctx) {
+  return std::is_same<real, double>::value && !ctx->mlpLegacy && bpnn_mma_fits(ctx->net);
+}
+struct MmaLaunch { int grid; size_t smem; };
+static MmaLaunch plan_mma(const fnetgpu_ctx *ctx, const Slot &s, int mode) {
+  MmaLaunch M;
+  M.smem = bpnn_mma_smem_bytes(ctx->net, mode);
+  const int perSM = std::max(1, std::min((int)(225 * 1024 / (M.smem + 1024)), 4));
+  M.grid = std::max(1, std::min(s.nTiles16, ctx->nSM * perSM));
+  return M;
+}
+
 template <typename real>
 static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
   const NetTables &n = ctx->net;
+  if constexpr (std::is_same<real, double>::value) {
+    if (use_mma<real>(ctx)) {
+      const MmaLaunch M = plan_mma(ctx, s, 2);
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem));
+      LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1><<<M.grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(
+                                 s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, n,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw)));
+      return 0;
+    }
+  }
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 2);
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
   LAUNCH(ctx, K_MLP_FWD, (k_bpnn<real, 2><<<B.grid, B.threads, B.smem, ctx->stream>>>(
@@ -1037,16 +1084,38 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
   const size_t nDD = (size_t)n.nTot * n.nSpecies;
   if (run_forward<real>(ctx, s)) return 1;
   if (run_struct_loss<real>(ctx, s, lossId)) return 1;
+  const bool mma = use_mma<real>(ctx);
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 0);
-  const int grid = B.grid;
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  const MmaLaunch M = plan_mma(ctx, s, 0);
+  const int grid = mma ? M.grid : B.grid;
   size_t need = (size_t)grid * nDD;
   if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_partials, 0, need * sizeof(double), ctx->stream));
-  LAUNCH(ctx, K_MLP_GRAD, (k_bpnn<real, 0><<<grid, B.threads, B.smem, ctx->stream>>>(
-                              s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
-                              s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
-                              lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
+  bool launched = false;
+  if constexpr (std::is_same<real, double>::value) {
+    if (mma) {
+      const MmaLayout ml = mma_layout(n);
+      const int perWarp = (ml.nGradTiles + FNET_MMA_WARPS - 1) / FNET_MMA_WARPS;
+#define FNET_MMA_GRAD(NSLOT)                                                                                      \
+      do {                                                                                                        \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(        \
+                                    s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
+                                    (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
+                                    s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr)));   \
+      } while (0)
+      if (perWarp <= 6) FNET_MMA_GRAD(6); else if (perWarp <= 12) FNET_MMA_GRAD(12); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
+#undef FNET_MMA_GRAD
+      launched = true;
+    }
+  }
+  if (!launched) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    LAUNCH(ctx, K_MLP_GRAD, (k_bpnn<real, 0><<<grid, B.threads, B.smem, ctx->stream>>>(
+                                s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
+                                s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
+                                lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
+  }
   LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
   if (allreduce_sum(ctx, ctx->d_dd, nDD + 2)) return 1;   // gradient | loss numerator | denominator
   if (ddSerial || loss) {

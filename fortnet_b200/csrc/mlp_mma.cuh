@@ -1,0 +1,423 @@
+// mlp_mma.cuh -- FP64 subnetwork kernels on the FP64 tensor-core path (DMMA m8n8k4).
+//
+// Same maths and the same reference sites as mlp.cuh (TNetwork_fprop / bprop, lib_nn/network.F90:
+// 146-180, 248-296; TBpnn_sysTrain / updateGradients, lib_nn/bpnn.F90:394-481, 610-704); this file
+// changes how the three small contractions of every layer are executed in precision 64:
+//     forward    Z[t][o]  = sum_i A[t][i] W[i][o]          (M = atoms, N = outputs, K = inputs)
+//     backward   D[t][i]  = sum_o Dn[t][o] W[i][o]         (M = atoms, N = inputs,  K = outputs)
+//     gradient   dW[i][o] = sum_t A[t][i] Dn[t][o]         (M = inputs, N = outputs, K = atoms)
+// Layer widths of 1..100 leave the register-tiled DFMA kernel of mlp.cuh latency- and
+// barrier-bound (ncu: FP64 pipe 26 % busy, 7 CTA barriers per 64 atoms, idle warps in every
+// phase).  mma.sync.m8n8k4.f64 issues 256 FMAs per warp instruction with one 8-byte operand per
+// lane and matrix, so
+//   * a WARP owns a tile of 16 atoms from the features to the input-layer deltas: no CTA
+//     barrier inside the forward / backward sweeps, every lane busy, 2 + NT shared-memory loads
+//     per 2*NT DMMAs;
+//   * the weight gradients are accumulated in REGISTERS for the whole kernel: the 8x8 output
+//     tiles of all dW_l are dealt out to the CTA's warps once (<= FNET_MMA_MAXSLOTS each); after
+//     each round (one tile per warp) the warps sweep all tiles of the round, K = atoms.  Two CTA
+//     barriers per round, no shared-memory gradient buffer, no atomics: the result is
+//     bit-reproducible (fixed order), as before.
+// Activations / deltas sit in shared memory as [row][atom] with a row stride of 20 doubles
+// (= 4 mod 16) and the weights as [out][in] with a row stride = 4 mod 16, which makes every
+// fragment load (8 rows x 4 columns or 4 rows x 8 columns of doubles) bank-conflict free.
+// FP64 tensor cores run at the DFMA rate on B200 (tools/peaks.cu: 18.5 vs 16.9 TFMA/s) -- the
+// gain is issue slots and latency, not peak.  Precision 32, the input-gradient sweep of the
+// forces (MODE 1) and networks that do not fit the limits below stay on mlp.cuh.
+#pragma once
+#include "mlp.cuh"
+
+#define FNET_MMA_TA 16             // atoms per warp tile (two m8 tiles)
+#define FNET_MMA_TS 20             // row stride of the [row][atom] tiles, doubles
+#define FNET_MMA_WARPS 4
+#define FNET_MMA_MAXSLOTS 18       // weight-gradient output tiles a warp can own
+
+__host__ __device__ inline int fnet_ru4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline int fnet_ru8(int x) { return (x + 7) & ~7; }
+
+struct MmaLayout {
+  int wS[FNET_MAX_LAYERS];     // row stride of W_l, stored [out][in] like the serialised ww(i,o): >= roundup4(din), = 4 mod 16
+  int wOff[FNET_MAX_LAYERS];   // W_l: roundup8(dout) rows (zero padded)
+  int bOff[FNET_MAX_LAYERS];   // bias of layer l >= 1: roundup8(dims[l]) entries (zero padded)
+  int wTotal;                  // doubles (multiple of 2, + slack for the column over-read of the last row)
+  int aOff[FNET_MAX_LAYERS];   // first row of a_l in a warp tile; block height roundup8(dims[l])
+  int dOff[FNET_MAX_LAYERS];   // first row of f'(z_l), then delta_l (l >= 1); block height roundup8(dims[l])
+  int rowsA, rows;             // rows of the forward-only tile / of the training tile
+  int nGradTiles;              // 8x8 output tiles of all weight gradients
+  int nBias;                   // sum of dims[1..L-1]
+};
+
+__host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
+  MmaLayout m;
+  int off = 0;
+  m.nGradTiles = 0; m.nBias = 0;
+  for (int l = 0; l + 1 < net.L; l++) {
+    int s = fnet_ru4(net.dims[l]);
+    while ((s & 15) != 4) s += 4;
+    m.wS[l] = s;
+    m.wOff[l] = off;
+    off += fnet_ru8(net.dims[l + 1]) * s;
+    m.nGradTiles += (fnet_ru8(net.dims[l]) >> 3) * (fnet_ru8(net.dims[l + 1]) >> 3);
+    m.nBias += net.dims[l + 1];
+  }
+  m.bOff[0] = off;
+  for (int l = 1; l < net.L; l++) { m.bOff[l] = off; off += fnet_ru8(net.dims[l]); }
+  m.wTotal = off + 8;
+  int r = 0;
+  for (int l = 0; l < net.L; l++) { m.aOff[l] = r; r += fnet_ru8(net.dims[l]); }
+  m.rowsA = r;
+  m.dOff[0] = r;
+  for (int l = 1; l < net.L; l++) { m.dOff[l] = r; r += fnet_ru8(net.dims[l]); }
+  m.rows = r;
+  return m;
+}
+
+__host__ inline size_t bpnn_mma_smem_bytes(const NetTables &net, int mode) {
+  const MmaLayout m = mma_layout(net);
+  return ((size_t)m.wTotal + (size_t)FNET_MMA_WARPS * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
+}
+// limits of this path (else mlp.cuh): bias accumulators are one per thread, gradient tiles
+// <= MAXSLOTS per warp, everything in 220 KB of shared memory
+__host__ inline bool bpnn_mma_fits(const NetTables &net) {
+  const MmaLayout m = mma_layout(net);
+  return m.nBias <= FNET_MMA_WARPS * 32 && m.nGradTiles <= FNET_MMA_WARPS * FNET_MMA_MAXSLOTS &&
+         bpnn_mma_smem_bytes(net, 0) <= 220 * 1024;
+}
+
+// D += A(8x4, row) * B(4x8, col).  Lane (g = lane / 4, c = lane % 4) holds A[g][c], B[c][g] and
+// D[g][2c], D[g][2c + 1].
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// weights of one species: serialised ww(i,o) at i + din*o (network.F90:413-419) -> [o][wS] padded
+__device__ __forceinline__ void mma_load_weights(const NetTables &net, const MmaLayout &m,
+                                                 const double *__restrict__ wb, double *__restrict__ wsm) {
+  for (int e = threadIdx.x; e < m.wTotal; e += blockDim.x) wsm[e] = 0.0;
+  __syncthreads();
+  for (int l = 0; l + 1 < net.L; l++) {
+    const int din = net.dims[l], dout = net.dims[l + 1];
+    const double *W = wb + net.woff[l];
+    for (int e = threadIdx.x; e < din * dout; e += blockDim.x) {
+      const int i = e % din, o = e / din;
+      wsm[m.wOff[l] + o * m.wS[l] + i] = W[e];
+    }
+  }
+  for (int l = 1; l < net.L; l++)
+    for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = wb[net.boff[l] + e];
+}
+
+// forward layer of one warp tile: out[o][t] = f(sum_i W[o][i] in[i][t] + b[o]); DERIV also
+// stores f'(z) (later overwritten by the delta)
+template <bool DERIV>
+__device__ __forceinline__ void mma_forward(int din, int dout, int actId, const double *__restrict__ W, int wS,
+                                            const double *__restrict__ bias, const double *__restrict__ in,
+                                            double *__restrict__ out, double *__restrict__ dact, int lane) {
+  const int g = lane >> 2, c = lane & 3;
+  const int KT = fnet_ru4(din) >> 2, NT = fnet_ru8(dout) >> 3;
+  for (int nt0 = 0; nt0 < NT; nt0 += 4) {
+    double acc[2][4][2];
+#pragma unroll
+    for (int nc = 0; nc < 4; nc++) {
+      const int nb = 8 * min(nt0 + nc, NT - 1) + 2 * c;
+      const double b0 = bias[nb], b1 = bias[nb + 1];
+      acc[0][nc][0] = b0; acc[0][nc][1] = b1; acc[1][nc][0] = b0; acc[1][nc][1] = b1;
+    }
+    const double *ip = in + c * FNET_MMA_TS + g;
+    const double *wp = W + (size_t)(8 * nt0 + g) * wS + c;
+#pragma unroll 2
+    for (int kt = 0; kt < KT; kt++) {
+      const double a0 = ip[(4 * kt) * FNET_MMA_TS], a1 = ip[(4 * kt) * FNET_MMA_TS + 8];
+#pragma unroll
+      for (int nc = 0; nc < 4; nc++)
+        if (nt0 + nc < NT) {
+          const double b = wp[(size_t)(8 * nc) * wS + 4 * kt];
+          dmma(acc[0][nc], a0, b);
+          dmma(acc[1][nc], a1, b);
+        }
+    }
+#pragma unroll
+    for (int nc = 0; nc < 4; nc++)
+      if (nt0 + nc < NT) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int o = 8 * (nt0 + nc) + 2 * c + e;
+          if (o < dout) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+              const double x = acc[mt][nc][e];
+              const double v = act_f<double>(actId, x);
+              out[o * FNET_MMA_TS + 8 * mt + g] = v;
+              if (DERIV) dact[o * FNET_MMA_TS + 8 * mt + g] = act_d<double>(actId, x, v);
+            }
+          }
+        }
+      }
+  }
+}
+
+// backward layer of one warp tile: dl[i][t] = (sum_o W[o][i] dn[o][t]) * f'(z)[i][t]
+// (network.F90:282-288); dl holds f'(z) on entry
+__device__ __forceinline__ void mma_backward(int din, int dout, const double *__restrict__ W, int wS,
+                                             const double *__restrict__ dn, double *__restrict__ dl, int lane) {
+  const int g = lane >> 2, c = lane & 3;
+  const int KT = fnet_ru4(dout) >> 2, NT = fnet_ru8(din) >> 3;
+  for (int nt0 = 0; nt0 < NT; nt0 += 4) {
+    double acc[2][4][2];
+#pragma unroll
+    for (int nc = 0; nc < 4; nc++) { acc[0][nc][0] = 0.0; acc[0][nc][1] = 0.0; acc[1][nc][0] = 0.0; acc[1][nc][1] = 0.0; }
+    const double *ip = dn + c * FNET_MMA_TS + g;
+    const double *wp = W + (size_t)c * wS + 8 * nt0 + g;
+#pragma unroll 2
+    for (int kt = 0; kt < KT; kt++) {
+      const double a0 = ip[(4 * kt) * FNET_MMA_TS], a1 = ip[(4 * kt) * FNET_MMA_TS + 8];
+#pragma unroll
+      for (int nc = 0; nc < 4; nc++)
+        if (nt0 + nc < NT) {
+          const double b = wp[(size_t)(4 * kt) * wS + 8 * nc];
+          dmma(acc[0][nc], a0, b);
+          dmma(acc[1][nc], a1, b);
+        }
+    }
+#pragma unroll
+    for (int nc = 0; nc < 4; nc++)
+      if (nt0 + nc < NT) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int i = 8 * (nt0 + nc) + 2 * c + e;
+          if (i < din) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+              double *p = dl + i * FNET_MMA_TS + 8 * mt + g;
+              *p = acc[mt][nc][e] * *p;
+            }
+          }
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MODE 0: training gradient -> partials[cta][nSpecies*nTot]; MODE 2: forward only -> raw[atom][k].
+// `tiles` holds the ROUNDS: (start, count <= 64, species) triples of the species-sorted atom
+// order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 16 w .. 16 w + 15.
+// smem: weights | warp 0 tile | warp 1 tile | ...   (tile: a_0 .. a_{L-1} | delta_1 .. delta_{L-1})
+// ------------------------------------------------------------------------------------------
+template <int MODE, int NSLOT>
+__global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 6 ? 2 : 1))
+k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
+           int nFeat, const double *__restrict__ wb, NetTables net, const int *__restrict__ structOf,
+           const int *__restrict__ offsets, const double *__restrict__ gS, const double *__restrict__ at,
+           const double *__restrict__ aw, const double *__restrict__ dsw, int nG, int nA, int lossId,
+           double *__restrict__ partials, double *__restrict__ raw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TS = FNET_MMA_TS, TA = FNET_MMA_TA, NW = FNET_MMA_WARPS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int L = net.L, d0 = net.dims[0];
+  const MmaLayout m = mma_layout(net);
+  const int rows = (MODE == 2) ? m.rowsA : m.rows;
+  double *wsm = (double *)smem_raw;
+  double *tiles0 = wsm + m.wTotal;
+  double *T = tiles0 + (size_t)warp * rows * TS;
+  for (int e = lane; e < rows * TS; e += 32) T[e] = 0.0;      // padding rows stay zero from here on
+
+  // ---- weight-gradient tiles owned by this warp: q = warp*per + s <-> (layer, i-tile, o-tile) ----
+  int aRow[NSLOT], dRow[NSLOT], gInfo[NSLOT];
+  bool newA[NSLOT];
+  double acc[NSLOT][2];
+  double bacc = 0.0;
+  int nMine = 0, bRow = -1, bIdx = -1;
+  if (MODE == 0) {
+    const int per = (m.nGradTiles + NW - 1) / NW;
+    const int q0 = warp * per, q1 = min(m.nGradTiles, q0 + per);
+    nMine = max(q1 - q0, 0);
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+      acc[s][0] = 0.0; acc[s][1] = 0.0;
+      aRow[s] = 0; dRow[s] = 0; gInfo[s] = -1; newA[s] = false;
+      if (s < nMine) {
+        int q = q0 + s, l = 0;
+        while (true) {
+          const int cnt = (fnet_ru8(net.dims[l]) >> 3) * (fnet_ru8(net.dims[l + 1]) >> 3);
+          if (q < cnt) break;
+          q -= cnt; l++;
+        }
+        const int ntl = fnet_ru8(net.dims[l + 1]) >> 3;
+        const int mt = q / ntl, nt = q % ntl;
+        aRow[s] = m.aOff[l] + 8 * mt;
+        dRow[s] = m.dOff[l + 1] + 8 * nt;
+        gInfo[s] = (l << 16) | (mt << 8) | nt;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) newA[s] = (s == 0) || (aRow[s] != aRow[s > 0 ? s - 1 : 0]);
+    // bias gradients: thread tid <-> (layer l >= 1, output o)
+    int t = threadIdx.x;
+    if (t < m.nBias) {
+      int l = 1;
+      while (t >= net.dims[l]) { t -= net.dims[l]; l++; }
+      bRow = m.dOff[l] + t;
+      bIdx = net.boff[l] + t;
+    }
+  }
+  auto flush = [&](int sp) {     // registers -> this CTA's partial row of species sp (visited once per CTA)
+    double *gp = partials + ((size_t)blockIdx.x * net.nSpecies + sp) * net.nTot;
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) {
+      if (s < nMine) {
+        const int l = gInfo[s] >> 16, mt = (gInfo[s] >> 8) & 255, nt = gInfo[s] & 255;
+        const int din = net.dims[l], dout = net.dims[l + 1];
+        const int i = 8 * mt + g;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int o = 8 * nt + 2 * c + e;
+          if (i < din && o < dout) gp[net.woff[l] + i + din * o] = acc[s][e];
+        }
+      }
+      acc[s][0] = 0.0; acc[s][1] = 0.0;
+    }
+    if (bIdx >= 0) gp[bIdx] = bacc;
+    bacc = 0.0;
+  };
+
+  // A CTA walks a contiguous range of ROUNDS: (start, count <= 64, species) entries of the
+  // species-sorted atom order; warp w takes atoms [start + 16 w, start + 16 w + 16) of the round.
+  // The next round's entry and atom indices are fetched one round ahead and its feature rows are
+  // pulled into L2, so a tile waits for one L2 round trip instead of a chain of dependent HBM loads.
+  const int round0 = (int)(((long long)nTiles * blockIdx.x) / gridDim.x);
+  const int round1 = (int)(((long long)nTiles * (blockIdx.x + 1)) / gridDim.x);
+  int curSp = -1;
+  int eStart = 0, eCount = 0, eSp = 0, myAtom = -1;
+  if (round0 < round1) {
+    eStart = tiles[3 * round0]; eCount = tiles[3 * round0 + 1]; eSp = tiles[3 * round0 + 2];
+    const int cnt0 = min(max(eCount - TA * warp, 0), TA);
+    myAtom = (lane < cnt0) ? perm[eStart + TA * warp + lane] : -1;
+  }
+  for (int r = round0; r < round1; r++) {
+    const int sp = eSp, nIn = (eCount + TA - 1) / TA;
+    const int count = min(max(eCount - TA * warp, 0), TA);
+    // next round's entry (consumed at the bottom of the loop)
+    int nStart = 0, nCount = 0, nSp = 0;
+    if (r + 1 < round1) { nStart = tiles[3 * r + 3]; nCount = tiles[3 * r + 4]; nSp = tiles[3 * r + 5]; }
+    if (sp != curSp) {
+      __syncthreads();
+      if (MODE == 0 && curSp >= 0) flush(curSp);
+      mma_load_weights(net, m, wb + (size_t)net.nTot * sp, wsm);
+      curSp = sp;
+      __syncthreads();
+    }
+    int nextAtom = -1;
+    // per-atom loss-gradient scale (MODE 0): issued now, consumed after the forward sweep
+    double lgScale = 0.0, lgG0 = 0.0, lgG1 = 0.0;
+    int lgStruct = 0;
+    if (warp < nIn) {
+      if (MODE == 0 && myAtom >= 0) {
+        lgStruct = structOf[myAtom];
+        lgScale = dsw[lgStruct] * aw[myAtom] / (double)(offsets[lgStruct + 1] - offsets[lgStruct]);   // bpnn.F90:446,698
+        if (nG > 0) lgG0 = gS[(size_t)nG * lgStruct];
+        if (nG > 1) lgG1 = gS[(size_t)nG * lgStruct + 1];
+      }
+      // ---- features -> a_0[f][t]: lane <-> feature (coalesced rows), all 16 atoms in flight ----
+      for (int f0 = 0; f0 < d0; f0 += 32) {
+        const int f = f0 + lane;
+        double v[TA];
+#pragma unroll
+        for (int u = 0; u < TA; u++) {
+          const int atom = __shfl_sync(0xffffffffu, myAtom, u);
+          v[u] = (atom >= 0 && f < d0) ? feat[(size_t)nFeat * atom + f] : 0.0;
+        }
+        if (f0 == 0 && r + 1 < round1) {      // atom indices of the next round, behind the feature loads
+          const int cntN = min(max(nCount - TA * warp, 0), TA);
+          nextAtom = (lane < cntN) ? perm[nStart + TA * warp + lane] : -1;
+        }
+        if (f < d0) {
+#pragma unroll
+          for (int u = 0; u < TA; u++) T[f * TS + u] = v[u];
+        }
+      }
+      __syncwarp();
+      // ---- forward ----
+      for (int l = 1; l < L; l++) {
+        const bool last = (l == L - 1);
+        const int actId = last ? FNETGPU_ACT_LINEAR : net.act;   // network.F90:391
+        const double *in = T + m.aOff[l - 1] * TS;
+        double *out = T + m.aOff[l] * TS;
+        if (MODE == 2 || last)
+          mma_forward<false>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out, nullptr, lane);
+        else
+          mma_forward<true>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out,
+                            T + m.dOff[l] * TS, lane);
+        __syncwarp();
+        if (l == 1) {     // next round's feature rows -> L2 (128-byte lines; lanes 16..31 take the odd lines)
+          const int pa = __shfl_sync(0xffffffffu, nextAtom, lane & 15);
+          if (pa >= 0) {
+            const char *row = (const char *)(feat + (size_t)nFeat * pa);
+            for (int b = (lane >> 4) * 128; b < d0 * 8; b += 256)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+          }
+        }
+      }
+      if (MODE == 2) {
+        const double *o = T + m.aOff[L - 1] * TS;
+        if (lane < count)
+          for (int k = 0; k < net.nOut; k++) raw[(size_t)net.nOut * myAtom + k] = o[k * TS + lane];
+        __syncwarp();
+      } else {
+        // ---- output layer (linear): delta = lossgrad * scale (network.F90:276, bpnn.F90:446,677-701) ----
+        double *dL = T + m.dOff[L - 1] * TS;
+        if (lane < TA) {
+          const int s = lgStruct;
+          const double scale = lgScale;
+          for (int k = 0; k < net.nOut; k++) {
+            double gr = 0.0;
+            if (myAtom >= 0) {
+              if (k < nG) gr = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gS[(size_t)nG * s + k];
+              else gr = loss_grad_fn(lossId, T[(m.aOff[L - 1] + k) * TS + lane], at[(size_t)nA * myAtom + (k - nG)]);
+            }
+            dL[k * TS + lane] = gr * scale;
+          }
+        }
+        __syncwarp();
+        // ---- hidden layers: delta_{l} = (W_l delta_{l+1}) * f'(z_l), l = L-2 .. 1 ----
+        for (int l = L - 2; l >= 1; l--) {
+          mma_backward(net.dims[l], net.dims[l + 1], wsm + m.wOff[l], m.wS[l], T + m.dOff[l + 1] * TS, T + m.dOff[l] * TS, lane);
+          __syncwarp();
+        }
+      }
+    }
+    if (MODE == 0) {
+      __syncthreads();
+      // ---- weight gradients of the round: K = atoms of all tiles of the round ----
+      for (int w2 = 0; w2 < nIn; w2++) {
+        const double *tb = tiles0 + (size_t)w2 * rows * TS + g * TS + c;
+#pragma unroll
+        for (int kt = 0; kt < TA / 4; kt++) {
+          double a = 0.0;
+#pragma unroll
+          for (int s = 0; s < NSLOT; s++)
+            if (s < nMine) {
+              if (newA[s]) a = tb[aRow[s] * TS + 4 * kt];
+              const double b = tb[dRow[s] * TS + 4 * kt];
+              dmma(acc[s], a, b);
+            }
+        }
+        if (bRow >= 0) {
+          const double *dr = tiles0 + (size_t)w2 * rows * TS + bRow * TS;
+          double sb = 0.0;
+#pragma unroll
+          for (int t = 0; t < TA; t++) sb += dr[t];
+          bacc += sb;
+        }
+      }
+      __syncthreads();
+    }
+    if (warp >= nIn && r + 1 < round1) {     // idle in this round: still fetch the next round's atoms
+      const int cntN = min(max(nCount - TA * warp, 0), TA);
+      nextAtom = (lane < cntN) ? perm[nStart + TA * warp + lane] : -1;
+    }
+    eStart = nStart; eCount = nCount; eSp = nSp; myAtom = nextAtom;
+  }
+  if (MODE == 0 && curSp >= 0) flush(curSp);
+}

@@ -17,8 +17,8 @@ def fb():
 PATHS = ["auto", "cells"]   # whole-structure neighbour search (all fixtures are small structures) and the cell list
 
 
-def _setup(fb, case, precision=64, acsf_path="auto"):
-    ctx = fb.Context(precision=precision, acsf_path=acsf_path)
+def _setup(fb, case, precision=64, acsf_path="auto", mlp="auto"):
+    ctx = fb.Context(precision=precision, acsf_path=acsf_path, mlp=mlp)
     ds = case.dataset
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=case.zmeans is not None,
@@ -55,11 +55,13 @@ def test_predictions_and_forces(fb, entry, path):
 SD = gio.cases(mode=("train",), training=("sd",))
 
 
+@pytest.mark.parametrize("mlp", ["auto", "legacy"])   # DMMA kernels / register-tiled kernels
 @pytest.mark.parametrize("entry", SD, ids=[e["case"] for e in SD])
-def test_sd_training_step(fb, entry):
+def test_sd_training_step(fb, entry, mlp):
     from oracle import oracle as orc
     case = gio.Case(entry)
-    ctx, acsf, net = _setup(fb, case)
+    ctx, acsf, net = _setup(fb, case, mlp=mlp)
+    assert ctx.mlp_path() == (1 if mlp == "auto" else 0)
     ds = case.dataset
     wb0 = case.wb()
     dd, loss = net.update_gradients(0, loss=case.loss_name())

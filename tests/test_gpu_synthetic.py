@@ -42,11 +42,11 @@ STRUCT, CELLS = (2,), (0, 1)   # values of Context.acsf_path()
 
 
 def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3, acsf_path="auto",
-                expect_path=None):
+                expect_path=None, mlp="auto", expect_mlp=None):
     """features (raw + z-scored), statistics, predictions, loss, gradient and forces vs the oracle"""
     fd = funcs.asdicts()
     nt = _nthreads()
-    ctx = fb.Context(acsf_path=acsf_path)
+    ctx = fb.Context(acsf_path=acsf_path, mlp=mlp)
     ctx.upload(0, ds)
     a_raw = fb.Acsf(ctx, funcs, standardize=False)
     a_raw.calculate(0)
@@ -69,6 +69,10 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
     net = fb.Bpnn(ctx, dims, nsp, act)
     wb = np.random.default_rng(seed).uniform(-0.5, 0.5, size=(nsp, _ntot(dims)))
     net.set_params(wb)
+    if mlp == "legacy":
+        expect_mlp = 0
+    if expect_mlp is not None:
+        assert ctx.mlp_path() == expect_mlp, ctx.mlp_path()
     raw = net.predict_batch(0)
     raw_o = orc.predict(zref, ds.globalsp, dims, act, wb, nthreads=nt)
     assert np.allclose(raw, raw_o, rtol=RTOL, atol=ATOL), _md(raw, raw_o)
@@ -93,21 +97,39 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json configs at oracle-sized samples
 # ---------------------------------------------------------------------------------------------
+MLPS = ["auto", "legacy"]      # precision 64 subnetworks: DMMA kernels (mlp_mma.cuh) or the register-tiled ones (mlp.cuh)
+
+
+@pytest.mark.parametrize("mlp", MLPS)
 @pytest.mark.parametrize("path", PATHS)
-def test_c2_si_bulk(fb, orc, path):
+def test_c2_si_bulk(fb, orc, path, mlp):
     from fortnet_b200 import synthetic
     ds = synthetic.si_bulk(n_struct=12, seed=20260001)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
-    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT)
+    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1)
 
 
+@pytest.mark.parametrize("mlp", MLPS)
 @pytest.mark.parametrize("path", PATHS)
-def test_c3_tio2(fb, orc, path):
+def test_c3_tio2(fb, orc, path, mlp):
     from fortnet_b200 import synthetic
     ds = synthetic.tio2(n_struct=3, seed=20260002)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
     assert len(funcs) == 64
-    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT)
+    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1)
+
+
+@pytest.mark.parametrize("dims,expect", [([9, 1], 1), ([9, 3, 1], 1), ([9, 17, 9, 33, 2, 1], 1), ([9, 40, 40, 40, 1], 1),
+                                         ([9, 100, 100, 1], 0), ([9, 70, 60, 1], 0)])
+def test_subnetwork_shapes(fb, orc, dims, expect):
+    """layer widths that are not multiples of the 8x8x4 DMMA tile, a network without hidden layer,
+    deep / narrow ones, and widths beyond the DMMA path's limits (-> register-tiled kernels);
+    ragged tiles (structures of 64 atoms, 3 structures = 192 atoms = 12 tiles of 16)"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=3, seed=12)
+    ds.gtargets[:] = np.random.default_rng(6).uniform(1.0, 2.0, size=ds.gtargets.shape)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 5, 4)
+    _full_check(fb, orc, ds, funcs, dims, forces=True, expect_mlp=expect)
 
 
 def test_c5_dense_liquid_values(fb, orc):
@@ -156,7 +178,7 @@ def _mixed_functions(fb, rc, zs=None):
 
 
 @pytest.mark.parametrize("path", PATHS)
-def test_ragged_clusters_and_single_atoms(fb, orc, path):
+def test_ragged_clusters_and_single_atoms(fb, orc, path, mlp="auto"):
     """non-periodic structures of 1..40 atoms in one batch (prediction/** goldens are clusters);
     a single atom has no neighbours -> all ACSF are 0 (before the z-score)"""
     rng = np.random.default_rng(21)
