@@ -1050,10 +1050,16 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
   if constexpr (std::is_same<real, double>::value) {
     if (use_mma<real>(ctx)) {
       const MmaLaunch M = plan_mma(ctx, s, 2);
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem));
-      LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1><<<M.grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(
-                                 s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, n,
-                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw)));
+#define FNET_MMA_FWD(FCH)                                                                                         \
+      do {                                                                                                        \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<2, 1, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1, FCH><<<M.grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(      \
+                                   s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,          \
+                                   (const double *)ctx->d_wb, n, nullptr, nullptr, nullptr, nullptr, nullptr,     \
+                                   nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw)));                         \
+      } while (0)
+      if (n.dims[0] <= 32) FNET_MMA_FWD(1); else FNET_MMA_FWD(2);
+#undef FNET_MMA_FWD
       return 0;
     }
   }
@@ -1097,15 +1103,18 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
       const MmaLayout ml = mma_layout(n);
       const int perWarp = (ml.nGradTiles + FNET_MMA_WARPS - 1) / FNET_MMA_WARPS;
 #define FNET_MMA_GRAD(NSLOT)                                                                                      \
+      do { if (n.dims[0] <= 32) FNET_MMA_GRAD2(NSLOT, 1); else FNET_MMA_GRAD2(NSLOT, 2); } while (0)
+#define FNET_MMA_GRAD2(NSLOT, FCH)                                                                                \
       do {                                                                                                        \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
-        LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(        \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(   \
                                     s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                     (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
                                     s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr)));   \
       } while (0)
       if (perWarp <= 6) FNET_MMA_GRAD(6); else if (perWarp <= 12) FNET_MMA_GRAD(12); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
 #undef FNET_MMA_GRAD
+#undef FNET_MMA_GRAD2
       launched = true;
     }
   }

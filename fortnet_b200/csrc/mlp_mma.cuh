@@ -108,6 +108,22 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
     for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = wb[net.boff[l] + e];
 }
 
+// transfer function as a separate element-wise pass over a warp tile (z -> f(z), optionally f'(z)):
+// ONE copy of the activation code in the kernel (the unrolled fragment epilogue would inline it 16
+// times per call site) and an even split of the dout*16 elements over the lanes
+template <bool DERIV>
+__device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane) {
+#pragma unroll 1
+  for (int idx = lane; idx < dout * FNET_MMA_TA; idx += 32) {
+    const int o = idx >> 4, t = idx & 15;
+    double *p = out + o * FNET_MMA_TS + t;
+    const double x = *p;
+    const double v = act_f<double>(actId, x);
+    *p = v;
+    if (DERIV) dact[o * FNET_MMA_TS + t] = act_d<double>(actId, x, v);
+  }
+}
+
 // forward layer of one warp tile: out[o][t] = f(sum_i W[o][i] in[i][t] + b[o]); DERIV also
 // stores f'(z) (later overwritten by the delta)
 template <bool DERIV>
@@ -144,16 +160,15 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
         for (int e = 0; e < 2; e++) {
           const int o = 8 * (nt0 + nc) + 2 * c + e;
           if (o < dout) {
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-              const double x = acc[mt][nc][e];
-              const double v = act_f<double>(actId, x);
-              out[o * FNET_MMA_TS + 8 * mt + g] = v;
-              if (DERIV) dact[o * FNET_MMA_TS + 8 * mt + g] = act_d<double>(actId, x, v);
-            }
+            out[o * FNET_MMA_TS + g] = acc[0][nc][e];
+            out[o * FNET_MMA_TS + 8 + g] = acc[1][nc][e];
           }
         }
       }
+  }
+  if (actId != FNETGPU_ACT_LINEAR || DERIV) {
+    __syncwarp();
+    mma_activate<DERIV>(actId, dout, out, dact, lane);
   }
 }
 
@@ -204,7 +219,7 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
 // order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 16 w .. 16 w + 15.
 // smem: weights | warp 0 tile | warp 1 tile | ...   (tile: a_0 .. a_{L-1} | delta_1 .. delta_{L-1})
 // ------------------------------------------------------------------------------------------
-template <int MODE, int NSLOT>
+template <int MODE, int NSLOT, int FCH>
 __global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 6 ? 2 : 1))
 k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
            int nFeat, const double *__restrict__ wb, NetTables net, const int *__restrict__ structOf,
@@ -284,23 +299,46 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
 
   // A CTA walks a contiguous range of ROUNDS: (start, count <= 64, species) entries of the
   // species-sorted atom order; warp w takes atoms [start + 16 w, start + 16 w + 16) of the round.
-  // The next round's entry and atom indices are fetched one round ahead and its feature rows are
-  // pulled into L2, so a tile waits for one L2 round trip instead of a chain of dependent HBM loads.
+  // Software pipeline over the rounds, so that no tile waits for a chain of dependent HBM loads:
+  //   entries two rounds ahead, atom indices two rounds ahead, feature rows of round r+2 pulled
+  //   into L2, feature rows of round r+1 loaded into registers (pf) while round r's weight
+  //   gradients are accumulated (MODE 0) / its hidden layers are evaluated (MODE 2).
   const int round0 = (int)(((long long)nTiles * blockIdx.x) / gridDim.x);
   const int round1 = (int)(((long long)nTiles * (blockIdx.x + 1)) / gridDim.x);
   int curSp = -1;
-  int eStart = 0, eCount = 0, eSp = 0, myAtom = -1;
-  if (round0 < round1) {
-    eStart = tiles[3 * round0]; eCount = tiles[3 * round0 + 1]; eSp = tiles[3 * round0 + 2];
-    const int cnt0 = min(max(eCount - TA * warp, 0), TA);
-    myAtom = (lane < cnt0) ? perm[eStart + TA * warp + lane] : -1;
-  }
+  int e0[3] = {0, 0, 0}, e1[3] = {0, 0, 0};           // entries of round r and r + 1
+  int atom0 = -1, atom1 = -1;                         // lane < 16: atom of this warp's tile in round r / r + 1
+  double pf[FCH][TA];                                 // features of round r (lane <-> feature 32 ch + lane)
+  auto load_entry = [&](int r, int (&e)[3]) {
+    e[0] = e[1] = e[2] = 0;
+    if (r < round1) { e[0] = tiles[3 * r]; e[1] = tiles[3 * r + 1]; e[2] = tiles[3 * r + 2]; }
+  };
+  auto load_atom = [&](const int (&e)[3]) -> int {
+    const int cnt = min(max(e[1] - TA * warp, 0), TA);
+    return (lane < cnt) ? perm[e[0] + TA * warp + lane] : -1;
+  };
+  auto load_features = [&](int atomv) {
+#pragma unroll
+    for (int ch = 0; ch < FCH; ch++) {
+      const int f = 32 * ch + lane;
+#pragma unroll
+      for (int u = 0; u < TA; u++) {
+        const int atom = __shfl_sync(0xffffffffu, atomv, u);
+        pf[ch][u] = (atom >= 0 && f < d0) ? feat[(size_t)nFeat * atom + f] : 0.0;
+      }
+    }
+  };
+  load_entry(round0, e0);
+  load_entry(round0 + 1, e1);
+  atom0 = load_atom(e0);
+  atom1 = load_atom(e1);
+  load_features(atom0);
   for (int r = round0; r < round1; r++) {
-    const int sp = eSp, nIn = (eCount + TA - 1) / TA;
-    const int count = min(max(eCount - TA * warp, 0), TA);
-    // next round's entry (consumed at the bottom of the loop)
-    int nStart = 0, nCount = 0, nSp = 0;
-    if (r + 1 < round1) { nStart = tiles[3 * r + 3]; nCount = tiles[3 * r + 4]; nSp = tiles[3 * r + 5]; }
+    const int sp = e0[2], nIn = (e0[1] + TA - 1) / TA;
+    const int count = min(max(e0[1] - TA * warp, 0), TA);
+    const int myAtom = atom0;
+    int e2[3];
+    load_entry(r + 2, e2);
     if (sp != curSp) {
       __syncthreads();
       if (MODE == 0 && curSp >= 0) flush(curSp);
@@ -308,7 +346,6 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       curSp = sp;
       __syncthreads();
     }
-    int nextAtom = -1;
     // per-atom loss-gradient scale (MODE 0): issued now, consumed after the forward sweep
     double lgScale = 0.0, lgG0 = 0.0, lgG1 = 0.0;
     int lgStruct = 0;
@@ -319,8 +356,16 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         if (nG > 0) lgG0 = gS[(size_t)nG * lgStruct];
         if (nG > 1) lgG1 = gS[(size_t)nG * lgStruct + 1];
       }
-      // ---- features -> a_0[f][t]: lane <-> feature (coalesced rows), all 16 atoms in flight ----
-      for (int f0 = 0; f0 < d0; f0 += 32) {
+      // ---- features -> a_0[f][t] ----
+#pragma unroll
+      for (int ch = 0; ch < FCH; ch++) {
+        const int f = 32 * ch + lane;
+        if (f < d0) {
+#pragma unroll
+          for (int u = 0; u < TA; u++) T[f * TS + u] = pf[ch][u];
+        }
+      }
+      for (int f0 = 32 * FCH; f0 < d0; f0 += 32) {     // rows beyond the register window: loaded in place
         const int f = f0 + lane;
         double v[TA];
 #pragma unroll
@@ -328,15 +373,12 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           const int atom = __shfl_sync(0xffffffffu, myAtom, u);
           v[u] = (atom >= 0 && f < d0) ? feat[(size_t)nFeat * atom + f] : 0.0;
         }
-        if (f0 == 0 && r + 1 < round1) {      // atom indices of the next round, behind the feature loads
-          const int cntN = min(max(nCount - TA * warp, 0), TA);
-          nextAtom = (lane < cntN) ? perm[nStart + TA * warp + lane] : -1;
-        }
         if (f < d0) {
 #pragma unroll
           for (int u = 0; u < TA; u++) T[f * TS + u] = v[u];
         }
       }
+      if (MODE == 2) load_features(atom1);             // next round's rows: in flight during the whole sweep
       __syncwarp();
       // ---- forward ----
       for (int l = 1; l < L; l++) {
@@ -350,14 +392,6 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           mma_forward<true>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out,
                             T + m.dOff[l] * TS, lane);
         __syncwarp();
-        if (l == 1) {     // next round's feature rows -> L2 (128-byte lines; lanes 16..31 take the odd lines)
-          const int pa = __shfl_sync(0xffffffffu, nextAtom, lane & 15);
-          if (pa >= 0) {
-            const char *row = (const char *)(feat + (size_t)nFeat * pa);
-            for (int b = (lane >> 4) * 128; b < d0 * 8; b += 256)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
-          }
-        }
       }
       if (MODE == 2) {
         const double *o = T + m.aOff[L - 1] * TS;
@@ -387,8 +421,11 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         }
       }
     }
+    // atoms of round r + 2; their feature rows -> L2 (128-byte lines; lanes 16..31 take the odd lines)
+    const int atom2 = load_atom(e2);
     if (MODE == 0) {
       __syncthreads();
+      load_features(atom1);                              // next round's rows: in flight during the gradient sweep
       // ---- weight gradients of the round: K = atoms of all tiles of the round ----
       for (int w2 = 0; w2 < nIn; w2++) {
         const double *tb = tiles0 + (size_t)w2 * rows * TS + g * TS + c;
@@ -413,11 +450,18 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       }
       __syncthreads();
     }
-    if (warp >= nIn && r + 1 < round1) {     // idle in this round: still fetch the next round's atoms
-      const int cntN = min(max(nCount - TA * warp, 0), TA);
-      nextAtom = (lane < cntN) ? perm[nStart + TA * warp + lane] : -1;
+    if (MODE == 2 && warp >= nIn) load_features(atom1);   // idle in this round (short last round of a species)
+    {
+      const int pa = __shfl_sync(0xffffffffu, atom2, lane & 15);
+      if (pa >= 0) {
+        const char *row = (const char *)(feat + (size_t)nFeat * pa);
+        for (int b = (lane >> 4) * 128; b < d0 * 8; b += 256)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+      }
     }
-    eStart = nStart; eCount = nCount; eSp = nSp; myAtom = nextAtom;
+    e0[0] = e1[0]; e0[1] = e1[1]; e0[2] = e1[2];
+    e1[0] = e2[0]; e1[1] = e2[1]; e1[2] = e2[2];
+    atom0 = atom1; atom1 = atom2;
   }
   if (MODE == 0 && curSp >= 0) flush(curSp);
 }

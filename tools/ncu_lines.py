@@ -56,7 +56,12 @@ def main():
             cur_rows.append(r)
     # pick the report block whose instruction count matches the disassembly (or env NCU_BLOCK)
     bi = int(os.environ.get("NCU_BLOCK", "-1"))
-    if bi < 0:
+    want = os.environ.get("NCU_NAME")          # substring of the demangled kernel name, e.g. "k_bpnn_mma<(int)0"
+    if want:
+        cand = [k for k, (nm, rr) in enumerate(blocks) if want in nm]
+        exact = [k for k in cand if len(blocks[k][1]) - 1 == len(inst_lines)]
+        bi = (exact or cand or [0])[0]
+    elif bi < 0:
         bi = 0
         for k, (nm, rr) in enumerate(blocks):
             if len(rr) - 1 == len(inst_lines):
