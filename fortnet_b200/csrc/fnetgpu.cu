@@ -1043,6 +1043,13 @@ static MmaLaunch plan_mma(const fnetgpu_ctx *ctx, const Slot &s, int mode) {
   M.grid = std::max(1, std::min(s.nTiles16, ctx->nSM * perSM));
   return M;
 }
+// persistent grid = what is actually resident (registers can bind before shared memory does)
+template <typename K>
+static int mma_grid(const fnetgpu_ctx *ctx, const Slot &s, K kernel, size_t smem, int fallback) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, FNET_MMA_WARPS * 32, smem) != cudaSuccess || nb < 1) return fallback;
+  return std::max(1, std::min(s.nTiles16, ctx->nSM * nb));
+}
 
 template <typename real>
 static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
@@ -1053,7 +1060,8 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
 #define FNET_MMA_FWD(FCH)                                                                                         \
       do {                                                                                                        \
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<2, 1, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
-        LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1, FCH><<<M.grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(      \
+        const int fgrid = mma_grid(ctx, s, k_bpnn_mma<2, 1, FCH>, M.smem, M.grid);                                \
+        LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(       \
                                    s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,          \
                                    (const double *)ctx->d_wb, n, nullptr, nullptr, nullptr, nullptr, nullptr,     \
                                    nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw)));                         \

@@ -42,6 +42,7 @@ struct MmaLayout {
   int wTotal;                  // doubles (multiple of 2, + slack for the column over-read of the last row)
   int aOff[FNET_MAX_LAYERS];   // first row of a_l in a warp tile; block height roundup8(dims[l])
   int dOff[FNET_MAX_LAYERS];   // first row of f'(z_l), then delta_l (l >= 1); block height roundup8(dims[l])
+  int aOffF[FNET_MAX_LAYERS];  // forward-only tile: layers ping-pong between two row blocks
   int rowsA, rows;             // rows of the forward-only tile / of the training tile
   int nGradTiles;              // 8x8 output tiles of all weight gradients
   int nBias;                   // sum of dims[1..L-1]
@@ -65,7 +66,12 @@ __host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
   m.wTotal = off + 8;
   int r = 0;
   for (int l = 0; l < net.L; l++) { m.aOff[l] = r; r += fnet_ru8(net.dims[l]); }
-  m.rowsA = r;
+  {
+    int x = 0, y = 0;
+    for (int l = 0; l < net.L; l++) { if (l & 1) y = max(y, fnet_ru8(net.dims[l])); else x = max(x, fnet_ru8(net.dims[l])); }
+    for (int l = 0; l < net.L; l++) m.aOffF[l] = (l & 1) ? x : 0;
+    m.rowsA = x + y;
+  }
   m.dOff[0] = r;
   for (int l = 1; l < net.L; l++) { m.dOff[l] = r; r += fnet_ru8(net.dims[l]); }
   m.rows = r;
@@ -113,14 +119,45 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
 // times per call site) and an even split of the dout*16 elements over the lanes
 template <bool DERIV>
 __device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane) {
+  // four elements per lane and iteration: independent dependency chains (the FP64 exp / reciprocal
+  // sequences are latency-bound at two warps per scheduler)
+  const int n = dout * FNET_MMA_TA;
 #pragma unroll 1
-  for (int idx = lane; idx < dout * FNET_MMA_TA; idx += 32) {
-    const int o = idx >> 4, t = idx & 15;
-    double *p = out + o * FNET_MMA_TS + t;
-    const double x = *p;
-    const double v = act_f<double>(actId, x);
-    *p = v;
-    if (DERIV) dact[o * FNET_MMA_TS + t] = act_d<double>(actId, x, v);
+  for (int base = lane; base < n; base += 128) {
+    double x[4], v[4];
+    int off[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int idx = min(base + 32 * q, n - 1);
+      off[q] = (idx >> 4) * FNET_MMA_TS + (idx & 15);
+      x[q] = out[off[q]];
+    }
+    if (actId == FNETGPU_ACT_TANH) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = fnet_tanh(x[q]);
+    } else if (actId == FNETGPU_ACT_SIGMOID) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < 4; q++) v[q] = act_f<double>(actId, x[q]);
+    }
+    double d[4];
+    if (DERIV) {
+      if (actId == FNETGPU_ACT_TANH || actId == FNETGPU_ACT_SIGMOID) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) d[q] = act_d<double>(actId == FNETGPU_ACT_TANH ? FNETGPU_ACT_TANH : FNETGPU_ACT_SIGMOID, x[q], v[q]);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) d[q] = act_d<double>(actId, x[q], v[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (base + 32 * q < n) {
+        out[off[q]] = v[q];
+        if (DERIV) dact[off[q]] = d[q];
+      }
   }
 }
 
@@ -384,8 +421,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       for (int l = 1; l < L; l++) {
         const bool last = (l == L - 1);
         const int actId = last ? FNETGPU_ACT_LINEAR : net.act;   // network.F90:391
-        const double *in = T + m.aOff[l - 1] * TS;
-        double *out = T + m.aOff[l] * TS;
+        const double *in = T + (MODE == 2 ? m.aOffF[l - 1] : m.aOff[l - 1]) * TS;
+        double *out = T + (MODE == 2 ? m.aOffF[l] : m.aOff[l]) * TS;
         if (MODE == 2 || last)
           mma_forward<false>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out, nullptr, lane);
         else
@@ -394,7 +431,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         __syncwarp();
       }
       if (MODE == 2) {
-        const double *o = T + m.aOff[L - 1] * TS;
+        const double *o = T + m.aOffF[L - 1] * TS;
         if (lane < count)
           for (int k = 0; k < net.nOut; k++) raw[(size_t)net.nOut * myAtom + k] = o[k * TS + lane];
         __syncwarp();
