@@ -131,10 +131,20 @@ def cpu_baseline(name, target_seconds=12.0, threads=None):
     ds2, _, _, _, _ = workload(name, threads * per_thread * scale)
     ta, tg = one(ds2)
     atoms = ds2.n_atoms
+    # the reference's serial path: one thread on a sample sized for a few seconds
+    n_ser = max(1, min(ds2.n_struct, int(round(ds2.n_struct * 3.0 / max((ta + tg) * threads, 1e-3)))))
+    ds1, _, _, _, _ = workload(name, n_ser)
+    t0 = time.perf_counter()
+    v1 = orc.acsf(ds1.offsets, ds1.coords, ds1.periodic, ds1.latvecs, ds1.atnum, fd, nthreads=1)
+    orc.grad(ds1.offsets, v1, ds1.globalsp, dims, "tanh", wb, "mse", ds1.weights, ds1.atomic_weights,
+             ds1.gtargets, ds1.atargets, nthreads=1)
+    t_ser = time.perf_counter() - t0
     return {"value": atoms / (ta + tg), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d structures (%d atoms): oracle ACSF %.2f s + fwd/bwd %.3f s, %d OpenMP threads, "
                       "reference block partition" % (ds2.n_struct, atoms, ta, tg, threads),
-            "acsf_atoms_per_s": atoms / ta, "train_iter_atoms_per_s": atoms / tg}
+            "acsf_atoms_per_s": atoms / ta, "train_iter_atoms_per_s": atoms / tg,
+            "serial_value": ds1.n_atoms / t_ser,
+            "serial_sample": "%d structures (%d atoms) on 1 thread, %.2f s" % (ds1.n_struct, ds1.n_atoms, t_ser)}
 
 
 def run_reference(args, rank):
@@ -302,6 +312,17 @@ def main():
         alg_bytes = bytes_per_atom * N + 72 * ds.n_struct
         achieved = alg_bytes / (acsf_ms * 1e-3) / 1e9
         kshare = {k: v["ms_total"] / args.steps for k, v in prof.items()}
+        # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch,
+        # scaled by atoms when the launch size differs); None when no capture exists for this workload
+        traffic, ncu_extra = None, {}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json"))).get(args.workload)
+            if tr and args.precision == 64:
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (N / tr["atoms_per_launch"])
+                ncu_extra = {"ncu_issue_active_pct": tr["issue_active_pct"], "ncu_fp64_pipe_active_pct": tr["fp64_pipe_active_pct"],
+                             "ncu_warp_inst_per_atom": tr["warp_inst_per_atom"], "ncu_source": tr["source"]}
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": total_atoms / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -319,9 +340,12 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_acsf", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
-                         "algorithmic_bytes_per_atom": bytes_per_atom, "avg_launch_ms": acsf_ms, "peak_source": peak_src,
-                         "note": "FP64 angular ACSF is FP64-issue bound (SURVEY.md 8d); HBM fraction reported as the contract asks"},
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "algorithmic_bytes_per_atom": bytes_per_atom, "algorithmic_bytes": alg_bytes,
+                         "avg_launch_ms": acsf_ms, "peak_source": peak_src,
+                         "note": "FP64 angular ACSF is instruction-issue bound, not HBM bound (SURVEY.md 8d: ~45k FP64 "
+                                 "lane-ops per atom against 284 B); the HBM fraction is reported as the contract asks, "
+                                 "the binding figures are the ncu issue / FP64-pipe utilisation", **ncu_extra},
             "kernel_ms_per_step": kshare,
             "loss": loss,
         }
