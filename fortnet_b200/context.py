@@ -91,6 +91,17 @@ class Context:
         self._check(self._lib.fnetgpu_coords_update(self._h, C.c_int(slot), _p(_d(coords)),
                                                     _p(_d(latvecs)) if latvecs is not None else None))
 
+    def socket_step(self, slot, coords, latvecs=None, n_out=1, forces=True):
+        """one MD / i-PI step (predictForSocketComm, fortnet.F90:503-609): new geometry in ->
+        (global predictions [nStruct, nOut], atomic predictions [N, nOut], forces [N, 3*nOut])"""
+        N, nS = self.n_atoms[slot], self.n_struct[slot]
+        glob = np.zeros((nS, n_out)); raw = np.zeros((N, n_out))
+        frc = np.zeros((N, 3 * n_out)) if forces else None
+        self._check(self._lib.fnetgpu_socket_step(self._h, C.c_int(slot), _p(_d(coords)),
+                                                  _p(_d(latvecs)) if latvecs is not None else None,
+                                                  _p(glob), _p(raw), _p(frc)))
+        return glob, raw, frc
+
     # ---- plumbing -------------------------------------------------------------------
     def synchronize(self):
         self._check(self._lib.fnetgpu_synchronize(self._h))

@@ -232,33 +232,34 @@ __device__ __forceinline__ void ladder_init(double b, double L, double xi0, doub
   else p = fnet_exp_call(xi0 * L);
   q = (dxi == 0.0) ? 1.0 : fnet_exp(dxi * L);
 }
-// acc[m] += pw q^m (m = 0..7) with the powers built by doubling (dependency depth 3 instead of
-// 8); returns pw q^8 for a continuing ladder slot
+// acc[m] += pw q^m (m = 0..7): powers of q by doubling (dependency depth 3), then one FMA per
+// accumulator; returns pw q^8 for a continuing ladder slot
 __device__ __forceinline__ double ladder_accumulate(double *acc, double pw, double q) {
-  const double q2 = q * q, q4 = q2 * q2;
-  const double p1 = pw * q, p2 = pw * q2, p3 = p1 * q2;
-  acc[0] += pw; acc[1] += p1; acc[2] += p2; acc[3] += p3;
-  const double p4 = pw * q4, p5 = p1 * q4, p6 = p2 * q4, p7 = p3 * q4;
-  acc[4] += p4; acc[5] += p5; acc[6] += p6; acc[7] += p7;
-  return p4 * q4;
+  const double q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+  const double q5 = q4 * q, q6 = q4 * q2, q7 = q4 * q3;
+  acc[0] += pw;
+  acc[1] = fma(pw, q, acc[1]); acc[2] = fma(pw, q2, acc[2]); acc[3] = fma(pw, q3, acc[3]);
+  acc[4] = fma(pw, q4, acc[4]); acc[5] = fma(pw, q5, acc[5]); acc[6] = fma(pw, q6, acc[6]);
+  acc[7] = fma(pw, q7, acc[7]);
+  return (pw * q4) * q4;
 }
 
-// pair index -> (row j, column k) of the flattened pair walk.  same: upper triangle incl. the
-// diagonal of an n1 x n1 matrix (row j holds k = j..n1-1); else the full n1 x n2 rectangle.
-__device__ __forceinline__ void pair_decode(int p, int same, int n1, int n2, float invn2, int &j, int &k) {
+// pair index -> (row j, column k) of the flattened pair walk.  same: the upper triangle incl. the
+// diagonal of an n1 x n1 matrix folded into a rectangle of width W = n1 | 1 -- row r of the
+// triangle (n1 - r entries, k = r..n1-1) shares rectangle row r with triangle row n1 - r (n1 odd)
+// or n1 - 1 - r (n1 even); else the full n1 x n2 rectangle (W = n2).  invW = 1 / W.
+__device__ __forceinline__ void pair_decode(int p, int same, int n1, int W, float invW, int &j, int &k) {
+  int r = (int)(((float)p + 0.5f) * invW);
+  if (r * W > p) r--;
+  else if ((r + 1) * W <= p) r++;
+  const int c = p - r * W;
   if (same) {
-    const float fn = (float)(2 * n1 + 1);
-    j = (int)((fn - sqrtf(fmaxf(fn * fn - 8.0f * (float)p, 0.0f))) * 0.5f);
-    j = min(max(j, 0), n1 - 1);
-    int rs = j * n1 - ((j * (j - 1)) >> 1);
-    if (rs > p) { j--; rs = j * n1 - ((j * (j - 1)) >> 1); }
-    else if (rs + (n1 - j) <= p) { rs += n1 - j; j++; }
-    k = j + (p - rs);
+    const int h = n1 - r;                       // entries of triangle row r
+    const bool first = c < h;
+    j = first ? r : h - ((n1 & 1) ^ 1);
+    k = first ? r + c : j + (c - h);
   } else {
-    j = (int)(((float)p + 0.5f) * invn2);
-    if (j * n2 > p) j--;
-    else if ((j + 1) * n2 <= p) j++;
-    k = p - j * n2;
+    j = r; k = c;
   }
 }
 
@@ -409,10 +410,11 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
     for (int f = 0; f < FNET_LADDER; f++) acc[s * FNET_LADDER + f] = 0.0;
   }
   const int nPairs = same ? (n1 * (n1 + 1)) >> 1 : n1 * n2;
-  const float invn2 = n2 > 0 ? 1.0f / (float)n2 : 0.0f;
+  const int W = same ? (n1 | 1) : n2;
+  const float invW = W > 0 ? 1.0f / (float)W : 0.0f;
   for (int p = lane; p < nPairs; p += 32) {
     int j, k;
-    pair_decode(p, same, n1, n2, invn2, j, k);
+    pair_decode(p, same, n1, W, invW, j, k);
     const int a = list_at(l1, j), b = list_at(l2, k);
     double base = w.fcE[a] * w.fcE[b];
     if (same && a != b) base *= 2.0;

@@ -717,6 +717,33 @@ static int allreduce_sum(fnetgpu_ctx *ctx, double *d_buf, size_t n) {
 // ------------------------------------------------------------------------------------------
 // ACSF calculation
 // ------------------------------------------------------------------------------------------
+// one launch of the ACSF value kernel for the planned geometry path (no flag read-back)
+template <typename real>
+static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, const double *zp) {
+  const AcsfTables &T = ctx->acsf;
+  const int nExtSel = (int)ctx->extIdx.size();
+  const int nFeat = T.F + nExtSel;
+  real *feat = (real *)s.d_feat;
+  const GeomArgs geo = geom_args(s);
+#define FNET_ACSF_LAUNCH(NS, PATH)                                                                             \
+  do {                                                                                                         \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, PATH><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(                   \
+                            L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, feat, nFeat, zp, nExtSel,        \
+                            ctx->d_extIdx, ctx->d_flags)));                                                    \
+  } while (0)
+#define FNET_ACSF_LAUNCH_NS(PATH)                                                                              \
+  do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
+  const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
+  if (L.path == FNET_PATH_STRUCT) FNET_ACSF_LAUNCH_NS(FNET_PATH_STRUCT);
+  else if (L.path == FNET_PATH_STAGED) FNET_ACSF_LAUNCH_NS(FNET_PATH_STAGED);
+  else FNET_ACSF_LAUNCH_NS(FNET_PATH_DIRECT);
+#undef FNET_ACSF_LAUNCH_NS
+#undef FNET_ACSF_LAUNCH
+  return 0;
+}
+
+
 template <typename real>
 static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *zprec, int have_zprec) {
   const AcsfTables &T = ctx->acsf;
@@ -734,7 +761,9 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
   }
   real *feat = (real *)s.d_feat;
   const bool useGiven = standardize && have_zprec;
-  if (useGiven) {
+  if (useGiven && have_zprec == 2) {            // internal: the statistics already on the device (fnetgpu_socket_step)
+    if (!ctx->haveZ) FNET_FAIL(ctx, "acsf_calculate: no z-score statistics on the device");
+  } else if (useGiven) {
     if (!zprec) FNET_FAIL(ctx, "acsf_calculate: zprec missing");
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zprec, zprec, (size_t)2 * F * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->haveZ = true;
@@ -755,23 +784,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
         if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
       }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-      const GeomArgs geo = geom_args(s);
-      const double *zp = useGiven ? ctx->d_zprec : nullptr;
-#define FNET_ACSF_LAUNCH(NS, PATH)                                                                             \
-      do {                                                                                                     \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
-        LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, PATH><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(               \
-                                L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, feat, nFeat, zp, nExtSel,    \
-                                ctx->d_extIdx, ctx->d_flags)));                                                \
-      } while (0)
-#define FNET_ACSF_LAUNCH_NS(PATH)                                                                              \
-      do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
-      const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
-      if (L.path == FNET_PATH_STRUCT) FNET_ACSF_LAUNCH_NS(FNET_PATH_STRUCT);
-      else if (L.path == FNET_PATH_STAGED) FNET_ACSF_LAUNCH_NS(FNET_PATH_STAGED);
-      else FNET_ACSF_LAUNCH_NS(FNET_PATH_DIRECT);
-#undef FNET_ACSF_LAUNCH_NS
-#undef FNET_ACSF_LAUNCH
+      if (launch_acsf_values<real>(ctx, s, L, useGiven ? ctx->d_zprec : nullptr)) return 1;
       int h[16];
       CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -853,6 +866,7 @@ extern "C" int fnetgpu_acsf_calculate(fnetgpu_ctx *ctx, int slot, int standardiz
   if (!s.used) FNET_FAIL(ctx, "acsf_calculate: empty slot");
   if (!ctx->acsfSet && ctx->extIdx.empty()) FNET_FAIL(ctx, "acsf_calculate: call fnetgpu_acsf_set / fnetgpu_features_config first");
   cudaSetDevice(ctx->device);
+  have_zprec = have_zprec ? 1 : 0;
   if (ctx->precision == 64) return acsf_calculate_t<double>(ctx, s, standardize, zprec, have_zprec);
   return acsf_calculate_t<float>(ctx, s, standardize, zprec, have_zprec);
 }
@@ -1202,6 +1216,27 @@ extern "C" int fnetgpu_loss(fnetgpu_ctx *ctx, int slot, int lossId, double *loss
 // ------------------------------------------------------------------------------------------
 // forces
 // ------------------------------------------------------------------------------------------
+// one launch of the fused force kernel for the planned geometry path (no flag read-back)
+static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, const double *dEdG64, const double *zp) {
+  const AcsfTables &T = ctx->acsf;
+  const NetTables &n = ctx->net;
+  const dim3 g(L.grid.x, L.grid.y, n.nOut);
+  const GeomArgs geo = geom_args(s);
+#define FNET_FORCE_LAUNCH(PATH)                                                                                 \
+  do {                                                                                                          \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<PATH><<<g, L.wpb * 32, L.smem, ctx->stream>>>(                      \
+                                  L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp,         \
+                                  s.d_forces, ctx->d_flags)));                                                  \
+  } while (0)
+  if (L.path == FNET_PATH_STRUCT) FNET_FORCE_LAUNCH(FNET_PATH_STRUCT);
+  else if (L.path == FNET_PATH_STAGED) FNET_FORCE_LAUNCH(FNET_PATH_STAGED);
+  else FNET_FORCE_LAUNCH(FNET_PATH_DIRECT);
+#undef FNET_FORCE_LAUNCH
+  return 0;
+}
+
+
 template <typename real>
 static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   if (check_ready<real>(ctx, s, false)) return 1;
@@ -1246,19 +1281,7 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
     }
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-    const dim3 g(L.grid.x, L.grid.y, n.nOut);
-    const GeomArgs geo = geom_args(s);
-#define FNET_FORCE_LAUNCH(PATH)                                                                                 \
-    do {                                                                                                        \
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
-      LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<PATH><<<g, L.wpb * 32, L.smem, ctx->stream>>>(                    \
-                                    L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp,       \
-                                    s.d_forces, ctx->d_flags)));                                                \
-    } while (0)
-    if (L.path == FNET_PATH_STRUCT) FNET_FORCE_LAUNCH(FNET_PATH_STRUCT);
-    else if (L.path == FNET_PATH_STAGED) FNET_FORCE_LAUNCH(FNET_PATH_STAGED);
-    else FNET_FORCE_LAUNCH(FNET_PATH_DIRECT);
-#undef FNET_FORCE_LAUNCH
+    if (launch_acsf_forces(ctx, s, L, dEdG64, zp)) return 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     s.lastPath = L.path;
@@ -1282,4 +1305,100 @@ extern "C" int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces) {
   Slot &s = ctx->slots[slot];
   if (ctx->precision == 64) return forces_t<double>(ctx, s, forces);
   return forces_t<float>(ctx, s, forces);
+}
+
+// ------------------------------------------------------------------------------------------
+// one MD / i-PI step for a resident slot: new geometry in -> predictions + forces out
+// (calculateMappingsForSocketComm + predictForSocketComm, prg_fnet/fortnet.F90:430-609).
+// Fast path (precision 64, whole-structure neighbour search): everything is enqueued on the
+// stream with the capacities of the previous step and the host synchronises ONCE; overflow /
+// lattice flags are inspected afterwards and send the step through the general entry points.
+// ------------------------------------------------------------------------------------------
+extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs,
+                                   double *globalPred, double *atomicPred, double *forces) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used) FNET_FAIL(ctx, "socket_step: empty slot");
+  if (!coords) FNET_FAIL(ctx, "socket_step: coords missing");
+  cudaSetDevice(ctx->device);
+  const AcsfTables &T = ctx->acsf;
+  const NetTables &n = ctx->net;
+  if (!ctx->acsfSet || T.F == 0) FNET_FAIL(ctx, "socket_step: need an ACSF configuration");
+  if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "socket_step: not defined with external features (fortnet.F90:560-561)");
+  if (!ctx->netSet || !ctx->paramsSet) FNET_FAIL(ctx, "socket_step: network / parameters not set");
+  if (!s.d_feat || s.nFeat != T.F)
+    FNET_FAIL(ctx, "socket_step: call fnetgpu_acsf_calculate on this slot once first (it fixes the standardisation)");
+  if (s.zscored && !ctx->haveZ) FNET_FAIL(ctx, "socket_step: z-score statistics missing");
+  const size_t nRaw = (size_t)s.N * n.nOut, nFrc = (size_t)3 * n.nOut * s.N;
+  bool done = false;
+  if (ctx->precision == 64) {
+    for (int attempt = 0; attempt < 3 && !done && use_struct_path(ctx, s); attempt++) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      if (latvecs) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
+      }
+      s.cellRc = -1.0; s.neighStale = true;
+      const double *zp = s.zscored ? ctx->d_zprec : nullptr;
+      AcsfLaunch Lv, Lf;
+      if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F), Lv)) return 1;
+      if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), Lf)) return 1;
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+      if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;
+      s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
+      if (check_ready<double>(ctx, s, false)) return 1;
+      if (run_forward<double>(ctx, s)) return 1;
+      if (!s.d_dEdG) { double *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
+      {
+        const BpnnLaunch B = plan_bpnn<double>(ctx, s, 1);
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+        LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<double, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
+                                      s.nTiles, s.d_tiles, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, n,
+                                      s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
+                                      nullptr, (double *)s.d_dEdG, (double *)nullptr)));
+      }
+      if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, nFrc)) return 1; }
+      CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));
+      if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
+      if (ensure_pinned(ctx, nRaw + nFrc + 16)) return 1;
+      double *hp = ctx->h_pinned;
+      CUDA_TRY(ctx, cudaMemcpyAsync(hp, s.d_raw, nRaw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw + nFrc, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      int h[8];
+      memcpy(h, hp + nRaw + nFrc, sizeof(h));
+      if (h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; s.featValid = false; break; }   // lattice too small: general path below
+      if (h[7] != 0) { s.featValid = false; break; }
+      if (h[1] != 0) { s.maxNeigh = h[1]; s.featValid = false; continue; }               // neighbour buffers too small: retry
+      if (atomicPred) memcpy(atomicPred, hp, nRaw * sizeof(double));
+      if (forces) memcpy(forces, hp + nRaw, nFrc * sizeof(double));
+      if (globalPred)
+        for (int st = 0; st < s.nStruct; st++)
+          for (int k = 0; k < n.nOut; k++) {
+            double e = 0.0;
+            for (int i = s.h_offsets[st]; i < s.h_offsets[st + 1]; i++) e += hp[(size_t)n.nOut * i + k];
+            globalPred[(size_t)n.nOut * st + k] = e;
+          }
+      done = true;
+    }
+  }
+  if (done) return 0;
+  // general path: the blocking entry points, any precision, any structure size
+  if (fnetgpu_coords_update(ctx, slot, coords, latvecs)) return 1;
+  const int zs = s.zscored ? 1 : 0;
+  if (ctx->precision == 64) { if (acsf_calculate_t<double>(ctx, s, zs, nullptr, zs ? 2 : 0)) return 1; }
+  else { if (acsf_calculate_t<float>(ctx, s, zs, nullptr, zs ? 2 : 0)) return 1; }
+  std::vector<double> raw(nRaw);
+  if (fnetgpu_predict(ctx, slot, raw.data())) return 1;
+  if (forces) { if (fnetgpu_forces(ctx, slot, forces)) return 1; }
+  if (atomicPred) memcpy(atomicPred, raw.data(), nRaw * sizeof(double));
+  if (globalPred)
+    for (int st = 0; st < s.nStruct; st++)
+      for (int k = 0; k < n.nOut; k++) {
+        double e = 0.0;
+        for (int i = s.h_offsets[st]; i < s.h_offsets[st + 1]; i++) e += raw[(size_t)n.nOut * i + k];
+        globalPred[(size_t)n.nOut * st + k] = e;
+      }
+  return 0;
 }

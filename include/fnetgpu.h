@@ -118,6 +118,16 @@ int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces /* [3*nOut*N] */);
 int fnetgpu_comm_unique_id(char *id /* [FNETGPU_UNIQUE_ID_BYTES] */);
 int fnetgpu_comm_init(fnetgpu_ctx *ctx, int nRanks, int rank, const char *id);
 
+/* One MD / i-PI step for a resident slot -- replaces calculateMappingsForSocketComm +
+ * predictForSocketComm (prg_fnet/fortnet.F90:430-609): new coordinates (and cell, or NULL when it is
+ * unchanged) in; per-structure summed outputs globalPred[nOut*nStruct], per-atom outputs
+ * atomicPred[nOut*N] and forces[3*nOut*N] out (any of them may be NULL).  The slot keeps the
+ * topology, species and standardisation of the last fnetgpu_dataset_upload / fnetgpu_acsf_calculate
+ * (call the latter once before the first step).  Precision 64 + small structures: one host
+ * synchronisation per step.  Not defined with external features (fortnet.F90:560-561). */
+int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs_or_null,
+                        double *globalPred, double *atomicPred, double *forces);
+
 /* ---- plumbing for benchmarks / profiling ---- */
 int fnetgpu_set_stream(fnetgpu_ctx *ctx, void *cudaStream);   /* run on the caller's stream */
 long long fnetgpu_launch_count(const fnetgpu_ctx *ctx);       /* kernels launched so far */

@@ -310,6 +310,62 @@ def test_whole_structure_path_hands_over_after_lattice_update(fb, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("path,precision", [("auto", 64), ("cells", 64), ("auto", 32)])
+def test_socket_step(fb, orc, path, precision):
+    """fnetgpu_socket_step (predictForSocketComm, fortnet.F90:503-609): an MD trajectory of a resident
+    structure -- every step must equal the blocking call sequence and the oracle; the cell shrinking
+    below 2 rc in mid-trajectory sends the step through the general path and back"""
+    from fortnet_b200 import synthetic
+    rng = np.random.default_rng(41)
+    ds = synthetic.si_bulk(n_struct=2, seed=9)
+    rc = 4.0 * fb.BOHR_PER_AA
+    funcs = fb.GFunctions.from_auto_scheme(rc, 6, 6)
+    dims = [12, 7, 5, 1]
+    wb = rng.uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    ctx = fb.Context(acsf_path=path, precision=precision)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)                                   # fixes the z-score statistics (training-set role)
+    mu, sg = acsf.zprec
+    net = fb.Bpnn(ctx, dims, 1, "tanh")
+    net.set_params(wb)
+    rt, at = (RTOL, ATOL) if precision == 64 else (2e-4, 2e-4)
+    # second context: the blocking call sequence on the cell list (forces for edges < 2 rc are the true
+    # gradient, which the reference's dense derivative does not give -- SURVEY.md section 7)
+    ctx2 = fb.Context(acsf_path="cells", precision=precision)
+    ctx2.upload(0, ds)
+    acsf2 = fb.Acsf(ctx2, funcs, standardize=True)
+    acsf2.calculate(0, zprec=np.stack([mu, sg]))
+    net2 = fb.Bpnn(ctx2, dims, 1, "tanh")
+    net2.set_params(wb)
+    coords = ds.coords.copy()
+    for step, scale in enumerate([1.0, 1.0, 0.7, 0.7, 1.0, 1.0]):
+        coords = coords + rng.normal(scale=0.02, size=coords.shape)
+        c, l = coords * scale, ds.latvecs * scale
+        glob, raw, frc = ctx.socket_step(0, c, l if step != 1 else None)
+        if precision == 64:
+            want = (2,) if (path == "auto" and scale == 1.0) else (0, 1)
+            assert ctx.acsf_path(0) in want, (step, ctx.acsf_path(0))
+        ref = orc.zscore_apply(orc.acsf(ds.offsets, c, ds.periodic, l, ds.atnum, funcs.asdicts()), mu, sg)
+        raw_o = orc.predict(ref, ds.globalsp, dims, "tanh", wb)
+        assert np.allclose(raw, raw_o, rtol=rt, atol=at), (step, _md(raw, raw_o))
+        assert np.allclose(glob[:, 0], np.add.reduceat(raw_o[:, 0], ds.offsets[:-1].astype(int)), rtol=rt, atol=at * 64)
+        if scale == 1.0:
+            f_o = orc.forces(ds.offsets, c, ds.periodic, l, ds.atnum, funcs.asdicts(), ref, ds.globalsp, dims, "tanh", wb, sigmas=sg)
+        else:
+            ctx2.update_coords(0, c, l)
+            acsf2.calculate(0, zprec=np.stack([mu, sg]))
+            f_o = net2.forces(0)
+        assert np.allclose(frc, f_o, rtol=rt, atol=at * max(1.0, np.abs(f_o).max())), (step, _md(frc, f_o))
+    # and the blocking sequence on the last geometry gives the same numbers
+    ctx.update_coords(0, c, l)
+    acsf.calculate(0, zprec=np.stack([mu, sg]))
+    assert np.allclose(net.predict_batch(0), raw, rtol=rt, atol=at)
+    assert np.allclose(net.forces(0), frc, rtol=rt, atol=at * max(1.0, np.abs(frc).max()))
+    ctx.close()
+    ctx2.close()
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_atom_id_scaling_and_external_features(fb, orc, path):
     """q_i q_j prefactors from an external-feature row (acsf.F90:836-840,1003-1052) and external

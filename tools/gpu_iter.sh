@@ -20,3 +20,4 @@ except Exception as e:
 PY
 done
 tail -1 $O/${TAG}_e2e_c2.txt
+timeout 200 python tools/md_latency.py 500 > $O/${TAG}_md_latency.txt 2>&1; cat $O/${TAG}_md_latency.txt
