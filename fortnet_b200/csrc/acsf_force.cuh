@@ -83,7 +83,10 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
         const double D = w.outv[tab.rfeat[G.fBeg + f]];
         const double p1 = tab.rp1[G.fBeg + f], p2 = tab.rp2[G.fBeg + f];
         if (G.type == FNETGPU_G1) s += D * dfc;
-        else if (G.type == FNETGPU_G2) { const double d = rr - p2; s += D * (dfc - fc * 2.0 * p1 * d) * exp(-p1 * d * d); }
+        else if (G.type == FNETGPU_G2) {
+          const double d = rr - p2, e = p1 * d * d;
+          s += D * (dfc - fc * 2.0 * p1 * d) * (e < 700.0 ? fnet_exp(-e) : 0.0);
+        }
         else { double sn, cs; sincos(p1 * rr, &sn, &cs); s += D * (cs * dfc - sn * fc * p1); }
       }
       // each slot is owned by exactly one lane inside this loop, but lists of different groups
@@ -109,7 +112,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
       if (rr > rc) { w.fcE[t] = 0.0; dE[t] = 0.0; }
       else {
         const double fc = cutoff_fn(rr, qi * qj, invrc), dfc = dcutoff_fn(rr, qi * qj, rc, invrc);
-        const double ex = exp(-eta * rr * rr);
+        const double ex = fnet_exp(-eta * rr * rr);
         w.fcE[t] = fc * ex;
         dE[t] = (dfc - 2.0 * eta * rr * fc) * ex;   // acsf.F90:1577-1578
       }
@@ -132,13 +135,13 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
         c1[s][f] = on ? D * P->slot[s].xi[f] * lam[s] : 0.0;
       }
     }
-    if (n1 > 0 && n2 > 0) {
-      int j = 0, o = lane;
-      while (j < n1) {
-        int len = same ? n1 - j : n2;
-        while (o >= len) { o -= len; j++; if (j >= n1) break; len = same ? n1 - j : n2; }
-        if (j >= n1) break;
-        const int k = (same ? j : 0) + o;
+    {
+      const int nPairs = same ? (n1 * (n1 + 1)) >> 1 : n1 * n2;
+      const int W = same ? (n1 | 1) : n2;
+      const float invW = W > 0 ? 1.0f / (float)W : 0.0f;
+      for (int p = lane; p < nPairs; p += 32) {
+        int j, k;
+        pair_decode(p, same, n1, W, invW, j, k);
         const int a = list_at(l1, j), b = list_at(l2, k);
         const double Ea = w.fcE[a], Eb = w.fcE[b];
         double wgt = (same && a != b) ? 2.0 : 1.0;
@@ -154,7 +157,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
           if (dab > rc) on = false;
           else {
             const double qq = w.qv[a] * w.qv[b];
-            const double fc = cutoff_fn(dab, qq, invrc), ex = exp(-eta * d2);
+            const double fc = cutoff_fn(dab, qq, invrc), ex = fnet_exp(-eta * d2);
             H = fc * ex;
             if (a != b) {
               dH = (dcutoff_fn(dab, qq, rc, invrc) - 2.0 * eta * dab * fc) * ex;
@@ -169,15 +172,15 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
 #pragma unroll
           for (int s = 0; s < FNET_SLOTS; s++) {
             if (cnt[s] > 0) {
-              if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = log(bb); }
+              if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log(bb); }
               double pm, q;
               ladder_init(bb, L, xi0[s] - 1.0, dxi[s], pm, q);     // b^(xi-1)
+              // sum_f c[f] pm q^f = pm * P(q): two Horner chains instead of a serial pm *= q ladder
+              double P1 = c1[s][FNET_LADDER - 1], P0 = c0[s][FNET_LADDER - 1];
 #pragma unroll
-              for (int f = 0; f < FNET_LADDER; f++) {
-                S1 += c1[s][f] * pm;
-                S0 += c0[s][f] * (pm * bb);
-                pm *= q;
-              }
+              for (int f = FNET_LADDER - 2; f >= 0; f--) { P1 = fma(P1, q, c1[s][f]); P0 = fma(P0, q, c0[s][f]); }
+              S1 = fma(P1, pm, S1);
+              S0 = fma(P0, pm * bb, S0);
             }
           }
           // g_a = w [ Eb H ( S1 Ea (u_b - c u_a)/r_a + S0 dEa u_a ) + S0 Ea Eb dH u_ab ]
@@ -193,7 +196,6 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
           atomicAdd(&fy[b], tb * w.dy[a] + sb * w.dy[b] - th * vy);
           atomicAdd(&fz[b], tb * w.dz[a] + sb * w.dz[b] - th * vz);
         }
-        o += 32;
       }
     }
     __syncwarp();
