@@ -87,6 +87,15 @@ module fnet_gpu
       integer(c_int), value :: slot
       real(c_double), intent(out) :: forces(*)
     end function
+    integer(c_int) function fnetgpu_socket_step(ctx, slot, coords, latvecs, globalPred, atomicPred, forces)&
+        & bind(C, name='fnetgpu_socket_step')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: slot
+      real(c_double), intent(in) :: coords(*)
+      type(c_ptr), value :: latvecs                     ! c_null_ptr: cell unchanged
+      real(c_double), intent(out) :: globalPred(*), atomicPred(*), forces(*)
+    end function
   end interface
 
 contains
@@ -189,5 +198,19 @@ contains
     real(dp), intent(out) :: forces(:,:)     ! (3*nOut, nTotAtoms)
     call check(env, fnetgpu_forces(env%ctx, int(slot, c_int), forces))
   end subroutine gpuForces
+
+  !> One i-PI / MD step: replaces calculateMappingsForSocketComm + predictForSocketComm
+  !! (prg_fnet/fortnet.F90:430-609) for the geometry resident in slot.
+  subroutine gpuSocketStep(env, slot, coords, latVecs, globalPrediction, atomicPredictions, atomicForces)
+    type(TGpuEnv), intent(in) :: env
+    integer, intent(in) :: slot
+    real(dp), intent(in) :: coords(:,:)                 ! (3, nAtom)
+    real(dp), intent(in), target :: latVecs(:,:)        ! (3, 3)
+    real(dp), intent(out) :: globalPrediction(:)        ! (nOut)
+    real(dp), intent(out) :: atomicPredictions(:,:)     ! (nOut, nAtom)
+    real(dp), intent(out) :: atomicForces(:,:)          ! (3*nOut, nAtom)
+    call check(env, fnetgpu_socket_step(env%ctx, int(slot, c_int), coords, c_loc(latVecs), globalPrediction,&
+        & atomicPredictions, atomicForces))
+  end subroutine gpuSocketStep
 
 end module fnet_gpu

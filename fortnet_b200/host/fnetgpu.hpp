@@ -137,6 +137,14 @@ class TBpnn {
     env_.check(fnetgpu_forces(env_.ctx(), slot, f.data()));
     return f;
   }
+  // predictForSocketComm (prg_fnet/fortnet.F90:503-609): one MD step of the resident geometry
+  void socketStep(int slot, const std::vector<double> &coords, const double *latVecsOrNull, std::vector<double> &globalPrediction,
+                  std::vector<double> &atomicPredictions, std::vector<double> &atomicForces) {
+    const size_t nOut = dims_.back(), N = env_.nAtoms(slot);
+    globalPrediction.resize(nOut * env_.nStruct(slot)); atomicPredictions.resize(nOut * N); atomicForces.resize(3 * nOut * N);
+    env_.check(fnetgpu_socket_step(env_.ctx(), slot, coords.data(), latVecsOrNull, globalPrediction.data(),
+                                   atomicPredictions.data(), atomicForces.data()));
+  }
 
  private:
   TEnv &env_;
