@@ -47,9 +47,10 @@ __host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F) {
 }
 // CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates (PATH 1) or the
 // structure's lattice (PATH 2)
+#define FNET_FTAB_BYTES (FNET_TAB_DOUBLES * sizeof(double))     // exp / log tables of fmath.cuh, first thing in the CTA's smem
 __host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC, int path = 1) {
-  const size_t tail = path == 2 ? sizeof(StructGeom) : sizeof(StageTabs);
-  return (size_t)capC * sizeof(CRec) + ((tail + 15) & ~(size_t)15);
+  const size_t tail = path == 2 ? sizeof(StructGeom) : (path == 1 ? sizeof(StageTabs) : 0);
+  return FNET_FTAB_BYTES + (size_t)capC * sizeof(CRec) + ((tail + 15) & ~(size_t)15);
 }
 
 // Where the central atoms and their candidates come from.  PATH 0: cell list, candidates read
@@ -65,6 +66,7 @@ struct GeomArgs {                     // device pointers, passed by value to the
 struct CtaGeom {                      // per-CTA view produced by acsf_cta_prologue
   const StructInfo *S; BinPos bp; const int *cellStart; const CRec *crec;
   const CRec *cand; int nCand; const StructGeom *sg;
+  const double *ftab;                 // exp / log tables (shared memory)
   int a0, a1, first;                  // central atoms [a0, a1): slots of crec (PATH 0/1) or atoms (PATH 2, first = atomBeg)
 };
 
@@ -74,6 +76,13 @@ template <int PATH>
 __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit, double rcMax, int capC,
                                                   unsigned char *smem_raw, int *__restrict__ flags, CtaGeom &c,
                                                   unsigned char *&wbase) {
+  {   // tables first; the barriers of the staging below (or the explicit one of PATH 0) publish them
+    double *ft = (double *)smem_raw;
+    for (int e = threadIdx.x; e < FNET_TAB_DOUBLES; e += blockDim.x)
+      ft[e] = e < FNET_EXP_TAB_N ? fnet_exp_tab_d[e] : fnet_log_tab_d[e - FNET_EXP_TAB_N];
+    c.ftab = ft;
+    smem_raw += FNET_FTAB_BYTES;
+  }
   c.S = nullptr; c.cellStart = G.cellStart; c.crec = G.crec; c.cand = (const CRec *)smem_raw; c.nCand = 0; c.sg = nullptr;
   c.first = 0;
   wbase = smem_raw;
@@ -87,7 +96,7 @@ __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit,
     c.nCand = stage_structure(st, beg, end - beg, G.coords, G.atnum, G.lat, G.periodic, rcMax, (CRec *)smem_raw, capC, sg, flags);
     c.sg = sg;
     if (c.nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], -c.nCand); return false; }
-    wbase += acsf_cta_prefix_bytes(capC, 2);
+    wbase += acsf_cta_prefix_bytes(capC, 2) - FNET_FTAB_BYTES;
     return true;
   }
   const int bin = blockIdx.x;
@@ -101,7 +110,9 @@ __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit,
     StageTabs *tabs = (StageTabs *)(smem_raw + (size_t)capC * sizeof(CRec));
     c.nCand = stage_candidates(*c.S, c.bp, G.cellStart, G.crec, (CRec *)smem_raw, capC, tabs);
     if (c.nCand < 0) { if (threadIdx.x == 0) atomicMax(&flags[7], c.nCand == -1 ? 0x7fffffff : -c.nCand); return false; }
-    wbase += acsf_cta_prefix_bytes(capC, 1);
+    wbase += acsf_cta_prefix_bytes(capC, 1) - FNET_FTAB_BYTES;
+  } else {
+    __syncthreads();
   }
   return true;
 }
@@ -226,11 +237,12 @@ __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) 
 // (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
 // pow(0,0)=1 / pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
 __device__ __noinline__ double fnet_exp_call(double x) { return fnet_exp(x); }   // keeps rare paths out of line
-__device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q) {
+__device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q,
+                                            const double *__restrict__ ftab) {
   if (xi0 == 1.0) p = b;                       // auto scheme: every ladder starts at xi = 1 (acsf.F90:341)
   else if (xi0 == 0.0) p = 1.0;
   else p = fnet_exp_call(xi0 * L);
-  q = (dxi == 0.0) ? 1.0 : fnet_exp(dxi * L);
+  q = (dxi == 0.0) ? 1.0 : fnet_exp_tab(dxi * L, ftab);
 }
 // acc[m] += pw q^m (m = 0..7): powers of q by doubling (dependency depth 3), then one FMA per
 // accumulator; returns pw q^8 for a continuing ladder slot
@@ -299,7 +311,7 @@ __device__ __noinline__ double radial_term_generic(int type, double p1, double p
 }
 
 __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &tab, const WarpSmem &w, int nExt,
-                                              const double *__restrict__ ext) {
+                                              const double *__restrict__ ext, const double *__restrict__ ftab) {
   const int lane = threadIdx.x & 31;
   for (int g = 0; g < tab.nRadialGroups; g++) {
     const RadialGroup *__restrict__ G = &tab.rgroups[g];
@@ -332,8 +344,8 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
           const double u = rr - rsf;
           const double e0 = eta * u * u, a1 = 2.0 * eta * drs * u;
           if (e0 < 690.0 && fabs(a1) < 690.0) {         // g_0 and the ratio stay normal numbers
-            double gv = fnet_exp(-e0) * fc;
-            const double A = fnet_exp(a1);
+            double gv = fnet_exp_tab(-e0, ftab) * fc;
+            const double A = fnet_exp_tab(a1, ftab);
             acc[0] += gv;
 #pragma unroll
             for (int m = 0; m < FNET_RCHUNK - 1; m++) { gv *= A * kk[m]; acc[m + 1] += gv; }
@@ -379,7 +391,8 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
 // ------------------------------------------------------------------------------------------
 template <int NS>
 __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab, const AngularPass *__restrict__ P,
-                                             const WarpSmem &w, int nExt, const double *__restrict__ ext) {
+                                             const WarpSmem &w, int nExt, const double *__restrict__ ext,
+                                             const double *__restrict__ ftab) {
   const int lane = threadIdx.x & 31;
   const int type = P->type, same = P->same, atomId = P->atomId;
   const int nSlots = min(P->nSlots, NS);
@@ -393,7 +406,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
     const double rr = w.r[t];
     const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
     w.qv[t] = qj;
-    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * fnet_exp(-eta * rr * rr);
+    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * fnet_exp_tab(-eta * rr * rr, ftab);
   }
   __syncwarp();
   double lam[NS], xi0[NS], dxi[NS];
@@ -422,7 +435,7 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       const double ex = w.dx[a] - w.dx[b], ey = w.dy[a] - w.dy[b], ez = w.dz[a] - w.dz[b];
       const double djk2 = ex * ex + ey * ey + ez * ez;
       const double djk = sqrt(djk2);
-      base = (djk > rc) ? 0.0 : base * fnet_exp(-eta * djk2) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
+      base = (djk > rc) ? 0.0 : base * fnet_exp_tab(-eta * djk2, ftab) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
     }
     if (base != 0.0) {
       const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
@@ -433,8 +446,8 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       for (int s = 0; s < NS; s++) {
         if (on[s]) {
           if (!cont[s]) {
-            if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log(bb); }
-            ladder_init(bb, L, xi0[s], dxi[s], pw, q);
+            if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log_tab(bb, ftab); }
+            ladder_init(bb, L, xi0[s], dxi[s], pw, q, ftab);
             pw *= base;
           }
           pw = ladder_accumulate(&acc[s * FNET_LADDER], pw, q);
@@ -469,8 +482,8 @@ k_acsf(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfT
     const int i = me.idx;
     const int n = gather_neighbors<PATH>(me, cg, tab, cap, w);
     if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
-    radial_groups(i, n, tab, w, nExt, ext);
-    for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) angular_pass<NS>(i, n, tab, &tab.apasses[pi_], w, nExt, ext);
+    radial_groups(i, n, tab, w, nExt, ext, cg.ftab);
+    for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) angular_pass<NS>(i, n, tab, &tab.apasses[pi_], w, nExt, ext, cg.ftab);
     __syncwarp();
     // ---------------- coalesced feature write (+ z-score, + external features) ----------------
     real *out = feat + (size_t)nFeat * i;

@@ -85,7 +85,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
         if (G.type == FNETGPU_G1) s += D * dfc;
         else if (G.type == FNETGPU_G2) {
           const double d = rr - p2, e = p1 * d * d;
-          s += D * (dfc - fc * 2.0 * p1 * d) * (e < 700.0 ? fnet_exp(-e) : 0.0);
+          s += D * (dfc - fc * 2.0 * p1 * d) * (e < 700.0 ? fnet_exp_tab(-e, cg.ftab) : 0.0);
         }
         else { double sn, cs; sincos(p1 * rr, &sn, &cs); s += D * (cs * dfc - sn * fc * p1); }
       }
@@ -112,7 +112,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
       if (rr > rc) { w.fcE[t] = 0.0; dE[t] = 0.0; }
       else {
         const double fc = cutoff_fn(rr, qi * qj, invrc), dfc = dcutoff_fn(rr, qi * qj, rc, invrc);
-        const double ex = fnet_exp(-eta * rr * rr);
+        const double ex = fnet_exp_tab(-eta * rr * rr, cg.ftab);
         w.fcE[t] = fc * ex;
         dE[t] = (dfc - 2.0 * eta * rr * fc) * ex;   // acsf.F90:1577-1578
       }
@@ -157,7 +157,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
           if (dab > rc) on = false;
           else {
             const double qq = w.qv[a] * w.qv[b];
-            const double fc = cutoff_fn(dab, qq, invrc), ex = fnet_exp(-eta * d2);
+            const double fc = cutoff_fn(dab, qq, invrc), ex = fnet_exp_tab(-eta * d2, cg.ftab);
             H = fc * ex;
             if (a != b) {
               dH = (dcutoff_fn(dab, qq, rc, invrc) - 2.0 * eta * dab * fc) * ex;
@@ -172,9 +172,9 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
 #pragma unroll
           for (int s = 0; s < FNET_SLOTS; s++) {
             if (cnt[s] > 0) {
-              if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log(bb); }
+              if (s == 0 || lam[s] != lam[s - 1]) { bb = fmax(1.0 + lam[s] * c, 0.0); L = fnet_log_tab(bb, cg.ftab); }
               double pm, q;
-              ladder_init(bb, L, xi0[s] - 1.0, dxi[s], pm, q);     // b^(xi-1)
+              ladder_init(bb, L, xi0[s] - 1.0, dxi[s], pm, q, cg.ftab);     // b^(xi-1)
               // sum_f c[f] pm q^f = pm * P(q): two Horner chains instead of a serial pm *= q ladder
               double P1 = c1[s][FNET_LADDER - 1], P0 = c0[s][FNET_LADDER - 1];
 #pragma unroll

@@ -170,6 +170,62 @@ FNET_HD double fnet_exp(double x) { return fnet_exp_t<FNET_ACSF_ESTRIN != 0>(x);
 FNET_HD double fnet_log(double x) { return fnet_log_t<FNET_ACSF_ESTRIN != 0>(x); }
 FNET_HD double fnet_exp_lat(double x) { return fnet_exp_t<true>(x); }
 
+// ------------------------------------------------------------------------------------------
+// Table-driven variants for the ACSF pair loops (tables: fmath_tables.h, generated by
+// tools/gen_fmath_tables.py; the kernels keep a copy in shared memory).  Same domains and edge
+// conventions as fnet_exp / fnet_log; ~2 ulp for exp, absolute error < 4e-16 for log (which is
+// what (1 + lam cos)^xi = exp(xi log b) needs: the error of the power is xi * |dL|).
+//   exp(x) = 2^k T[j] e^r,  x = (64 k + j) ln2/64 + r, |r| <= ln2/128: degree-5 Taylor
+//   log(x) = k ln2 + logc_i + log1p(r),  x = 2^k z, z in [0.6875, 1.375), r = z invc_i - 1,
+//            |r| < 2^-7: degree-7 series
+// 10 / 13 FP64 operations instead of 19 / 24, and 4 / 8 constants instead of 14 / 12.
+// ------------------------------------------------------------------------------------------
+#include "fmath_tables.h"
+static const double fnet_exp_tab_h[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
+static const double fnet_log_tab_h[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
+#ifdef __CUDACC__
+__constant__ double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
+__constant__ double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
+#endif
+#define FNET_TAB_DOUBLES (FNET_EXP_TAB_N + 2 * FNET_LOG_TAB_N)     // exp table, then (invc, logc) pairs
+
+FNET_HD double fnet_exp_tab(double x, const double *__restrict__ tab) {
+  const double magic = 6755399441055744.0;
+  const double tk = fma(x, 92.332482616893656877, magic);          // 64 / ln2
+  const int kj = fnet_lo(tk);
+  const double kd = tk - magic;
+  double r = fma(kd, -1.08304246932675596327e-02, x);              // ln2/64 high part (32 significant bits)
+  r = fma(kd, -2.98158582698529328128e-12, r);                     // ln2/64 low part
+  const double T = tab[kj & 63];
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  const double q = fma(p, r * r, r);                               // e^r - 1
+  const double v = fma(T, q, T);
+  const double res = fnet_mk_double(fnet_hi(v) + ((kj >> 6) << 20), fnet_lo(v));   // * 2^k (normal results only)
+  return (x < -708.0) ? 0.0 : res;
+}
+
+FNET_HD double fnet_log_tab(double x, const double *__restrict__ tab) {
+  const int hi = fnet_hi(x);
+  const int tmp = hi - 0x3fe60000;
+  const int i = (tmp >> 13) & 127;
+  const int k = tmp >> 20;                                         // arithmetic shift: floor
+  const double z = fnet_mk_double(hi - (tmp & (int)0xfff00000), fnet_lo(x));
+  const double invc = tab[FNET_EXP_TAB_N + 2 * i], logc = tab[FNET_EXP_TAB_N + 2 * i + 1];
+  const double r = fma(z, invc, -1.0);
+  const double kd = (double)k;
+  double p = fma(r, 1.4285714285714285e-01, -1.6666666666666666e-01);   // 1/7, -1/6
+  p = fma(p, r, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 3.3333333333333331e-01);
+  p = fma(p, r, -0.5);
+  const double w = fma(kd, 6.93147180369123816490e-01, logc);      // exact: ln2_hi has 32 significant bits
+  double res = fma(p, r * r, r) + w;
+  res = fma(kd, 1.90821492927058770002e-10, res);
+  return (hi < 0x00100000) ? -INFINITY : res;
+}
+
 // 1/d for d >= 1 (no zero / inf / denormal handling): hardware seed + two Newton steps + a
 // residual correction; within 1 ulp.
 FNET_HD double fnet_rcp(double d) {

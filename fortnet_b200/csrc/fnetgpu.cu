@@ -610,11 +610,11 @@ static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, A
   L.staged = s.maxCells <= FNET_MAX_NCELLS && s.maxCand >= 0 && s.maxCand <= 1536;
   L.capC = L.staged ? ((s.maxCand + s.maxCand / 8 + 31) & ~31) : 0;
   L.wpb = 4;
-  const size_t prefix = L.staged ? acsf_cta_prefix_bytes(L.capC) : 0;
+  const size_t prefix = L.staged ? acsf_cta_prefix_bytes(L.capC) : acsf_cta_prefix_bytes(0, 0);
   L.smem = prefix + warpBytes * L.wpb;
   while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
-  if (L.smem > 220 * 1024 && L.staged) { L.staged = false; L.capC = 0; L.wpb = 4; L.smem = warpBytes * L.wpb;
-    while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = warpBytes * L.wpb; } }
+  if (L.smem > 220 * 1024 && L.staged) { L.staged = false; L.capC = 0; L.wpb = 4; L.smem = acsf_cta_prefix_bytes(0, 0) + warpBytes * L.wpb;
+    while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = acsf_cta_prefix_bytes(0, 0) + warpBytes * L.wpb; } }
   if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
   // atoms of a bin are split over blockIdx.y so that a CTA sees ~4 rounds of its warps and the
   // grid still fills the GPU when a structure has few, crowded bins

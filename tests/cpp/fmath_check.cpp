@@ -49,6 +49,37 @@ int main() {
     if (re > mt) mt = re;
   }
   if (fnet_tanh(0.0) != 0.0 || fnet_tanh(1e3) != 1.0 || fnet_tanh(-1e3) != -1.0) { printf("tanh edge cases failed\n"); return 1; }
-  printf("FMATH_OK %.3e %.3e %.3e\n", me, ml, mt);
-  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13) ? 0 : 2;
+  // table-driven variants (ACSF pair loops): exp relative, log absolute + relative mix (the power
+  // (1 + lam cos)^xi = exp(xi log b) needs a small ABSOLUTE error of the logarithm)
+  static double tab[FNET_TAB_DOUBLES];
+  for (int i = 0; i < FNET_EXP_TAB_N; i++) tab[i] = fnet_exp_tab_h[i];
+  for (int i = 0; i < 2 * FNET_LOG_TAB_N; i++) tab[FNET_EXP_TAB_N + i] = fnet_log_tab_h[i];
+  double met = 0.0, mlt = 0.0;
+  for (int i = 0; i < 4000000; i++) {
+    double u = urand(seed);
+    double x = (i % 4 == 0) ? -700.0 * u : (i % 4 == 1 ? 700.0 * u : (i % 4 == 2 ? -40.0 * u : 3.0 * (u - 0.5)));
+    double a = fnet_exp_tab(x, tab), b = exp(x);
+    double re = fabs(a - b) / b;
+    if (re > met) met = re;
+  }
+  if (fnet_exp_tab(-709.0, tab) != 0.0 || fnet_exp_tab(-INFINITY, tab) != 0.0 || fnet_exp_tab(0.0, tab) != 1.0) { printf("exp_tab edge cases failed\n"); return 1; }
+  for (int i = 0; i < 4000000; i++) {
+    double u = urand(seed);
+    double x;
+    switch (i % 6) {
+      case 0: x = 2.0 * u; break;
+      case 1: x = ldexp(1.0 + u, -(int)(60 * urand(seed))); break;
+      case 2: x = 1.0 + 1e-6 * (u - 0.5); break;
+      case 3: x = exp(-700.0 * u); break;
+      case 4: x = 0.6875 + 0.6875 * u; break;                  // the whole table range
+      default: x = 0.70710678 + 0.0000001 * (u - 0.5) + (i & 8 ? 0.70710678 : 0.0); break;
+    }
+    if (x <= 0.0) continue;
+    double a = fnet_log_tab(x, tab), b = log(x);
+    double err = fabs(a - b) / (4e-16 + 4e-16 * fabs(b));       // in units of the bound
+    if (err > mlt) mlt = err;
+  }
+  if (fnet_log_tab(0.0, tab) != -INFINITY || fnet_log_tab(1.0, tab) != 0.0) { printf("log_tab edge cases failed\n"); return 1; }
+  printf("FMATH_OK %.3e %.3e %.3e tab: %.3e %.3f\n", me, ml, mt, met, mlt);
+  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13 && met < 1e-14 && mlt < 1.0) ? 0 : 2;
 }
