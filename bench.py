@@ -243,8 +243,7 @@ def main():
     lat_pinned = torch.from_numpy(ds.latvecs.copy()).pin_memory()
 
     def step_e2e():
-        ctx.update_coords(0, coords_pinned.numpy(), lat_pinned.numpy())
-        acsf.calculate(0)
+        acsf.calculate(0, coords=coords_pinned.numpy(), latvecs=lat_pinned.numpy())
         return net.update_gradients(0, "mse", fetch=True)
 
     def barrier():
@@ -336,7 +335,7 @@ def main():
             "e2e": {"value": total_atoms / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(ds.coords.nbytes + ds.latvecs.nbytes + 2 * F * 8),
                     "d2h_bytes_per_step": int((wb.size + 2) * 8 + 2 * 32),
-                    "path": "fnetgpu_coords_update(host pinned) -> cell list -> acsf_calculate -> grad -> ddSerial+loss on host (wall clock)"},
+                    "path": "fnetgpu_acsf_update_calculate(coords + lattices from pinned host memory, copy chunks overlapped with the ACSF kernel) -> fnetgpu_grad -> ddSerial + loss on the host (wall clock)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_acsf", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -17,7 +17,7 @@ SYMBOLS = [
     "fnetgpu_forces", "fnetgpu_comm_unique_id", "fnetgpu_comm_init", "fnetgpu_set_stream",
     "fnetgpu_launch_count", "fnetgpu_profile", "fnetgpu_profile_get", "fnetgpu_kernel_name",
     "fnetgpu_max_neighbors", "fnetgpu_acsf_path_set", "fnetgpu_acsf_path_get",
-    "fnetgpu_mlp_path_set", "fnetgpu_mlp_path_get", "fnetgpu_socket_step",
+    "fnetgpu_mlp_path_set", "fnetgpu_mlp_path_get", "fnetgpu_socket_step", "fnetgpu_acsf_update_calculate",
 ]
 
 

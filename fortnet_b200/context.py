@@ -172,15 +172,22 @@ class Acsf:
         self.n_acsf = F
         self.n_feat = F + len(idx)
 
-    def calculate(self, slot, zprec=None):
+    def calculate(self, slot, zprec=None, coords=None, latvecs=None):
         """``TAcsf%calculate`` (acsf.F90:540-639): features of the slot's dataset stay on the GPU.
-        zprec given (or already stored) -> use it; else computed from this dataset (training set)."""
+        zprec given (or already stored) -> use it; else computed from this dataset (training set).
+        coords (and optionally latvecs) given: new geometry for the slot, uploaded by the same call
+        (copy overlapped with the kernel, ``fnetgpu_acsf_update_calculate``)."""
         if zprec is not None:
             self.zprec = _d(zprec).reshape(2, -1).copy()
         have = self.zprec is not None
         buf = self.zprec.reshape(-1).copy() if have else np.zeros(2 * max(self.n_acsf, 1))
-        self.ctx._check(self.ctx._lib.fnetgpu_acsf_calculate(self.ctx._h, C.c_int(slot), C.c_int(int(self.t_zscore)),
-                                                             _p(buf), C.c_int(int(have))))
+        if coords is not None:
+            self.ctx._check(self.ctx._lib.fnetgpu_acsf_update_calculate(
+                self.ctx._h, C.c_int(slot), _p(_d(coords)), _p(_d(latvecs)) if latvecs is not None else None,
+                C.c_int(int(self.t_zscore)), _p(buf), C.c_int(int(have))))
+        else:
+            self.ctx._check(self.ctx._lib.fnetgpu_acsf_calculate(self.ctx._h, C.c_int(slot), C.c_int(int(self.t_zscore)),
+                                                                 _p(buf), C.c_int(int(have))))
         if self.t_zscore and not have and self.n_acsf:
             self.zprec = buf.reshape(2, -1)[:, :self.n_acsf].copy()
         self.ctx.n_feat[slot] = self.n_feat

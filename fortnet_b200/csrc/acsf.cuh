@@ -62,6 +62,7 @@ __host__ __device__ inline size_t acsf_cta_prefix_bytes(int capC, int path = 1) 
 struct GeomArgs {                     // device pointers, passed by value to the kernels
   const int *binStruct; const StructInfo *sinfo; const int *cellStart; const CRec *crec;      // PATH 0 / 1
   const int *offsets; const double *coords; const double *lat; const int *periodic; const int *atnum;   // PATH 2
+  int stBase;                         // PATH 2: first structure of this launch (chunked, copy-overlapped launches)
 };
 struct CtaGeom {                      // per-CTA view produced by acsf_cta_prologue
   const StructInfo *S; BinPos bp; const int *cellStart; const CRec *crec;
@@ -87,7 +88,7 @@ __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit,
   c.first = 0;
   wbase = smem_raw;
   if (PATH == FNET_PATH_STRUCT) {
-    const int st = blockIdx.x;
+    const int st = G.stBase + blockIdx.x;
     const int beg = G.offsets[st], end = G.offsets[st + 1];
     const int per = (end - beg + nSplit - 1) / nSplit;
     c.a0 = beg + blockIdx.y * per; c.a1 = min(end, c.a0 + per); c.first = beg;

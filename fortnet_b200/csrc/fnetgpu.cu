@@ -89,6 +89,7 @@ extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
     if (d) d(ctx->comm);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->evChunk[i]); }
   if (ctx->prof) { for (int i = 0; i < FNET_PROF_RING; i++) { cudaEventDestroy(ctx->prof[i].a); cudaEventDestroy(ctx->prof[i].b); } delete[] ctx->prof; }
   if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -572,7 +573,7 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
 }
 
 // launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
-struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; };
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; };
 // the whole-structure path (cells.cuh): small structures, lattice check passed so far
 static bool use_struct_path(const fnetgpu_ctx *ctx, const Slot &s) {
   return !ctx->acsfPathCells && s.structPath && s.maxAtoms <= FNET_STRUCT_MAX_ATOMS && s.d_coords && s.d_lat;
@@ -585,6 +586,7 @@ static GeomArgs geom_args(const Slot &s) {
   GeomArgs g;
   g.binStruct = s.d_binStruct; g.sinfo = s.d_sinfo; g.cellStart = s.d_cellStart; g.crec = s.d_crec;
   g.offsets = s.d_offsets; g.coords = s.d_coords; g.lat = s.d_lat; g.periodic = s.d_periodic; g.atnum = s.d_atnum;
+  g.stBase = 0;
   return g;
 }
 static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
@@ -724,7 +726,8 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   const int nExtSel = (int)ctx->extIdx.size();
   const int nFeat = T.F + nExtSel;
   real *feat = (real *)s.d_feat;
-  const GeomArgs geo = geom_args(s);
+  GeomArgs geo = geom_args(s);
+  geo.stBase = L.stBase;
 #define FNET_ACSF_LAUNCH(NS, PATH)                                                                             \
   do {                                                                                                         \
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
@@ -745,7 +748,10 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 
 
 template <typename real>
-static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *zprec, int have_zprec) {
+static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *zprec, int have_zprec,
+                            const double *h_coords = nullptr) {
+  // h_coords: new coordinates still on the host (fnetgpu_acsf_update_calculate) -- uploaded in
+  // chunks of structures on a second stream while the kernel already works on the earlier chunks
   const AcsfTables &T = ctx->acsf;
   const int F = T.F, nExtSel = (int)ctx->extIdx.size();
   const int nFeat = F + nExtSel;
@@ -779,12 +785,39 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       if (sp) {
         if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), F), L)) return 1;
       } else {
+        if (h_coords) {                         // the cell list is built from the device copy: plain upload first
+          CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, h_coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+          h_coords = nullptr;
+        }
         if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
         if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
         if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
       }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-      if (launch_acsf_values<real>(ctx, s, L, useGiven ? ctx->d_zprec : nullptr)) return 1;
+      if (h_coords && sp) {
+        // whole-structure path: structures are independent launches -> pipeline copy and kernel
+        if (!ctx->copyStream) {
+          CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+          for (int c = 0; c < 8; c++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evChunk[c], cudaEventDisableTiming));
+        }
+        const int nChunk = std::max(1, std::min(8, s.nStruct / 512));
+        for (int c = 0; c < nChunk; c++) {
+          const int st0 = (int)((long long)s.nStruct * c / nChunk), st1 = (int)((long long)s.nStruct * (c + 1) / nChunk);
+          const size_t a0 = s.h_offsets[st0], a1 = s.h_offsets[st1];
+          CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords + 3 * a0, h_coords + 3 * a0, 3 * (a1 - a0) * sizeof(double), cudaMemcpyHostToDevice, ctx->copyStream));
+          CUDA_TRY(ctx, cudaEventRecord(ctx->evChunk[c], ctx->copyStream));
+        }
+        for (int c = 0; c < nChunk; c++) {
+          const int st0 = (int)((long long)s.nStruct * c / nChunk), st1 = (int)((long long)s.nStruct * (c + 1) / nChunk);
+          CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evChunk[c], 0));
+          AcsfLaunch Lc = L;
+          Lc.stBase = st0; Lc.grid = dim3(st1 - st0, L.nSplit);
+          if (launch_acsf_values<real>(ctx, s, Lc, useGiven ? ctx->d_zprec : nullptr)) return 1;
+        }
+        h_coords = nullptr;                     // on the device now: retries relaunch over the whole slot
+      } else {
+        if (launch_acsf_values<real>(ctx, s, L, useGiven ? ctx->d_zprec : nullptr)) return 1;
+      }
       int h[16];
       CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -869,6 +902,28 @@ extern "C" int fnetgpu_acsf_calculate(fnetgpu_ctx *ctx, int slot, int standardiz
   have_zprec = have_zprec ? 1 : 0;
   if (ctx->precision == 64) return acsf_calculate_t<double>(ctx, s, standardize, zprec, have_zprec);
   return acsf_calculate_t<float>(ctx, s, standardize, zprec, have_zprec);
+}
+
+// fnetgpu_coords_update + fnetgpu_acsf_calculate in one blocking call; for small structures the
+// upload is pipelined with the kernel (chunks of structures, second stream)
+extern "C" int fnetgpu_acsf_update_calculate(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs,
+                                             int standardize, double *zprec, int have_zprec) {
+  CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
+  Slot &s = ctx->slots[slot];
+  if (!s.used) FNET_FAIL(ctx, "acsf_update_calculate: empty slot");
+  if (!coords) FNET_FAIL(ctx, "acsf_update_calculate: coords missing");
+  if (!ctx->acsfSet || ctx->acsf.F == 0) FNET_FAIL(ctx, "acsf_update_calculate: call fnetgpu_acsf_set first");
+  cudaSetDevice(ctx->device);
+  if (dev_reserve(ctx, &s.d_coords, &s.capCoords, (size_t)3 * s.N)) return 1;
+  if (latvecs) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
+    s.structPath = 1;
+  }
+  s.cellRc = -1.0; s.neighStale = true; s.featValid = false;
+  have_zprec = have_zprec ? 1 : 0;
+  if (ctx->precision == 64) return acsf_calculate_t<double>(ctx, s, standardize, zprec, have_zprec, coords);
+  return acsf_calculate_t<float>(ctx, s, standardize, zprec, have_zprec, coords);
 }
 
 template <typename real> __global__ void k_convert_out(size_t n, const real *__restrict__ in, double *__restrict__ out) {

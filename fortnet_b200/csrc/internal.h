@@ -158,6 +158,8 @@ struct fnetgpu_ctx {
   int precision = 64;
   int deterministic = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;   // chunked host->device copies overlapped with the ACSF kernel (fnetgpu_acsf_update_calculate)
+  cudaEvent_t evChunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ownStream = true;
   std::string err;
   int nSM = 148;

@@ -118,6 +118,13 @@ int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces /* [3*nOut*N] */);
 int fnetgpu_comm_unique_id(char *id /* [FNETGPU_UNIQUE_ID_BYTES] */);
 int fnetgpu_comm_init(fnetgpu_ctx *ctx, int nRanks, int rank, const char *id);
 
+/* fnetgpu_coords_update followed by fnetgpu_acsf_calculate as ONE blocking call (same arguments):
+ * for datasets of small structures the host->device copy is cut into chunks of structures and
+ * overlapped with the ACSF kernel of the chunks already on the device.  coords should be pinned
+ * host memory for the overlap to happen (pageable memory works, the copies are then staged). */
+int fnetgpu_acsf_update_calculate(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs_or_null,
+                                  int standardize, double *zprec_inout, int have_zprec);
+
 /* One MD / i-PI step for a resident slot -- replaces calculateMappingsForSocketComm +
  * predictForSocketComm (prg_fnet/fortnet.F90:430-609): new coordinates (and cell, or NULL when it is
  * unchanged) in; per-structure summed outputs globalPred[nOut*nStruct], per-atom outputs

@@ -310,6 +310,32 @@ def test_whole_structure_path_hands_over_after_lattice_update(fb, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_update_calculate_pipelined_upload(fb, path):
+    """fnetgpu_acsf_update_calculate (chunked upload overlapped with the kernel, 3 chunks here) gives
+    bit-identical features to fnetgpu_coords_update + fnetgpu_acsf_calculate, also when the lattice changes"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=1600, seed=77)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 6, 6)
+    ctx = fb.Context(acsf_path=path)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    rng = np.random.default_rng(3)
+    for scale in (1.0, 1.02, 0.7):
+        c = (ds.coords + rng.normal(scale=0.03, size=ds.coords.shape)) * scale
+        l = ds.latvecs * scale
+        acsf.calculate(0, coords=c, latvecs=l)
+        a = acsf.features(0)
+        if path == "auto":
+            assert ctx.acsf_path(0) in (STRUCT if scale > 0.9 else CELLS)
+        ctx.update_coords(0, c, l)
+        acsf.calculate(0)
+        b = acsf.features(0)
+        assert np.array_equal(a, b), _md(a, b)
+    ctx.close()
+
+
 @pytest.mark.parametrize("path,precision", [("auto", 64), ("cells", 64), ("auto", 32)])
 def test_socket_step(fb, orc, path, precision):
     """fnetgpu_socket_step (predictForSocketComm, fortnet.F90:503-609): an MD trajectory of a resident
