@@ -51,10 +51,10 @@ class Context:
             raise ValueError("acsf_path must be 'auto' or 'cells'")
         if acsf_path == "cells":
             self._check(self._lib.fnetgpu_acsf_path_set(self._h, C.c_int(1)))
-        if mlp not in ("auto", "legacy"):
-            raise ValueError("mlp must be 'auto' or 'legacy'")
-        if mlp == "legacy":
-            self._check(self._lib.fnetgpu_mlp_path_set(self._h, C.c_int(1)))
+        if mlp not in ("auto", "legacy", "nofuse"):
+            raise ValueError("mlp must be 'auto', 'legacy' or 'nofuse'")
+        if mlp != "auto":
+            self._check(self._lib.fnetgpu_mlp_path_set(self._h, C.c_int(1 if mlp == "legacy" else 2)))
         self.n_feat = {}
         self.n_atoms = {}
         self.n_struct = {}

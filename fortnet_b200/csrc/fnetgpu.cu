@@ -58,7 +58,8 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
   cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
-  { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0; }
+  { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0;
+    ctx->mlpNoFuse = (pm && strcmp(pm, "nofuse") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
   return 0;
@@ -69,7 +70,7 @@ static void free_slot(Slot &s) {
   cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
   cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
-  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
+  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_tilesS); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
   cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
   s = Slot();
 }
@@ -638,8 +639,9 @@ extern "C" int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode) {
 }
 extern "C" int fnetgpu_mlp_path_set(fnetgpu_ctx *ctx, int mode) {
   CHECK_CTX(ctx);
-  if (mode != 0 && mode != 1) FNET_FAIL(ctx, "mlp_path_set: mode must be 0 (auto) or 1 (register-tiled kernels)");
-  ctx->mlpLegacy = mode;
+  if (mode < 0 || mode > 2) FNET_FAIL(ctx, "mlp_path_set: mode must be 0 (auto), 1 (register-tiled kernels) or 2 (DMMA without fused sums)");
+  ctx->mlpLegacy = (mode == 1) ? 1 : 0;
+  ctx->mlpNoFuse = (mode == 2) ? 1 : 0;
   return 0;
 }
 extern "C" int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx) {
@@ -1012,7 +1014,7 @@ extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, cons
   if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
   if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
   ctx->netSet = true; ctx->paramsSet = false;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; }
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; }
   return 0;
 }
 
@@ -1061,6 +1063,22 @@ static int ensure_tiles(fnetgpu_ctx *ctx, Slot &s) {
       }
     s.nTiles16 = (int)t16.size() / 3;
     if (dev_upload(ctx, &s.d_tiles16, t16.data(), t16.size())) return 1;
+    // structure-aligned rounds: single-species data (the species-sorted order is the atom order) with
+    // <= 64 atoms per structure -> whole structures packed greedily into rounds of <= 64 atoms
+    s.nTilesS = 0;
+    if ((int)s.spBeg.size() == 2 && s.maxAtoms <= R) {
+      std::vector<int> ts;
+      int st = 0;
+      while (st < s.nStruct) {
+        const int b = s.h_offsets[st];
+        int e = st;
+        while (e < s.nStruct && s.h_offsets[e + 1] - b <= R) e++;
+        ts.push_back(b); ts.push_back(s.h_offsets[e] - b); ts.push_back(0);
+        st = e;
+      }
+      s.nTilesS = (int)ts.size() / 3;
+      if (dev_upload(ctx, &s.d_tilesS, ts.data(), ts.size())) return 1;
+    }
   }
   real *raw = nullptr;
   if (dev_alloc(ctx, &raw, (size_t)s.N * n.nOut)) return 1;
@@ -1165,11 +1183,17 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
   if (check_ready<real>(ctx, s, true)) return 1;
   const NetTables &n = ctx->net;
   const size_t nDD = (size_t)n.nTot * n.nSpecies;
-  if (run_forward<real>(ctx, s)) return 1;
-  if (run_struct_loss<real>(ctx, s, lossId)) return 1;
   const bool mma = use_mma<real>(ctx);
+  // every structure inside one round of the DMMA kernel: E_s, loss gradient and loss terms are formed
+  // in the gradient kernel itself -- no separate forward pass, no k_struct_loss
+  const bool fused = mma && s.nTilesS > 0 && s.nA == 0 && s.nG >= 1 && !ctx->mlpNoFuse;
+  if (!fused) {
+    if (run_forward<real>(ctx, s)) return 1;
+    if (run_struct_loss<real>(ctx, s, lossId)) return 1;
+  }
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 0);
-  const MmaLaunch M = plan_mma(ctx, s, 0);
+  MmaLaunch M = plan_mma(ctx, s, 0);
+  if (fused) M.grid = std::max(1, std::min(M.grid, s.nTilesS));
   const int grid = mma ? M.grid : B.grid;
   size_t need = (size_t)grid * nDD;
   if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
@@ -1183,6 +1207,15 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
       do { if (n.dims[0] <= 32) FNET_MMA_GRAD2(NSLOT, 1); else FNET_MMA_GRAD2(NSLOT, 2); } while (0)
 #define FNET_MMA_GRAD2(NSLOT, FCH)                                                                                \
       do {                                                                                                        \
+        if (fused) {                                                                                              \
+          CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT, FCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+          LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH, true><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>( \
+                                      s.nTilesS, s.d_tilesS, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
+                                      (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, s.d_at,   \
+                                      s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr,    \
+                                      s.d_gt, s.d_Es, s.d_lossPart)));                                            \
+          break;                                                                                                  \
+        }                                                                                                         \
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
         LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(   \
                                     s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
@@ -1203,6 +1236,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                 lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
   }
   LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
+  if (fused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
   if (allreduce_sum(ctx, ctx->d_dd, nDD + 2)) return 1;   // gradient | loss numerator | denominator
   if (ddSerial || loss) {
     if (ensure_pinned(ctx, nDD + 8)) return 1;

@@ -143,6 +143,7 @@ struct Slot {
   int *d_perm = nullptr;            // [N] atom ids sorted by species (stable)
   std::vector<int> spBeg;           // [nSpecies+1]
   int *d_tiles = nullptr; int nTiles = 0, tileT = 0; // (start, count, species) triples
+  int *d_tilesS = nullptr; int nTilesS = 0;          // structure-aligned rounds (fused per-structure sums), 0 = not applicable
   int *d_tiles16 = nullptr; int nTiles16 = 0;        // rounds (64 atoms of one species) of the FP64 tensor-core path (mlp_mma.cuh)
   // work buffers
   void *d_raw = nullptr;            // [N][nOut] real
@@ -194,6 +195,7 @@ struct fnetgpu_ctx {
   double *d_dd = nullptr;           // [nSpecies*nTot + 2] reduced gradient + loss numerator/denominator
   double *h_pinned = nullptr; size_t pinnedN = 0;
   int *d_flags = nullptr;           // [8] statistics / overflow flags (cells.cuh, acsf.cuh)
+  int mlpNoFuse = 0;                // FNETGPU_MLP=nofuse / mlp_path_set(2): DMMA kernels without the fused per-structure sums (tests, A/B)
   int mlpLegacy = 0;                // FNETGPU_MLP=legacy: register-tiled DFMA kernels of mlp.cuh also in precision 64 (tests, A/B)
   int acsfPathCells = 0;            // FNETGPU_ACSF_PATH=cells: never use the whole-structure path (tests, A/B)
   // comm

@@ -43,6 +43,7 @@ struct MmaLayout {
   int aOff[FNET_MAX_LAYERS];   // first row of a_l in a warp tile; block height roundup8(dims[l])
   int dOff[FNET_MAX_LAYERS];   // first row of f'(z_l), then delta_l (l >= 1); block height roundup8(dims[l])
   int aOffF[FNET_MAX_LAYERS];  // forward-only tile: layers ping-pong between two row blocks
+  int sOff;                    // 8 scratch rows of the training tile (fused per-structure sums)
   int rowsA, rows;             // rows of the forward-only tile / of the training tile
   int nGradTiles;              // 8x8 output tiles of all weight gradients
   int nBias;                   // sum of dims[1..L-1]
@@ -74,6 +75,7 @@ __host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
   }
   m.dOff[0] = r;
   for (int l = 1; l < net.L; l++) { m.dOff[l] = r; r += fnet_ru8(net.dims[l]); }
+  m.sOff = r; r += 8;
   m.rows = r;
   return m;
 }
@@ -256,13 +258,19 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
 // order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 16 w .. 16 w + 15.
 // smem: weights | warp 0 tile | warp 1 tile | ...   (tile: a_0 .. a_{L-1} | delta_1 .. delta_{L-1})
 // ------------------------------------------------------------------------------------------
-template <int MODE, int NSLOT, int FCH>
+// FUSED (MODE 0, global targets only, every structure inside ONE round -- single-species data with
+// <= 64 atoms per structure): the per-structure sums E_s, the loss gradients and the loss terms
+// (TBpnn_sysTrain, bpnn.F90:677-684; loss.F90:370-721) are formed inside the round, between the
+// forward and the backward sweep, so the separate forward kernel and k_struct_loss disappear and
+// every atom is propagated forward exactly once per iteration.
+template <int MODE, int NSLOT, int FCH, bool FUSED = false>
 __global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 6 ? 2 : 1))
 k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
            int nFeat, const double *__restrict__ wb, NetTables net, const int *__restrict__ structOf,
            const int *__restrict__ offsets, const double *__restrict__ gS, const double *__restrict__ at,
            const double *__restrict__ aw, const double *__restrict__ dsw, int nG, int nA, int lossId,
-           double *__restrict__ partials, double *__restrict__ raw) {
+           double *__restrict__ partials, double *__restrict__ raw, const double *__restrict__ gt = nullptr,
+           double *__restrict__ Es = nullptr, double *__restrict__ lossPart = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int TS = FNET_MMA_TS, TA = FNET_MMA_TA, NW = FNET_MMA_WARPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -384,14 +392,21 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       __syncthreads();
     }
     // per-atom loss-gradient scale (MODE 0): issued now, consumed after the forward sweep
-    double lgScale = 0.0, lgG0 = 0.0, lgG1 = 0.0;
-    int lgStruct = 0;
+    double lgScale = 0.0, lgG0 = 0.0, lgG1 = 0.0, lgAw = 0.0, lgW = 0.0;
+    int lgStruct = 0, lgB = 0, lgE = 0;
     if (warp < nIn) {
       if (MODE == 0 && myAtom >= 0) {
         lgStruct = structOf[myAtom];
-        lgScale = dsw[lgStruct] * aw[myAtom] / (double)(offsets[lgStruct + 1] - offsets[lgStruct]);   // bpnn.F90:446,698
-        if (nG > 0) lgG0 = gS[(size_t)nG * lgStruct];
-        if (nG > 1) lgG1 = gS[(size_t)nG * lgStruct + 1];
+        lgB = offsets[lgStruct]; lgE = offsets[lgStruct + 1];
+        lgAw = aw[myAtom]; lgW = dsw[lgStruct];
+        lgScale = lgW * lgAw / (double)(lgE - lgB);   // bpnn.F90:446,698
+        if (FUSED) {            // targets now, the sums after the forward sweep
+          if (nG > 0) lgG0 = gt[(size_t)nG * lgStruct];
+          if (nG > 1) lgG1 = gt[(size_t)nG * lgStruct + 1];
+        } else {
+          if (nG > 0) lgG0 = gS[(size_t)nG * lgStruct];
+          if (nG > 1) lgG1 = gS[(size_t)nG * lgStruct + 1];
+        }
       }
       // ---- features -> a_0[f][t] ----
 #pragma unroll
@@ -435,10 +450,53 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         if (lane < count)
           for (int k = 0; k < net.nOut; k++) raw[(size_t)net.nOut * myAtom + k] = o[k * TS + lane];
         __syncwarp();
-      } else {
+      }
+    }
+    if (MODE == 0 && FUSED) {
+      // ---- per-structure sums across the warps of the round (fixed order), loss gradient, loss terms ----
+      if (warp < nIn && lane < TA) T[m.sOff * TS + lane] = lgAw;       // atomic weights of the tile (0 for padding)
+      __syncthreads();
+      if (warp < nIn && lane < TA && myAtom >= 0) {
+        const int b = lgB - e0[0], e = lgE - e0[0];                    // the structure's atoms, round-local
+        const bool lead = (TA * warp + lane == b);                     // first atom of the structure: writes E_s and the loss terms
+        double ss = 0.0;
+        double *dL = T + m.dOff[L - 1] * TS;
+        for (int k = 0; k < nG; k++) {
+          double ek = 0.0;
+          for (int i = b; i < e; i++) ek += tiles0[(size_t)(i >> 4) * rows * TS + (m.aOff[L - 1] + k) * TS + (i & 15)];
+          const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
+          dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
+          if (lead) {
+            Es[(size_t)nG * lgStruct + k] = ek;
+            switch (lossId) {
+              case FNETGPU_LOSS_MAE: ss += fabs(tv - ek); break;
+              case FNETGPU_LOSS_MAPE: ss += fabs((tv - ek) / tv); break;
+              default: ss += (tv - ek) * (tv - ek);
+            }
+          }
+        }
+        if (lead) {
+          double sw = 0.0;
+          for (int i = b; i < e; i++) sw += tiles0[(size_t)(i >> 4) * rows * TS + m.sOff * TS + (i & 15)];
+          double lg;
+          switch (lossId) {
+            case FNETGPU_LOSS_RMS: lg = sqrt(ss / nG); break;
+            case FNETGPU_LOSS_MAPE: lg = 100.0 * ss / nG; break;
+            default: lg = ss / nG;
+          }
+          lossPart[2 * (size_t)lgStruct] = lgW * sw * lg;
+          lossPart[2 * (size_t)lgStruct + 1] = lgW * sw;
+        }
+      } else if (warp < nIn && lane < TA) {
+        double *dL = T + m.dOff[L - 1] * TS;
+        for (int k = 0; k < net.nOut; k++) dL[k * TS + lane] = 0.0;    // padding atoms
+      }
+    }
+    if (warp < nIn) {
+      if (MODE == 0) {
         // ---- output layer (linear): delta = lossgrad * scale (network.F90:276, bpnn.F90:446,677-701) ----
         double *dL = T + m.dOff[L - 1] * TS;
-        if (lane < TA) {
+        if (!FUSED && lane < TA) {
           const int s = lgStruct;
           const double scale = lgScale;
           for (int k = 0; k < net.nOut; k++) {

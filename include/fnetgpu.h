@@ -154,8 +154,11 @@ int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode);
 int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot);
 /* Subnetwork kernels in precision 64.  mode 0 (default): FP64 tensor-core (DMMA) kernels when the
  * network fits their limits (sum of layer widths <= 128, <= 72 8x8 weight-gradient tiles, shared
- * memory), else the register-tiled DFMA kernels; mode 1: always the latter (tests, A/B; also
- * FNETGPU_MLP=legacy at fnetgpu_init).  Precision 32 always uses the FFMA kernels. */
+ * memory), else the register-tiled DFMA kernels -- and, for single-species datasets with <= 64
+ * atoms per structure and global targets only, the per-structure sums / loss gradients fused into
+ * the gradient kernel (no separate forward pass); mode 1: always the register-tiled kernels;
+ * mode 2: DMMA kernels without that fusion (tests, A/B; also FNETGPU_MLP=legacy|nofuse at
+ * fnetgpu_init).  Precision 32 always uses the FFMA kernels. */
 int fnetgpu_mlp_path_set(fnetgpu_ctx *ctx, int mode);
 /* 1 if fnetgpu_grad / fnetgpu_predict would take the DMMA kernels for the current network */
 int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx);

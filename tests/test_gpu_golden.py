@@ -55,13 +55,13 @@ def test_predictions_and_forces(fb, entry, path):
 SD = gio.cases(mode=("train",), training=("sd",))
 
 
-@pytest.mark.parametrize("mlp", ["auto", "legacy"])   # DMMA kernels / register-tiled kernels
+@pytest.mark.parametrize("mlp", ["auto", "nofuse", "legacy"])   # DMMA kernels (+ fused per-structure sums where they apply) / register-tiled kernels
 @pytest.mark.parametrize("entry", SD, ids=[e["case"] for e in SD])
 def test_sd_training_step(fb, entry, mlp):
     from oracle import oracle as orc
     case = gio.Case(entry)
     ctx, acsf, net = _setup(fb, case, mlp=mlp)
-    assert ctx.mlp_path() == (1 if mlp == "auto" else 0)
+    assert ctx.mlp_path() == (0 if mlp == "legacy" else 1)
     ds = case.dataset
     wb0 = case.wb()
     dd, loss = net.update_gradients(0, loss=case.loss_name())

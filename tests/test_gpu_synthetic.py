@@ -71,6 +71,8 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
     net.set_params(wb)
     if mlp == "legacy":
         expect_mlp = 0
+    elif mlp == "nofuse" and expect_mlp is not None:
+        expect_mlp = min(expect_mlp, 1)
     if expect_mlp is not None:
         assert ctx.mlp_path() == expect_mlp, ctx.mlp_path()
     raw = net.predict_batch(0)
@@ -97,7 +99,8 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json configs at oracle-sized samples
 # ---------------------------------------------------------------------------------------------
-MLPS = ["auto", "legacy"]      # precision 64 subnetworks: DMMA kernels (mlp_mma.cuh) or the register-tiled ones (mlp.cuh)
+MLPS = ["auto", "nofuse", "legacy"]   # precision 64 subnetworks: DMMA kernels (mlp_mma.cuh; "auto" fuses the per-structure
+                                      # sums into the gradient kernel for single-species data), or the register-tiled ones
 
 
 @pytest.mark.parametrize("mlp", MLPS)
@@ -117,6 +120,25 @@ def test_c3_tio2(fb, orc, path, mlp):
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
     assert len(funcs) == 64
     _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1)
+
+
+@pytest.mark.parametrize("loss", ["mse", "rms", "mae", "mape"])
+@pytest.mark.parametrize("mlp", ["auto", "nofuse"])
+def test_fused_structure_sums_ragged_single_species(fb, orc, mlp, loss):
+    """single-species structures of 1..64 atoms (several per 64-atom round, ragged last tiles), two global
+    targets, dataset and atomic weights: the gradient kernel's fused per-structure sums / loss terms
+    against the oracle and against the unfused kernels"""
+    rng = np.random.default_rng(51)
+    natoms = [1, 7, 64, 3, 30, 30, 5, 64, 63, 2, 17, 40, 24, 1, 1, 9]
+    rc = 3.5 * fb.BOHR_PER_AA
+    coords = np.concatenate([rng.uniform(0.0, 2.0 * rc + 0.4 * rc * n ** (1 / 3), size=(n, 3)) for n in natoms])
+    N = sum(natoms)
+    ds = fb.Dataset.build(natoms, coords, np.zeros(len(natoms), np.int32), np.zeros((len(natoms), 3, 3)),
+                          np.full(N, 14, np.int32), gtargets=rng.uniform(1.0, 2.0, size=(len(natoms), 2)),
+                          weights=rng.integers(1, 4, size=len(natoms)), atomic_weights=rng.uniform(0.5, 1.5, size=N),
+                          atomic_numbers=[14])
+    funcs = _mixed_functions(fb, rc)
+    _full_check(fb, orc, ds, funcs, [len(funcs), 6, 5, 2], loss=loss, forces=False, mlp=mlp, expect_mlp=1)
 
 
 @pytest.mark.parametrize("dims,expect", [([9, 1], 1), ([9, 3, 1], 1), ([9, 17, 9, 33, 2, 1], 1), ([9, 40, 40, 40, 1], 1),

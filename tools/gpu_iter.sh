@@ -7,9 +7,10 @@ timeout 900 python -m pytest tests -m gpu -q -x "$@" > $O/${TAG}_pytest_gpu.log 
 tail -15 $O/${TAG}_pytest_gpu.log
 timeout 300 python bench.py --no-cpu-baseline > $O/${TAG}_bench_c2.json 2> $O/${TAG}_bench_c2.err; echo "bench c2 rc=$?"
 FNETGPU_ACSF_PATH=cells FNETGPU_MLP=legacy timeout 300 python bench.py --no-cpu-baseline > $O/${TAG}_bench_c2_cells.json 2> $O/${TAG}_bench_c2_cells.err; echo "bench c2 cells+legacy rc=$?"
+FNETGPU_MLP=nofuse timeout 300 python bench.py --no-cpu-baseline > $O/${TAG}_bench_c2_nofuse.json 2> $O/${TAG}_bench_c2_nofuse.err; echo "bench c2 nofuse rc=$?"
 timeout 300 python bench.py --workload c3 --no-cpu-baseline > $O/${TAG}_bench_c3.json 2> $O/${TAG}_bench_c3.err; echo "bench c3 rc=$?"
 timeout 200 python tools/e2e_breakdown.py c2 > $O/${TAG}_e2e_c2.txt 2>&1
-for f in c2 c2_cells c3; do python - $O/${TAG}_bench_$f.json <<'PY'
+for f in c2 c2_nofuse c2_cells c3; do python - $O/${TAG}_bench_$f.json <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
