@@ -11,10 +11,10 @@ timeout 400 python bench.py --workload c3 --no-cpu-baseline > $O/${TAG}_bench_c3
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; echo "bench ref rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_c2.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches_c2.log 2>&1; echo "launch list rc=$?"
-for K in k_acsf:1:1 k_bpnn:2:2; do
+for K in k_acsf:1:1 k_bpnn_mma:2:1; do
   C=${K##*:}; R=${K%:*}; S=${R##*:}; K=${R%%:*}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c $C -f -o $O/${TAG}_$K \
-      python tools/e2e_breakdown.py c2 2000 > $O/${TAG}_$K.log 2>&1
+      python tools/e2e_breakdown.py c2 10000 > $O/${TAG}_$K.log 2>&1
   ncu -i $O/${TAG}_$K.ncu-rep --page raw --csv > $O/${TAG}_$K.raw.csv 2>/dev/null
   echo "ncu $K rc=$?"
 done
