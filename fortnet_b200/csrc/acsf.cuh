@@ -390,7 +390,7 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
 // ------------------------------------------------------------------------------------------
 // one angular pass (acsf.F90:1377-1492) with up to NS ladder slots
 // ------------------------------------------------------------------------------------------
-template <int NS>
+template <int NS, bool FAST>
 __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab, const AngularPass *__restrict__ P,
                                              const WarpSmem &w, int nExt, const double *__restrict__ ext,
                                              const double *__restrict__ ftab) {
@@ -432,13 +432,24 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
     const int a = list_at(l1, j), b = list_at(l2, k);
     double base = w.fcE[a] * w.fcE[b];
     if (same && a != b) base *= 2.0;
-    if (type == FNETGPU_G4 && base != 0.0) {
+    if (!FAST && type == FNETGPU_G4 && base != 0.0) {
       const double ex = w.dx[a] - w.dx[b], ey = w.dy[a] - w.dy[b], ez = w.dz[a] - w.dz[b];
       const double djk2 = ex * ex + ey * ey + ez * ez;
       const double djk = sqrt(djk2);
       base = (djk > rc) ? 0.0 : base * fnet_exp_tab(-eta * djk2, ftab) * cutoff_fn(djk, w.qv[a] * w.qv[b], invrc);
     }
-    if (base != 0.0) {
+    if (FAST) {
+      // every slot: a fresh ladder from xi = 1 (p = b) with its own lam -- no branches, no joins
+      const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
+      const double pr = w.rinv[a] * w.rinv[b];
+      const double c = dot * (pr * (1.0 - 1e-13 * pr));   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        const double bb = fmax(fma(lam[s], c, 1.0), 0.0);
+        const double q = fnet_exp_tab(dxi[s] * fnet_log_tab(bb, ftab), ftab);
+        ladder_accumulate(&acc[s * FNET_LADDER], bb * base, q);
+      }
+    } else if (base != 0.0) {
       const double dot = w.dx[a] * w.dx[b] + w.dy[a] * w.dy[b] + w.dz[a] * w.dz[b];
       const double pr = w.rinv[a] * w.rinv[b];
       const double c = dot * (pr * (1.0 - 1e-13 * pr));   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
@@ -484,7 +495,10 @@ k_acsf(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfT
     const int n = gather_neighbors<PATH>(me, cg, tab, cap, w);
     if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
     radial_groups(i, n, tab, w, nExt, ext, cg.ftab);
-    for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) angular_pass<NS>(i, n, tab, &tab.apasses[pi_], w, nExt, ext, cg.ftab);
+    for (int pi_ = 0; pi_ < tab.nAngularPasses; pi_++) {
+      if (tab.apasses[pi_].fast) angular_pass<NS, true>(i, n, tab, &tab.apasses[pi_], w, nExt, ext, cg.ftab);
+      else angular_pass<NS, false>(i, n, tab, &tab.apasses[pi_], w, nExt, ext, cg.ftab);
+    }
     __syncwarp();
     // ---------------- coalesced feature write (+ z-score, + external features) ----------------
     real *out = feat + (size_t)nFeat * i;

@@ -188,17 +188,32 @@ __constant__ double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
 __constant__ double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
 #endif
 #define FNET_TAB_DOUBLES (FNET_EXP_TAB_N + 2 * FNET_LOG_TAB_N)     // exp table, then (invc, logc) pairs
+// scalar constants of the two routines: from the constant bank on the device (a 64-bit literal costs
+// two UMOVs per use; ncu counted 200 of them per atom in the ACSF kernel)
+#define FNET_TABC_INIT { 92.332482616893656877, -1.08304246932675596327e-02, -2.98158582698529328128e-12, \
+  8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, \
+  1.4285714285714285e-01, -1.6666666666666666e-01, 0.2, -0.25, 3.3333333333333331e-01, \
+  6.93147180369123816490e-01, 1.90821492927058770002e-10 }
+static const double fnet_tabc_h[13] = FNET_TABC_INIT;
+#ifdef __CUDACC__
+__constant__ double fnet_tabc_d[13] = FNET_TABC_INIT;
+#endif
+#ifdef __CUDA_ARCH__
+#define FNET_TC(i) fnet_tabc_d[i]
+#else
+#define FNET_TC(i) fnet_tabc_h[i]
+#endif
 
 FNET_HD double fnet_exp_tab(double x, const double *__restrict__ tab) {
   const double magic = 6755399441055744.0;
-  const double tk = fma(x, 92.332482616893656877, magic);          // 64 / ln2
+  const double tk = fma(x, FNET_TC(0), magic);                     // 64 / ln2
   const int kj = fnet_lo(tk);
   const double kd = tk - magic;
-  double r = fma(kd, -1.08304246932675596327e-02, x);              // ln2/64 high part (32 significant bits)
-  r = fma(kd, -2.98158582698529328128e-12, r);                     // ln2/64 low part
+  double r = fma(kd, FNET_TC(1), x);                               // -ln2/64 high part (32 significant bits)
+  r = fma(kd, FNET_TC(2), r);                                      // -ln2/64 low part
   const double T = tab[kj & 63];
-  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-  p = fma(p, r, 1.6666666666666666e-01);
+  double p = fma(r, FNET_TC(3), FNET_TC(4));                       // 1/120, 1/24
+  p = fma(p, r, FNET_TC(5));                                       // 1/6
   p = fma(p, r, 0.5);
   const double q = fma(p, r * r, r);                               // e^r - 1
   const double v = fma(T, q, T);
@@ -215,14 +230,14 @@ FNET_HD double fnet_log_tab(double x, const double *__restrict__ tab) {
   const double invc = tab[FNET_EXP_TAB_N + 2 * i], logc = tab[FNET_EXP_TAB_N + 2 * i + 1];
   const double r = fma(z, invc, -1.0);
   const double kd = (double)k;
-  double p = fma(r, 1.4285714285714285e-01, -1.6666666666666666e-01);   // 1/7, -1/6
-  p = fma(p, r, 0.2);
-  p = fma(p, r, -0.25);
-  p = fma(p, r, 3.3333333333333331e-01);
+  double p = fma(r, FNET_TC(6), FNET_TC(7));                       // 1/7, -1/6
+  p = fma(p, r, FNET_TC(8));                                       // 1/5
+  p = fma(p, r, FNET_TC(9));                                       // -1/4
+  p = fma(p, r, FNET_TC(10));                                      // 1/3
   p = fma(p, r, -0.5);
-  const double w = fma(kd, 6.93147180369123816490e-01, logc);      // exact: ln2_hi has 32 significant bits
+  const double w = fma(kd, FNET_TC(11), logc);                     // exact: ln2_hi has 32 significant bits
   double res = fma(p, r * r, r) + w;
-  res = fma(kd, 1.90821492927058770002e-10, res);
+  res = fma(kd, FNET_TC(12), res);
   return (hi < 0x00100000) ? -INFINITY : res;
 }
 

@@ -413,6 +413,14 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       ctx->h_apasses.push_back(P);
     }
   }
+  {   // straight-line variant of the pair loop (acsf.cuh angular_pass<NS, true>)
+    const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
+    for (AngularPass &P : ctx->h_apasses) {
+      bool fast = P.type == FNETGPU_G5 && P.nSlots == ns;
+      for (int q = 0; q < P.nSlots && fast; q++) fast = P.slot[q].cont == 0 && P.slot[q].xi0 == 1.0;
+      P.fast = fast ? 1 : 0;
+    }
+  }
   T.nRadialGroups = (int)ctx->h_rgroups.size();
   T.nAngularPasses = (int)ctx->h_apasses.size();
   if (dev_upload(ctx, &ctx->d_rgroups, ctx->h_rgroups.data(), ctx->h_rgroups.size())) return 1;

@@ -72,6 +72,8 @@ struct AngularPass {
   int same;          // lists identical (unordered pairs incl. diagonal)
   int atomId;
   int nSlots;
+  int fast;          // G5, nSlots == the kernel's NS, every slot a fresh ladder starting at xi = 1 (the auto scheme): straight-line pair loop
+  int pad_;
   double rc, eta;
   LadderSlot slot[FNET_SLOTS];
 };
