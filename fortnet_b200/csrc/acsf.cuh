@@ -36,13 +36,16 @@ struct WarpSmem {
   double *dx, *dy, *dz, *r, *rinv, *qv, *fcE;
   int *idx, *seg;
   double *outv;
+  double *red;       // [redRows][FNET_RED_STRIDE] scratch of reduce_smem
 };
+#define FNET_RED_STRIDE 33          // 32 lanes + 1: row r, column c sits in bank (r + c) mod 16
 
-__host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F) {
+__host__ __device__ inline size_t acsf_warp_smem_bytes(int cap, int F, int redRows) {
   size_t b = (size_t)cap * (7 * sizeof(double) + sizeof(int));
   b += (FNET_MAX_CODES + 4) * sizeof(int);
   b = (b + 7) & ~(size_t)7;
   b += (size_t)((F + 1) & ~1) * sizeof(double);
+  b += (size_t)redRows * FNET_RED_STRIDE * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
 // CTA prefix: staged candidates + the neighbour-cell tables of stage_candidates (PATH 1) or the
@@ -122,7 +125,7 @@ __device__ __forceinline__ CRec central_atom(const CtaGeom &c, int slot) {
   return PATH == FNET_PATH_STRUCT ? c.cand[slot - c.first] : c.crec[slot];
 }
 
-__device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap, int F) {
+__device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap, int F, int redRows = 0) {
   WarpSmem w;
   double *d = (double *)base;
   w.dx = d; w.dy = d + cap; w.dz = d + 2 * cap; w.r = d + 3 * cap; w.rinv = d + 4 * cap;
@@ -132,6 +135,7 @@ __device__ __forceinline__ WarpSmem carve_warp_smem(unsigned char *base, int cap
   size_t off = (size_t)cap * (7 * sizeof(double) + sizeof(int)) + (FNET_MAX_CODES + 4) * sizeof(int);
   off = (off + 7) & ~(size_t)7;
   w.outv = (double *)(base + off);
+  w.red = w.outv + ((F + 1) & ~1);
   return w;
 }
 
@@ -231,8 +235,19 @@ __device__ __forceinline__ NbList make_list(const AcsfTables &tab, const WarpSme
 }
 __device__ __forceinline__ int list_at(const NbList &l, int t) { return t < l.n0 ? l.s0 + t : l.s1 + (t - l.n0); }
 
+// fc = 0.5 q (cos(pi r / rc) + 1) (acsf.F90:1201) for 0 <= r <= rc, evaluated as q cos^2(pi r / (2 rc))
+// with the Taylor polynomial of cos on [0, pi/2] (12 terms, truncation 2e-17; absolute error ~2e-16,
+// what the reference's own cos + 1 cancellation has near rc) -- 14 FP64 operations instead of cospi's ~55
+__constant__ double fnet_cosh_cd[12] = {
+  1.0, -1.2337005501361697, 0.25366950790104803, -0.02086348076335296, 0.0009192602748394266,
+  -2.5202042373060607e-05, 4.710874778818172e-07, -6.386603083791852e-09, 6.565963114979473e-11,
+  -5.294400200734623e-13, 3.437739179098607e-15, -1.8359916521552453e-17 };   // (-1)^k (pi/2)^(2k) / (2k)!
 __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) {
-  return 0.5 * qq * (cospi(rr * invrc) + 1.0);   // acsf.F90:1201 (pi*rr/rcut)
+  const double x = rr * invrc, u = x * x;
+  double c = fnet_cosh_cd[11];
+#pragma unroll
+  for (int k = 10; k >= 0; k--) c = fma(c, u, fnet_cosh_cd[k]);
+  return qq * (c * c);
 }
 
 // (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
@@ -294,6 +309,31 @@ __device__ __forceinline__ double reduce_transpose(double (&v)[M], int lane, int
   }
   double r = v[0];
   for (int off = M * stride; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
+}
+
+// Same contract as reduce_transpose, through shared memory: every lane stores its M partial values
+// as column (lane / stride) of rows (lane % stride) * M + f, then lane L sums a slice of row
+// (L % stride) * M + (L / stride) % M and the slices are combined by xor shuffles.  M stores + 32 M /
+// (stride M) ... = 256 / 32 loads and adds per lane for the radial shape, 16 for a 16-value angular
+// pass -- about 40 % of the butterfly's instruction count (no 64-bit selects, two shuffles).
+template <int M>
+__device__ __forceinline__ double reduce_smem(const double (&v)[M], int lane, int stride, double *__restrict__ red) {
+  const int grp = lane % stride, sub = lane / stride;
+  const int rows = stride * M;                  // <= 32 here (M = 8: stride <= 4; M = 8 NS: stride = 1)
+  __syncwarp();
+#pragma unroll
+  for (int f = 0; f < M; f++) red[(grp * M + f) * FNET_RED_STRIDE + sub] = v[f];
+  __syncwarp();
+  const int nsub = 32 / stride;                 // columns in use
+  const int row = grp * M + sub % M;
+  const int parts = 32 / rows;                  // lanes sharing a row
+  const int part = sub / M;                     // = lane / rows
+  const int len = nsub / parts;
+  const double *rp = red + row * FNET_RED_STRIDE + part * len;
+  double r = 0.0;
+  for (int c = 0; c < len; c++) r += rp[c];
+  for (int off = rows; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
   return r;
 }
 
@@ -361,7 +401,7 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
           }
         }
       // sum over the sub-lanes: lane ends with function (lane / nch) % 8 of chunk lane % nch
-      const double v = reduce_transpose<FNET_RCHUNK>(acc, lane, nch);
+      const double v = reduce_smem<FNET_RCHUNK>(acc, lane, nch, w.red);
       const int f = (lane / nch) % FNET_RCHUNK;
       if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[fbase + f]] = v;
     } else {
@@ -467,7 +507,8 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       }
     }
   }
-  const double v = reduce_transpose<NS * FNET_LADDER>(acc, lane, 1);
+  const double v = (NS * FNET_LADDER < 32) ? reduce_smem<NS * FNET_LADDER>(acc, lane, 1, w.red)     // NS = 4: no scratch (redRows)
+                                            : reduce_transpose<NS * FNET_LADDER>(acc, lane, 1);
   {
     const int e = lane % (NS * FNET_LADDER);
     const int s = e / FNET_LADDER, f = e % FNET_LADDER;
@@ -488,7 +529,7 @@ k_acsf(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfT
   unsigned char *wbase;
   if (!acsf_cta_prologue<PATH>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;
   const int a0 = cg.a0, a1 = cg.a1;
-  WarpSmem w = carve_warp_smem(wbase + (size_t)wib * acsf_warp_smem_bytes(cap, tab.F), cap, tab.F);
+  WarpSmem w = carve_warp_smem(wbase + (size_t)wib * acsf_warp_smem_bytes(cap, tab.F, tab.redRows), cap, tab.F, tab.redRows);
   for (int slot = a0 + wib; slot < a1; slot += nw) {
     const CRec me = central_atom<PATH>(cg, slot);
     const int i = me.idx;

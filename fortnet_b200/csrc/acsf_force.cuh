@@ -22,7 +22,7 @@ struct ForceSmem {
 };
 
 __host__ __device__ inline size_t force_warp_smem_bytes(int cap, int F) {
-  return acsf_warp_smem_bytes(cap, F) + (size_t)cap * 4 * sizeof(double);
+  return acsf_warp_smem_bytes(cap, F, 0) + (size_t)cap * 4 * sizeof(double);
 }
 
 __device__ __forceinline__ double dcutoff_fn(double rr, double qq, double rc, double invrc) {
@@ -45,7 +45,7 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
   const int a0 = cg.a0, a1 = cg.a1;
   unsigned char *base = wbase + (size_t)wib * force_warp_smem_bytes(cap, tab.F);
   WarpSmem w = carve_warp_smem(base, cap, tab.F);
-  double *extra = (double *)(base + acsf_warp_smem_bytes(cap, tab.F));
+  double *extra = (double *)(base + acsf_warp_smem_bytes(cap, tab.F, 0));
   double *dE = extra, *fx = extra + cap, *fy = extra + 2 * cap, *fz = extra + 3 * cap;
   for (int slot = a0 + wib; slot < a1; slot += nw) {
   const CRec me = central_atom<PATH>(cg, slot);

@@ -420,6 +420,10 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       for (int q = 0; q < P.nSlots && fast; q++) fast = P.slot[q].cont == 0 && P.slot[q].xi0 == 1.0;
       P.fast = fast ? 1 : 0;
     }
+    int rows = 8 * std::min(ns, 4);
+    if (ns == 4) rows = 0;                       // 32 angular values per lane use the shuffle butterfly
+    for (const RadialGroup &G : ctx->h_rgroups) if (G.ladder) rows = std::max(rows, 8 * G.nChunksP2);
+    T.redRows = rows;
   }
   T.nRadialGroups = (int)ctx->h_rgroups.size();
   T.nAngularPasses = (int)ctx->h_apasses.size();
@@ -793,7 +797,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       AcsfLaunch L;
       const bool sp = use_struct_path(ctx, s);
       if (sp) {
-        if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), F), L)) return 1;
+        if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), F, T.redRows), L)) return 1;
       } else {
         if (h_coords) {                         // the cell list is built from the device copy: plain upload first
           CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, h_coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -801,7 +805,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
         }
         if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
         if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
-        if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F), L)) return 1;
+        if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F, T.redRows), L)) return 1;
       }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (h_coords && sp) {
@@ -1438,7 +1442,7 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
       s.cellRc = -1.0; s.neighStale = true;
       const double *zp = s.zscored ? ctx->d_zprec : nullptr;
       AcsfLaunch Lv, Lf;
-      if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F), Lv)) return 1;
+      if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F, T.redRows), Lv)) return 1;
       if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), Lf)) return 1;
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;

@@ -88,6 +88,7 @@ struct AcsfTables {           // device pointers + sizes, passed by value to ker
   int nCodes;                 // number of species codes
   int zcodes[FNET_MAX_CODES]; // atomic number of each code
   int anyAtomId;
+  int redRows;                // rows of the per-warp reduction scratch: 8 * max(NS, radial chunks)
   double rcMax;
 };
 
