@@ -463,7 +463,11 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         double *dL = T + m.dOff[L - 1] * TS;
         for (int k = 0; k < nG; k++) {
           double ek = 0.0;
-          for (int i = b; i < e; i++) ek += tiles0[(size_t)(i >> 4) * rows * TS + (m.aOff[L - 1] + k) * TS + (i & 15)];
+          for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {          // tile by tile, in atom order
+            const double *rp = tiles0 + (size_t)w2 * rows * TS + (m.aOff[L - 1] + k) * TS;
+            const int t1 = min(e - TA * w2, TA);
+            for (int t = max(b - TA * w2, 0); t < t1; t++) ek += rp[t];
+          }
           const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
           dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
           if (lead) {
@@ -477,7 +481,11 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         }
         if (lead) {
           double sw = 0.0;
-          for (int i = b; i < e; i++) sw += tiles0[(size_t)(i >> 4) * rows * TS + m.sOff * TS + (i & 15)];
+          for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {
+            const double *rp = tiles0 + (size_t)w2 * rows * TS + m.sOff * TS;
+            const int t1 = min(e - TA * w2, TA);
+            for (int t = max(b - TA * w2, 0); t < t1; t++) sw += rp[t];
+          }
           double lg;
           switch (lossId) {
             case FNETGPU_LOSS_RMS: lg = sqrt(ss / nG); break;
