@@ -184,8 +184,10 @@ FNET_HD double fnet_exp_lat(double x) { return fnet_exp_t<true>(x); }
 static const double fnet_exp_tab_h[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
 static const double fnet_log_tab_h[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
 #ifdef __CUDACC__
-__constant__ double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
-__constant__ double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
+// global (not constant) memory: the CTAs copy the tables into shared memory with one coalesced load
+// per thread -- lane-divergent reads of the constant bank would be serialised
+__device__ const double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
+__device__ const double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
 #endif
 #define FNET_TAB_DOUBLES (FNET_EXP_TAB_N + 2 * FNET_LOG_TAB_N)     // exp table, then (invc, logc) pairs
 // scalar constants of the two routines: from the constant bank on the device (a 64-bit literal costs
