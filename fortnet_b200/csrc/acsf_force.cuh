@@ -139,14 +139,21 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
       const int nPairs = same ? (n1 * (n1 + 1)) >> 1 : n1 * n2;
       const int W = same ? (n1 | 1) : n2;
       const float invW = W > 0 ? 1.0f / (float)W : 0.0f;
-      for (int p = lane; p < nPairs; p += 32) {
-        int j, k;
-        pair_decode(p, same, n1, W, invW, j, k);
+      // Lanes of one sweep hold consecutive pairs, i.e. runs of pairs with the same first neighbour a
+      // (row j of the pair walk): their contributions to a are combined by a segmented warp
+      // reduction and added once per run -- a plain atomicAdd per pair would serialise up to 32
+      // same-address shared-memory atomics.  The second neighbour b differs within a run.
+      for (int pbase = 0; pbase < nPairs; pbase += 32) {
+        const int p = pbase + lane;
+        const bool valid = p < nPairs;
+        int j = 0, k = 0;
+        if (valid) pair_decode(p, same, n1, W, invW, j, k);
         const int a = list_at(l1, j), b = list_at(l2, k);
         const double Ea = w.fcE[a], Eb = w.fcE[b];
         double wgt = (same && a != b) ? 2.0 : 1.0;
         double H = 1.0, dH = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
-        bool on = (Ea != 0.0 || dE[a] != 0.0) && (Eb != 0.0 || dE[b] != 0.0);
+        double gax = 0.0, gay = 0.0, gaz = 0.0;
+        bool on = valid && (Ea != 0.0 || dE[a] != 0.0) && (Eb != 0.0 || dE[b] != 0.0);
         if (type == FNETGPU_G4 && on) {
           // third leg r_ab (acsf.F90:1603-1611): d_a - d_b in Cartesian = r_a u_a - r_b u_b
           vx = w.r[a] * w.dx[a] - w.r[b] * w.dx[b];
@@ -189,12 +196,24 @@ k_acsf_force(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext,
           const double tb = wgt * Ea * H * S1 * Eb * w.rinv[b];
           const double sb = wgt * Ea * H * S0 * dE[b] - tb * c;
           const double th = wgt * S0 * Ea * Eb * dH;
-          atomicAdd(&fx[a], ta * w.dx[b] + sa * w.dx[a] + th * vx);
-          atomicAdd(&fy[a], ta * w.dy[b] + sa * w.dy[a] + th * vy);
-          atomicAdd(&fz[a], ta * w.dz[b] + sa * w.dz[a] + th * vz);
+          gax = ta * w.dx[b] + sa * w.dx[a] + th * vx;
+          gay = ta * w.dy[b] + sa * w.dy[a] + th * vy;
+          gaz = ta * w.dz[b] + sa * w.dz[a] + th * vz;
           atomicAdd(&fx[b], tb * w.dx[a] + sb * w.dx[b] - th * vx);
           atomicAdd(&fy[b], tb * w.dy[a] + sb * w.dy[b] - th * vy);
           atomicAdd(&fz[b], tb * w.dz[a] + sb * w.dz[b] - th * vz);
+        }
+        const int key = valid ? a : -1 - lane;           // runs of equal a are contiguous in the pair walk
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int ko = __shfl_down_sync(0xffffffffu, key, off);
+          const double x2 = __shfl_down_sync(0xffffffffu, gax, off), y2 = __shfl_down_sync(0xffffffffu, gay, off),
+                       z2 = __shfl_down_sync(0xffffffffu, gaz, off);
+          if (lane + off < 32 && ko == key) { gax += x2; gay += y2; gaz += z2; }
+        }
+        const int kp = __shfl_up_sync(0xffffffffu, key, 1);
+        if (valid && (lane == 0 || kp != key) && (gax != 0.0 || gay != 0.0 || gaz != 0.0)) {
+          atomicAdd(&fx[a], gax); atomicAdd(&fy[a], gay); atomicAdd(&fz[a], gaz);
         }
       }
     }

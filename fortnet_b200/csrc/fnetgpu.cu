@@ -862,8 +862,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
     double *part = ctx->d_partials, *sums = ctx->d_partials + (size_t)nb * F;   // sums[F] (+1 count)
     if (ensure_pinned(ctx, (size_t)2 * F + 8)) return 1;
-    double wN = 0.0;
-    for (int st = 0; st < s.nStruct; st++) wN += 1.0;  // placeholder, replaced below
+    double wN = 0.0;                             // sum_s w_s N_s (acsf.F90:462-470)
     {
       std::vector<double> dsw(s.nStruct);
       CUDA_TRY(ctx, cudaMemcpyAsync(dsw.data(), s.d_dsw, s.nStruct * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
