@@ -325,14 +325,13 @@ __device__ __forceinline__ double reduce_smem(const double (&v)[M], int lane, in
 #pragma unroll
   for (int f = 0; f < M; f++) red[(grp * M + f) * FNET_RED_STRIDE + sub] = v[f];
   __syncwarp();
-  const int nsub = 32 / stride;                 // columns in use
+  // 32 / stride columns are in use; 32 / rows lanes share a row, each sums (32 / stride) / (32 / rows) = M columns
   const int row = grp * M + sub % M;
-  const int parts = 32 / rows;                  // lanes sharing a row
   const int part = sub / M;                     // = lane / rows
-  const int len = nsub / parts;
-  const double *rp = red + row * FNET_RED_STRIDE + part * len;
+  const double *rp = red + row * FNET_RED_STRIDE + part * M;
   double r = 0.0;
-  for (int c = 0; c < len; c++) r += rp[c];
+#pragma unroll
+  for (int c = 0; c < M; c++) r += rp[c];
   for (int off = rows; off < 32; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
   return r;
 }
@@ -485,7 +484,9 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
       const double c = dot * (pr * (1.0 - 1e-13 * pr));   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
 #pragma unroll
       for (int s = 0; s < NS; s++) {
-        const double bb = fmax(fma(lam[s], c, 1.0), 0.0);
+        // |c| <= 1 up to rounding (the 1e-13 of the denominator pulls it inside for atomic distances);
+        // a last-bit negative b gives log = -inf, q = 0 and a term of 1e-16 * base: no clamp needed
+        const double bb = fma(lam[s], c, 1.0);
         const double q = fnet_exp_tab(dxi[s] * fnet_log_tab(bb, ftab), ftab);
         ladder_accumulate(&acc[s * FNET_LADDER], bb * base, q);
       }
