@@ -1233,7 +1233,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                     (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
                                     s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr)));   \
       } while (0)
-      if (perWarp <= 6) FNET_MMA_GRAD(6); else if (perWarp <= 12) FNET_MMA_GRAD(12); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
+      if (perWarp <= 4) FNET_MMA_GRAD(4); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
 #undef FNET_MMA_GRAD
 #undef FNET_MMA_GRAD2
       launched = true;

@@ -27,10 +27,12 @@
 #pragma once
 #include "mlp.cuh"
 
-#define FNET_MMA_TA 16             // atoms per warp tile (two m8 tiles)
+#define FNET_MMA_TA 8              // atoms per warp (one m8 tile)
+#define FNET_MMA_TW 16             // atoms per shared-memory tile: two warps share a tile (columns 0-7 / 8-15)
 #define FNET_MMA_TS 20             // row stride of the [row][atom] tiles, doubles
-#define FNET_MMA_WARPS 4
-#define FNET_MMA_MAXSLOTS 18       // weight-gradient output tiles a warp can own
+#define FNET_MMA_WARPS 8
+#define FNET_MMA_TILES (FNET_MMA_WARPS / 2)
+#define FNET_MMA_MAXSLOTS 9        // weight-gradient output tiles a warp can own
 
 __host__ __device__ inline int fnet_ru4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int fnet_ru8(int x) { return (x + 7) & ~7; }
@@ -82,7 +84,7 @@ __host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
 
 __host__ inline size_t bpnn_mma_smem_bytes(const NetTables &net, int mode) {
   const MmaLayout m = mma_layout(net);
-  return ((size_t)m.wTotal + (size_t)FNET_MMA_WARPS * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
+  return ((size_t)m.wTotal + (size_t)FNET_MMA_TILES * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
 }
 // limits of this path (else mlp.cuh): bias accumulators are one per thread, gradient tiles
 // <= MAXSLOTS per warp, everything in 220 KB of shared memory
@@ -121,41 +123,41 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
 // times per call site) and an even split of the dout*16 elements over the lanes
 template <bool DERIV>
 __device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane) {
-  // four elements per lane and iteration: independent dependency chains (the FP64 exp / reciprocal
-  // sequences are latency-bound at two warps per scheduler)
+  // two elements per lane and iteration: independent dependency chains (the FP64 exp / reciprocal
+  // sequences are latency-bound); the warp's 8 atoms are columns 0..7 of `out`
   const int n = dout * FNET_MMA_TA;
 #pragma unroll 1
-  for (int base = lane; base < n; base += 128) {
-    double x[4], v[4];
-    int off[4];
+  for (int base = lane; base < n; base += 64) {
+    double x[2], v[2];
+    int off[2];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2; q++) {
       const int idx = min(base + 32 * q, n - 1);
-      off[q] = (idx >> 4) * FNET_MMA_TS + (idx & 15);
+      off[q] = (idx >> 3) * FNET_MMA_TS + (idx & 7);
       x[q] = out[off[q]];
     }
     if (actId == FNETGPU_ACT_TANH) {
 #pragma unroll
-      for (int q = 0; q < 4; q++) v[q] = fnet_tanh(x[q]);
+      for (int q = 0; q < 2; q++) v[q] = fnet_tanh(x[q]);
     } else if (actId == FNETGPU_ACT_SIGMOID) {
 #pragma unroll
-      for (int q = 0; q < 4; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
+      for (int q = 0; q < 2; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
     } else {
 #pragma unroll 1
-      for (int q = 0; q < 4; q++) v[q] = act_f<double>(actId, x[q]);
+      for (int q = 0; q < 2; q++) v[q] = act_f<double>(actId, x[q]);
     }
-    double d[4];
+    double d[2];
     if (DERIV) {
       if (actId == FNETGPU_ACT_TANH || actId == FNETGPU_ACT_SIGMOID) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) d[q] = act_d<double>(actId == FNETGPU_ACT_TANH ? FNETGPU_ACT_TANH : FNETGPU_ACT_SIGMOID, x[q], v[q]);
+        for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId == FNETGPU_ACT_TANH ? FNETGPU_ACT_TANH : FNETGPU_ACT_SIGMOID, x[q], v[q]);
       } else {
 #pragma unroll 1
-        for (int q = 0; q < 4; q++) d[q] = act_d<double>(actId, x[q], v[q]);
+        for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId, x[q], v[q]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < 2; q++)
       if (base + 32 * q < n) {
         out[off[q]] = v[q];
         if (DERIV) dact[off[q]] = d[q];
@@ -172,25 +174,20 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
   const int g = lane >> 2, c = lane & 3;
   const int KT = fnet_ru4(din) >> 2, NT = fnet_ru8(dout) >> 3;
   for (int nt0 = 0; nt0 < NT; nt0 += 4) {
-    double acc[2][4][2];
+    double acc[4][2];
 #pragma unroll
     for (int nc = 0; nc < 4; nc++) {
       const int nb = 8 * min(nt0 + nc, NT - 1) + 2 * c;
-      const double b0 = bias[nb], b1 = bias[nb + 1];
-      acc[0][nc][0] = b0; acc[0][nc][1] = b1; acc[1][nc][0] = b0; acc[1][nc][1] = b1;
+      acc[nc][0] = bias[nb]; acc[nc][1] = bias[nb + 1];
     }
     const double *ip = in + c * FNET_MMA_TS + g;
     const double *wp = W + (size_t)(8 * nt0 + g) * wS + c;
 #pragma unroll 2
     for (int kt = 0; kt < KT; kt++) {
-      const double a0 = ip[(4 * kt) * FNET_MMA_TS], a1 = ip[(4 * kt) * FNET_MMA_TS + 8];
+      const double a0 = ip[(4 * kt) * FNET_MMA_TS];
 #pragma unroll
       for (int nc = 0; nc < 4; nc++)
-        if (nt0 + nc < NT) {
-          const double b = wp[(size_t)(8 * nc) * wS + 4 * kt];
-          dmma(acc[0][nc], a0, b);
-          dmma(acc[1][nc], a1, b);
-        }
+        if (nt0 + nc < NT) dmma(acc[nc], a0, wp[(size_t)(8 * nc) * wS + 4 * kt]);
     }
 #pragma unroll
     for (int nc = 0; nc < 4; nc++)
@@ -198,10 +195,7 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int o = 8 * (nt0 + nc) + 2 * c + e;
-          if (o < dout) {
-            out[o * FNET_MMA_TS + g] = acc[0][nc][e];
-            out[o * FNET_MMA_TS + 8 + g] = acc[1][nc][e];
-          }
+          if (o < dout) out[o * FNET_MMA_TS + g] = acc[nc][e];
         }
       }
   }
@@ -218,21 +212,17 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
   const int g = lane >> 2, c = lane & 3;
   const int KT = fnet_ru4(dout) >> 2, NT = fnet_ru8(din) >> 3;
   for (int nt0 = 0; nt0 < NT; nt0 += 4) {
-    double acc[2][4][2];
+    double acc[4][2];
 #pragma unroll
-    for (int nc = 0; nc < 4; nc++) { acc[0][nc][0] = 0.0; acc[0][nc][1] = 0.0; acc[1][nc][0] = 0.0; acc[1][nc][1] = 0.0; }
+    for (int nc = 0; nc < 4; nc++) { acc[nc][0] = 0.0; acc[nc][1] = 0.0; }
     const double *ip = dn + c * FNET_MMA_TS + g;
     const double *wp = W + (size_t)c * wS + 8 * nt0 + g;
 #pragma unroll 2
     for (int kt = 0; kt < KT; kt++) {
-      const double a0 = ip[(4 * kt) * FNET_MMA_TS], a1 = ip[(4 * kt) * FNET_MMA_TS + 8];
+      const double a0 = ip[(4 * kt) * FNET_MMA_TS];
 #pragma unroll
       for (int nc = 0; nc < 4; nc++)
-        if (nt0 + nc < NT) {
-          const double b = wp[(size_t)(4 * kt) * wS + 8 * nc];
-          dmma(acc[0][nc], a0, b);
-          dmma(acc[1][nc], a1, b);
-        }
+        if (nt0 + nc < NT) dmma(acc[nc], a0, wp[(size_t)(4 * kt) * wS + 8 * nc]);
     }
 #pragma unroll
     for (int nc = 0; nc < 4; nc++)
@@ -241,11 +231,8 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
         for (int e = 0; e < 2; e++) {
           const int i = 8 * (nt0 + nc) + 2 * c + e;
           if (i < din) {
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-              double *p = dl + i * FNET_MMA_TS + 8 * mt + g;
-              *p = acc[mt][nc][e] * *p;
-            }
+            double *p = dl + i * FNET_MMA_TS + g;
+            *p = acc[nc][e] * *p;
           }
         }
       }
@@ -255,8 +242,9 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
 // ------------------------------------------------------------------------------------------
 // MODE 0: training gradient -> partials[cta][nSpecies*nTot]; MODE 2: forward only -> raw[atom][k].
 // `tiles` holds the ROUNDS: (start, count <= 64, species) triples of the species-sorted atom
-// order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 16 w .. 16 w + 15.
-// smem: weights | warp 0 tile | warp 1 tile | ...   (tile: a_0 .. a_{L-1} | delta_1 .. delta_{L-1})
+// order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 8 w .. 8 w + 7.
+// smem: weights | tile 0 | .. | tile 3   (tile: rows a_0 .. a_{L-1} | delta_1 .. delta_{L-1} | scratch,
+// 16 atom columns: warps 2t and 2t+1 own columns 0-7 / 8-15 of tile t)
 // ------------------------------------------------------------------------------------------
 // FUSED (MODE 0, global targets only, every structure inside ONE round -- single-species data with
 // <= 64 atoms per structure): the per-structure sums E_s, the loss gradients and the loss terms
@@ -264,7 +252,7 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
 // forward and the backward sweep, so the separate forward kernel and k_struct_loss disappear and
 // every atom is propagated forward exactly once per iteration.
 template <int MODE, int NSLOT, int FCH, bool FUSED = false>
-__global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 6 ? 2 : 1))
+__global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 4 ? 2 : 1))
 k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
            int nFeat, const double *__restrict__ wb, NetTables net, const int *__restrict__ structOf,
            const int *__restrict__ offsets, const double *__restrict__ gS, const double *__restrict__ at,
@@ -272,7 +260,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
            double *__restrict__ partials, double *__restrict__ raw, const double *__restrict__ gt = nullptr,
            double *__restrict__ Es = nullptr, double *__restrict__ lossPart = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int TS = FNET_MMA_TS, TA = FNET_MMA_TA, NW = FNET_MMA_WARPS;
+  constexpr int TS = FNET_MMA_TS, TA = FNET_MMA_TA, TW = FNET_MMA_TW, NW = FNET_MMA_WARPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
   const int L = net.L, d0 = net.dims[0];
@@ -280,8 +268,9 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   const int rows = (MODE == 2) ? m.rowsA : m.rows;
   double *wsm = (double *)smem_raw;
   double *tiles0 = wsm + m.wTotal;
-  double *T = tiles0 + (size_t)warp * rows * TS;
-  for (int e = lane; e < rows * TS; e += 32) T[e] = 0.0;      // padding rows stay zero from here on
+  double *T = tiles0 + (size_t)(warp >> 1) * rows * TS + TA * (warp & 1);   // this warp's 8 columns of its tile
+  for (int e = threadIdx.x; e < FNET_MMA_TILES * rows * TS; e += blockDim.x) tiles0[e] = 0.0;   // padding rows stay zero from here on
+  __syncthreads();
 
   // ---- weight-gradient tiles owned by this warp: q = warp*per + s <-> (layer, i-tile, o-tile) ----
   int aRow[NSLOT], dRow[NSLOT], gInfo[NSLOT];
@@ -379,7 +368,10 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   atom1 = load_atom(e1);
   load_features(atom0);
   for (int r = round0; r < round1; r++) {
-    const int sp = e0[2], nIn = (e0[1] + TA - 1) / TA;
+    const int sp = e0[2];
+    const int nTl = (e0[1] + TW - 1) / TW;          // tiles with atoms in this round
+    const int nIn = 2 * nTl;                        // warps at work: BOTH halves of every such tile (a half without atoms
+                                                    // is swept with zero features so that no stale delta reaches the gradient sweep)
     const int count = min(max(e0[1] - TA * warp, 0), TA);
     const int myAtom = atom0;
     int e2[3];
@@ -465,8 +457,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           double ek = 0.0;
           for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {          // tile by tile, in atom order
             const double *rp = tiles0 + (size_t)w2 * rows * TS + (m.aOff[L - 1] + k) * TS;
-            const int t1 = min(e - TA * w2, TA);
-            for (int t = max(b - TA * w2, 0); t < t1; t++) ek += rp[t];
+            const int t1 = min(e - TW * w2, TW);
+            for (int t = max(b - TW * w2, 0); t < t1; t++) ek += rp[t];
           }
           const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
           dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
@@ -483,8 +475,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           double sw = 0.0;
           for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {
             const double *rp = tiles0 + (size_t)w2 * rows * TS + m.sOff * TS;
-            const int t1 = min(e - TA * w2, TA);
-            for (int t = max(b - TA * w2, 0); t < t1; t++) sw += rp[t];
+            const int t1 = min(e - TW * w2, TW);
+            for (int t = max(b - TW * w2, 0); t < t1; t++) sw += rp[t];
           }
           double lg;
           switch (lossId) {
@@ -524,16 +516,16 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         }
       }
     }
-    // atoms of round r + 2; their feature rows -> L2 (128-byte lines; lanes 16..31 take the odd lines)
+    // atoms of round r + 2; their feature rows -> L2 (128-byte lines, four lanes per atom)
     const int atom2 = load_atom(e2);
     if (MODE == 0) {
       __syncthreads();
       load_features(atom1);                              // next round's rows: in flight during the gradient sweep
       // ---- weight gradients of the round: K = atoms of all tiles of the round ----
-      for (int w2 = 0; w2 < nIn; w2++) {
+      for (int w2 = 0; w2 < nTl; w2++) {
         const double *tb = tiles0 + (size_t)w2 * rows * TS + g * TS + c;
 #pragma unroll
-        for (int kt = 0; kt < TA / 4; kt++) {
+        for (int kt = 0; kt < TW / 4; kt++) {
           double a = 0.0;
 #pragma unroll
           for (int s = 0; s < NSLOT; s++)
@@ -547,7 +539,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           const double *dr = tiles0 + (size_t)w2 * rows * TS + bRow * TS;
           double sb = 0.0;
 #pragma unroll
-          for (int t = 0; t < TA; t++) sb += dr[t];
+          for (int t = 0; t < TW; t++) sb += dr[t];
           bacc += sb;
         }
       }
@@ -555,10 +547,10 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
     }
     if (MODE == 2 && warp >= nIn) load_features(atom1);   // idle in this round (short last round of a species)
     {
-      const int pa = __shfl_sync(0xffffffffu, atom2, lane & 15);
+      const int pa = __shfl_sync(0xffffffffu, atom2, lane & 7);
       if (pa >= 0) {
         const char *row = (const char *)(feat + (size_t)nFeat * pa);
-        for (int b = (lane >> 4) * 128; b < d0 * 8; b += 256)
+        for (int b = (lane >> 3) * 128; b < d0 * 8; b += 512)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
       }
     }
