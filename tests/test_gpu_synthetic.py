@@ -78,7 +78,7 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
     raw = net.predict_batch(0)
     raw_o = orc.predict(zref, ds.globalsp, dims, act, wb, nthreads=nt)
     assert np.allclose(raw, raw_o, rtol=RTOL, atol=ATOL), _md(raw, raw_o)
-    dd, lossv = net.update_gradients(0, loss)
+    dd, lossv, gpred = net.update_gradients(0, loss, want_global=True)
     dd_o, raw_o2 = orc.grad(ds.offsets, zref, ds.globalsp, dims, act, wb, loss, ds.weights, ds.atomic_weights,
                             ds.gtargets, ds.atargets, nthreads=nt)
     assert np.allclose(dd, dd_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(dd_o).max())), _md(dd, dd_o)
@@ -86,6 +86,10 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
                       ds.atomic_weights, ds.weights)
     assert abs(lossv - loss_o) <= ATOL + RTOL * abs(loss_o), (lossv, loss_o)
     assert abs(net.loss(0, loss) - loss_o) <= ATOL + RTOL * abs(loss_o)
+    nG = ds.n_global_targets
+    if nG:   # globalPredictions of updateGradients (fnetout.F90:116-117): per-structure sums of the atomic outputs
+        g_o = np.add.reduceat(raw_o2[:, :nG], ds.offsets[:-1].astype(int), axis=0)
+        assert np.allclose(gpred, g_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(g_o).max())), _md(gpred, g_o)
     if forces:
         f = net.forces(0)
         f_o = orc.forces(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, zref, ds.globalsp, dims, act,
