@@ -243,6 +243,17 @@ FNET_HD double fnet_log_tab(double x, const double *__restrict__ tab) {
   return (hi < 0x00100000) ? -INFINITY : res;
 }
 
+// forward declaration (defined below)
+FNET_HD double fnet_rcp(double d);
+// tanh through the table-driven exp (tab: the 64-entry exp table); same structure and error as fnet_tanh
+FNET_HD double fnet_tanh_tab(double x, const double *__restrict__ tab) {
+  const double e2 = fnet_exp_tab(fmin(x + x, 700.0), tab);
+  const double big = 1.0 - 2.0 * fnet_rcp(e2 + 1.0);
+  const double x2 = x * x;
+  const double small = fma(x * x2, fma(x2, 0.13333333333333333, -0.33333333333333331), x);
+  return (fabs(x) < 0.001953125) ? small : big;
+}
+
 // 1/d for d >= 1 (no zero / inf / denormal handling): hardware seed + two Newton steps + a
 // residual correction; within 1 ulp.
 FNET_HD double fnet_rcp(double d) {

@@ -84,7 +84,7 @@ __host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
 
 __host__ inline size_t bpnn_mma_smem_bytes(const NetTables &net, int mode) {
   const MmaLayout m = mma_layout(net);
-  return ((size_t)m.wTotal + (size_t)FNET_MMA_TILES * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
+  return ((size_t)m.wTotal + FNET_EXP_TAB_N + (size_t)FNET_MMA_TILES * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
 }
 // limits of this path (else mlp.cuh): bias accumulators are one per thread, gradient tiles
 // <= MAXSLOTS per warp, everything in 220 KB of shared memory
@@ -122,7 +122,8 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
 // ONE copy of the activation code in the kernel (the unrolled fragment epilogue would inline it 16
 // times per call site) and an even split of the dout*16 elements over the lanes
 template <bool DERIV>
-__device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane) {
+__device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane,
+                                          const double *__restrict__ etab) {
   // two elements per lane and iteration: independent dependency chains (the FP64 exp / reciprocal
   // sequences are latency-bound); the warp's 8 atoms are columns 0..7 of `out`
   const int n = dout * FNET_MMA_TA;
@@ -138,7 +139,7 @@ __device__ __noinline__ void mma_activate(int actId, int dout, double *__restric
     }
     if (actId == FNETGPU_ACT_TANH) {
 #pragma unroll
-      for (int q = 0; q < 2; q++) v[q] = fnet_tanh(x[q]);
+      for (int q = 0; q < 2; q++) v[q] = fnet_tanh_tab(x[q], etab);
     } else if (actId == FNETGPU_ACT_SIGMOID) {
 #pragma unroll
       for (int q = 0; q < 2; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
@@ -170,7 +171,8 @@ __device__ __noinline__ void mma_activate(int actId, int dout, double *__restric
 template <bool DERIV>
 __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const double *__restrict__ W, int wS,
                                             const double *__restrict__ bias, const double *__restrict__ in,
-                                            double *__restrict__ out, double *__restrict__ dact, int lane) {
+                                            double *__restrict__ out, double *__restrict__ dact, int lane,
+                                            const double *__restrict__ etab) {
   const int g = lane >> 2, c = lane & 3;
   const int KT = fnet_ru4(din) >> 2, NT = fnet_ru8(dout) >> 3;
   for (int nt0 = 0; nt0 < NT; nt0 += 4) {
@@ -201,7 +203,7 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
   }
   if (actId != FNETGPU_ACT_LINEAR || DERIV) {
     __syncwarp();
-    mma_activate<DERIV>(actId, dout, out, dact, lane);
+    mma_activate<DERIV>(actId, dout, out, dact, lane, etab);
   }
 }
 
@@ -267,7 +269,9 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   const MmaLayout m = mma_layout(net);
   const int rows = (MODE == 2) ? m.rowsA : m.rows;
   double *wsm = (double *)smem_raw;
-  double *tiles0 = wsm + m.wTotal;
+  double *etab = wsm + m.wTotal;                  // 2^(j/64) table of the transfer functions (fmath.cuh)
+  double *tiles0 = etab + FNET_EXP_TAB_N;
+  for (int e = threadIdx.x; e < FNET_EXP_TAB_N; e += blockDim.x) etab[e] = fnet_exp_tab_d[e];
   double *T = tiles0 + (size_t)(warp >> 1) * rows * TS + TA * (warp & 1);   // this warp's 8 columns of its tile
   for (int e = threadIdx.x; e < FNET_MMA_TILES * rows * TS; e += blockDim.x) tiles0[e] = 0.0;   // padding rows stay zero from here on
   __syncthreads();
@@ -431,10 +435,10 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         const double *in = T + (MODE == 2 ? m.aOffF[l - 1] : m.aOff[l - 1]) * TS;
         double *out = T + (MODE == 2 ? m.aOffF[l] : m.aOff[l]) * TS;
         if (MODE == 2 || last)
-          mma_forward<false>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out, nullptr, lane);
+          mma_forward<false>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out, nullptr, lane, etab);
         else
           mma_forward<true>(net.dims[l - 1], net.dims[l], actId, wsm + m.wOff[l - 1], m.wS[l - 1], wsm + m.bOff[l], in, out,
-                            T + m.dOff[l] * TS, lane);
+                            T + m.dOff[l] * TS, lane, etab);
         __syncwarp();
       }
       if (MODE == 2) {

@@ -47,8 +47,10 @@ enum { FNETGPU_G1 = 1, FNETGPU_G2 = 2, FNETGPU_G3 = 3, FNETGPU_G4 = 4, FNETGPU_G
 
 /* ---- lifecycle: replaces TEnv_init / destructGlobalEnv (lib_dftbp/globalenv.F90:88-172) ---- */
 /* device < 0: use $LOCAL_RANK if set, else device 0.  precision: 64 or 32 (compute/storage
- * type of features and activations; parity guarantees are stated for 64).  deterministic != 0:
- * fixed-order reductions everywhere (force scatter uses per-atom ordered accumulation). */
+ * type of features and activations; parity guarantees are stated for 64).  deterministic is
+ * accepted for the reference's sake: features, predictions, the training gradient and the loss
+ * are always reduced in a fixed order (bit-reproducible run to run); only the force scatter uses
+ * FP64 atomics, i.e. forces are reproducible to the last bits, not bit for bit. */
 int fnetgpu_init(fnetgpu_ctx **ctx, int device, int precision, int deterministic);
 int fnetgpu_finalize(fnetgpu_ctx *ctx);
 const char *fnetgpu_last_error(const fnetgpu_ctx *ctx);

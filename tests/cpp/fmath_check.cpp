@@ -80,6 +80,16 @@ int main() {
     if (err > mlt) mlt = err;
   }
   if (fnet_log_tab(0.0, tab) != -INFINITY || fnet_log_tab(1.0, tab) != 0.0) { printf("log_tab edge cases failed\n"); return 1; }
-  printf("FMATH_OK %.3e %.3e %.3e tab: %.3e %.3f\n", me, ml, mt, met, mlt);
-  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13 && met < 1e-14 && mlt < 1.0) ? 0 : 2;
+  double mtt = 0.0;
+  for (int i = 0; i < 2000000; i++) {
+    double u = urand(seed);
+    double x = (i % 3 == 0) ? 40.0 * (u - 0.5) : (i % 3 == 1 ? 2.0 * (u - 0.5) : 0.01 * (u - 0.5));
+    if (i % 1000 == 7) x = 800.0 * (u - 0.5);
+    double a = fnet_tanh_tab(x, tab), b = tanh(x);
+    double re = (b == 0.0) ? fabs(a) : fabs(a - b) / fabs(b);
+    if (re > mtt) mtt = re;
+  }
+  if (fnet_tanh_tab(0.0, tab) != 0.0 || fnet_tanh_tab(1e3, tab) != 1.0 || fnet_tanh_tab(-1e3, tab) != -1.0) { printf("tanh_tab edge cases failed\n"); return 1; }
+  printf("FMATH_OK %.3e %.3e %.3e tab: %.3e %.3f %.3e\n", me, ml, mt, met, mlt, mtt);
+  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13 && met < 1e-14 && mlt < 1.0 && mtt < 5e-13) ? 0 : 2;
 }
