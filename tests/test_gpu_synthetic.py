@@ -145,6 +145,25 @@ def test_fused_structure_sums_ragged_single_species(fb, orc, mlp, loss):
     _full_check(fb, orc, ds, funcs, [len(funcs), 6, 5, 2], loss=loss, forces=False, mlp=mlp, expect_mlp=1)
 
 
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("nrad,nang", [(24, 4), (3, 40), (17, 18), (32, 34), (9, 2)])
+def test_auto_scheme_sizes(fb, orc, nrad, nang, path):
+    """auto-scheme sizes that exercise every shape of the kernels' function grouping: 1 / 2 / 4 radial
+    chunks of 8 (shared-memory reduction with 8 / 16 / 32 rows), 1 / 2 / 4 ladder slots per angular
+    pass, continuing ladders (more than 8 functions per lambda) and partially filled ladders"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=2, seed=13)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, nrad, nang)
+    ctx = fb.Context(acsf_path=path)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False)
+    acsf.calculate(0)
+    vals = acsf.features(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
+    assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
+    ctx.close()
+
+
 @pytest.mark.parametrize("dims,expect", [([9, 1], 1), ([9, 3, 1], 1), ([9, 17, 9, 33, 2, 1], 1), ([9, 40, 40, 40, 1], 1),
                                          ([9, 100, 100, 1], 0), ([9, 70, 60, 1], 0)])
 def test_subnetwork_shapes(fb, orc, dims, expect):
