@@ -442,12 +442,13 @@ __device__ __forceinline__ void angular_pass(int i, int n, const AcsfTables &tab
   const int n1 = l1.n0 + l1.n1, n2 = l2.n0 + l2.n1;
   const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
   __syncwarp();
-  for (int t = lane; t < n; t += 32) {   // per-neighbour radial factor fc * exp(-eta r^2)
-    const double rr = w.r[t];
-    const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
-    w.qv[t] = qj;
-    w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * fnet_exp_tab(-eta * rr * rr, ftab);
-  }
+  if (!P->keepFc)                        // species-resolved passes share (rc, eta): computed by the first of them
+    for (int t = lane; t < n; t += 32) {   // per-neighbour radial factor fc * exp(-eta r^2)
+      const double rr = w.r[t];
+      const double qj = atomId > 0 ? ext[(size_t)nExt * w.idx[t] + atomId - 1] : 1.0;
+      w.qv[t] = qj;
+      w.fcE[t] = (rr > rc) ? 0.0 : cutoff_fn(rr, qi * qj, invrc) * fnet_exp_tab(-eta * rr * rr, ftab);
+    }
   __syncwarp();
   double lam[NS], xi0[NS], dxi[NS];
   bool on[NS], cont[NS];

@@ -415,6 +415,11 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   }
   {   // straight-line variant of the pair loop (acsf.cuh angular_pass<NS, true>)
     const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
+    for (size_t k = 0; k < ctx->h_apasses.size(); k++) {
+      AngularPass &Q = ctx->h_apasses[k];
+      Q.keepFc = (k > 0 && Q.rc == ctx->h_apasses[k - 1].rc && Q.eta == ctx->h_apasses[k - 1].eta &&
+                  Q.atomId == ctx->h_apasses[k - 1].atomId) ? 1 : 0;
+    }
     for (AngularPass &P : ctx->h_apasses) {
       bool fast = P.type == FNETGPU_G5 && P.nSlots == ns;
       for (int q = 0; q < P.nSlots && fast; q++) fast = P.slot[q].cont == 0 && P.slot[q].xi0 == 1.0;

@@ -73,7 +73,7 @@ struct AngularPass {
   int atomId;
   int nSlots;
   int fast;          // G5, nSlots == the kernel's NS, every slot a fresh ladder starting at xi = 1 (the auto scheme): straight-line pair loop
-  int pad_;
+  int keepFc;        // same (rc, eta, atomId) as the previous pass: its per-neighbour factors fc * exp(-eta r^2) are still valid
   double rc, eta;
   LadderSlot slot[FNET_SLOTS];
 };
