@@ -55,6 +55,66 @@ def workload(name, n_struct, seed_shift=0):
     return ds, funcs, dims, wb, label
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons DURING the timed region through NVML in this process (a sample every
+    ~4 ms; `nvidia-smi -lms` forks a heavier query that can land on a 2 ms step and lengthen it).
+    Same quantities as the recipe's clocks line in B200_PROFILING.md; falls back to ClockSampler."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index):
+        self.ok = False
+        self.samples = []
+        self.run = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.h = h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        self.run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.run = False
+        self.t.join(timeout=1.0)
+        sm = [a for a, _ in self.samples]
+        reasons = set()
+        for _, rs in self.samples:
+            for bit, nm in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": sorted(reasons), "how": "NVML in-process, one sample per ~4 ms inside the timed region"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -255,7 +315,9 @@ def main():
         for _ in range(args.warmup):
             step_resident()
         # ---------------- timed region: device-resident inputs ----------------
-        sampler = ClockSampler(local)
+        sampler = NvmlSampler(local) if rank == 0 else None
+        if rank == 0 and not sampler.ok:
+            sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

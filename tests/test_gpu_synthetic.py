@@ -145,6 +145,19 @@ def test_fused_structure_sums_ragged_single_species(fb, orc, mlp, loss):
     _full_check(fb, orc, ds, funcs, [len(funcs), 6, 5, 2], loss=loss, forces=False, mlp=mlp, expect_mlp=1)
 
 
+def test_large_and_small_structures_in_one_batch(fb, orc):
+    """a 300-atom cell next to small ones: the batch exceeds the whole-structure path's 256-atom limit, so
+    the automatic choice must be the cell list for the whole slot; values, gradient and forces vs oracle"""
+    from fortnet_b200 import synthetic
+    big = synthetic.dense_liquid(n_atoms=300, density_aa3=0.05, seed=5, n_struct=1)      # L = 18.2 A >= 2 rc
+    small = synthetic.si_bulk(n_struct=2, seed=6)
+    ds = fb.Dataset.build([300, 64, 64], np.concatenate([big.coords, small.coords]), np.ones(3, np.int32),
+                          np.concatenate([big.latvecs, small.latvecs]), np.full(428, 14, np.int32),
+                          gtargets=np.array([[1.0], [2.0], [3.0]]), atomic_numbers=[14])
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 6, 6)
+    _full_check(fb, orc, ds, funcs, [12, 6, 1], expect_path=CELLS)
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("nrad,nang", [(24, 4), (3, 40), (17, 18), (32, 34), (9, 2)])
 def test_auto_scheme_sizes(fb, orc, nrad, nang, path):
