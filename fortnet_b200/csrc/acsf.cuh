@@ -319,7 +319,8 @@ __device__ __forceinline__ double reduce_transpose(double (&v)[M], int lane, int
 // pass -- about 40 % of the butterfly's instruction count (no 64-bit selects, two shuffles).
 template <int M>
 __device__ __forceinline__ double reduce_smem(const double (&v)[M], int lane, int stride, double *__restrict__ red) {
-  const int grp = lane % stride, sub = lane / stride;
+  const int lgs = __ffs(stride) - 1;            // stride is a power of two: shifts instead of integer divisions
+  const int grp = lane & (stride - 1), sub = lane >> lgs;
   const int rows = stride * M;                  // <= 32 here (M = 8: stride <= 4; M = 8 NS: stride = 1)
   __syncwarp();
 #pragma unroll
@@ -362,8 +363,9 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
     const double qi = atomId > 0 ? ext[(size_t)nExt * i + atomId - 1] : 1.0;
     const double invrc = 1.0 / rc;
     if (G->ladder) {
-      const int per = 32 / nch;
-      const int mychunk = lane % nch, sub = lane / nch;
+      const int lgn = __ffs(nch) - 1;           // nch = 1, 2 or 4
+      const int per = 32 >> lgn;
+      const int mychunk = lane & (nch - 1), sub = lane >> lgn;
       const int fbase = fBeg + mychunk * FNET_RCHUNK;
       const int fcnt = min(max(fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
       double acc[FNET_RCHUNK];
@@ -401,7 +403,7 @@ __device__ __forceinline__ void radial_groups(int i, int n, const AcsfTables &ta
         }
       // sum over the sub-lanes: lane ends with function (lane / nch) % 8 of chunk lane % nch
       const double v = reduce_smem<FNET_RCHUNK>(acc, lane, nch, w.red);
-      const int f = (lane / nch) % FNET_RCHUNK;
+      const int f = (lane >> lgn) % FNET_RCHUNK;
       if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[fbase + f]] = v;
     } else {
       int nfP2 = 1;
