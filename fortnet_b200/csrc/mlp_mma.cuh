@@ -166,6 +166,29 @@ __device__ __noinline__ void mma_activate(int actId, int dout, double *__restric
   }
 }
 
+// K loop of one group of NC <= 4 output tiles: NC is a template parameter (selected by a warp-uniform
+// switch) so that the loop body carries no per-tile guards -- guarded mma.sync costs predicated-off
+// issue slots and WARPSYNC / NOP padding (a 1-wide output layer would issue 4x its DMMAs)
+template <int NC>
+__device__ __forceinline__ void mma_k_loop(int KT, const double *__restrict__ ip, const double *__restrict__ wp,
+                                           size_t aStep, size_t bStep, size_t bTile, double (&acc)[4][2]) {
+#pragma unroll 2
+  for (int kt = 0; kt < KT; kt++) {
+    const double a0 = ip[kt * aStep];
+#pragma unroll
+    for (int nc = 0; nc < NC; nc++) dmma(acc[nc], a0, wp[nc * bTile + kt * bStep]);
+  }
+}
+__device__ __forceinline__ void mma_k_dispatch(int ncnt, int KT, const double *__restrict__ ip, const double *__restrict__ wp,
+                                               size_t aStep, size_t bStep, size_t bTile, double (&acc)[4][2]) {
+  switch (ncnt) {
+    case 1: mma_k_loop<1>(KT, ip, wp, aStep, bStep, bTile, acc); break;
+    case 2: mma_k_loop<2>(KT, ip, wp, aStep, bStep, bTile, acc); break;
+    case 3: mma_k_loop<3>(KT, ip, wp, aStep, bStep, bTile, acc); break;
+    default: mma_k_loop<4>(KT, ip, wp, aStep, bStep, bTile, acc); break;
+  }
+}
+
 // forward layer of one warp tile: out[o][t] = f(sum_i W[o][i] in[i][t] + b[o]); DERIV also
 // stores f'(z) (later overwritten by the delta)
 template <bool DERIV>
@@ -184,13 +207,7 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
     }
     const double *ip = in + c * FNET_MMA_TS + g;
     const double *wp = W + (size_t)(8 * nt0 + g) * wS + c;
-#pragma unroll 2
-    for (int kt = 0; kt < KT; kt++) {
-      const double a0 = ip[(4 * kt) * FNET_MMA_TS];
-#pragma unroll
-      for (int nc = 0; nc < 4; nc++)
-        if (nt0 + nc < NT) dmma(acc[nc], a0, wp[(size_t)(8 * nc) * wS + 4 * kt]);
-    }
+    mma_k_dispatch(min(4, NT - nt0), KT, ip, wp, 4 * FNET_MMA_TS, 4, (size_t)8 * wS, acc);
 #pragma unroll
     for (int nc = 0; nc < 4; nc++)
       if (nt0 + nc < NT) {
@@ -219,13 +236,7 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
     for (int nc = 0; nc < 4; nc++) { acc[nc][0] = 0.0; acc[nc][1] = 0.0; }
     const double *ip = dn + c * FNET_MMA_TS + g;
     const double *wp = W + (size_t)c * wS + 8 * nt0 + g;
-#pragma unroll 2
-    for (int kt = 0; kt < KT; kt++) {
-      const double a0 = ip[(4 * kt) * FNET_MMA_TS];
-#pragma unroll
-      for (int nc = 0; nc < 4; nc++)
-        if (nt0 + nc < NT) dmma(acc[nc], a0, wp[(size_t)(4 * kt) * wS + 8 * nc]);
-    }
+    mma_k_dispatch(min(4, NT - nt0), KT, ip, wp, 4 * FNET_MMA_TS, (size_t)4 * wS, 8, acc);
 #pragma unroll
     for (int nc = 0; nc < 4; nc++)
       if (nt0 + nc < NT) {
