@@ -252,6 +252,35 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
   }
 }
 
+// gradient sweep over one tile for the first NM of the warp's output tiles (NM by a warp-uniform
+// switch: no per-slot guards around mma.sync)
+template <int NM, int NSLOT>
+__device__ __forceinline__ void mma_wgrad_tile(const double *__restrict__ tb, const int (&aRow)[NSLOT], const int (&dRow)[NSLOT],
+                                               const bool (&newA)[NSLOT], double (&acc)[NSLOT][2]) {
+#pragma unroll
+  for (int kt = 0; kt < FNET_MMA_TW / 4; kt++) {
+    double a = 0.0;
+#pragma unroll
+    for (int s = 0; s < NM; s++) {
+      if (newA[s]) a = tb[aRow[s] * FNET_MMA_TS + 4 * kt];
+      dmma(acc[s], a, tb[dRow[s] * FNET_MMA_TS + 4 * kt]);
+    }
+  }
+}
+template <int NM, int NSLOT>
+struct MmaWgradDispatch {
+  static __device__ __forceinline__ void run(int nMine, const double *__restrict__ tb, const int (&aRow)[NSLOT],
+                                             const int (&dRow)[NSLOT], const bool (&newA)[NSLOT], double (&acc)[NSLOT][2]) {
+    if (nMine == NM) mma_wgrad_tile<NM, NSLOT>(tb, aRow, dRow, newA, acc);
+    else MmaWgradDispatch<NM - 1, NSLOT>::run(nMine, tb, aRow, dRow, newA, acc);
+  }
+};
+template <int NSLOT>
+struct MmaWgradDispatch<0, NSLOT> {
+  static __device__ __forceinline__ void run(int, const double *, const int (&)[NSLOT], const int (&)[NSLOT],
+                                             const bool (&)[NSLOT], double (&)[NSLOT][2]) {}
+};
+
 // ------------------------------------------------------------------------------------------
 // MODE 0: training gradient -> partials[cta][nSpecies*nTot]; MODE 2: forward only -> raw[atom][k].
 // `tiles` holds the ROUNDS: (start, count <= 64, species) triples of the species-sorted atom
@@ -539,17 +568,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       // ---- weight gradients of the round: K = atoms of all tiles of the round ----
       for (int w2 = 0; w2 < nTl; w2++) {
         const double *tb = tiles0 + (size_t)w2 * rows * TS + g * TS + c;
-#pragma unroll
-        for (int kt = 0; kt < TW / 4; kt++) {
-          double a = 0.0;
-#pragma unroll
-          for (int s = 0; s < NSLOT; s++)
-            if (s < nMine) {
-              if (newA[s]) a = tb[aRow[s] * TS + 4 * kt];
-              const double b = tb[dRow[s] * TS + 4 * kt];
-              dmma(acc[s], a, b);
-            }
-        }
+        MmaWgradDispatch<NSLOT, NSLOT>::run(nMine, tb, aRow, dRow, newA, acc);
         if (bRow >= 0) {
           const double *dr = tiles0 + (size_t)w2 * rows * TS + bRow * TS;
           double sb = 0.0;
