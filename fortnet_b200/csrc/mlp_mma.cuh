@@ -492,26 +492,39 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       // ---- per-structure sums across the warps of the round (fixed order), loss gradient, loss terms ----
       if (warp < nIn && lane < TA) T[m.sOff * TS + lane] = lgAw;       // atomic weights of the tile (0 for padding)
       __syncthreads();
-      if (warp < nIn && lane < TA && myAtom >= 0) {
-        const int b = lgB - e0[0], e = lgE - e0[0];                    // the structure's atoms, round-local
-        const bool lead = (TA * warp + lane == b);                     // first atom of the structure: writes E_s and the loss terms
+      if (warp < nIn) {
+        const bool mine = lane < TA && myAtom >= 0;
+        // usual case: all atoms of this warp belong to one structure -> the 32 lanes share its sum
+        const int bU = __shfl_sync(0xffffffffu, lgB, 0), eU = __shfl_sync(0xffffffffu, lgE, 0);
+        const bool uni = count > 0 && __all_sync(0xffffffffu, !mine || (lgB == bU && lgE == eU));
+        const int b = (uni ? bU : lgB) - e0[0], e = (uni ? eU : lgE) - e0[0];   // the structure's atoms, round-local
+        const bool lead = mine && (TA * warp + lane == b);             // first atom of the structure: writes E_s and the loss terms
         double ss = 0.0;
         double *dL = T + m.dOff[L - 1] * TS;
         for (int k = 0; k < nG; k++) {
+          const size_t rowk = (size_t)(m.aOff[L - 1] + k) * TS;
           double ek = 0.0;
-          for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {          // tile by tile, in atom order
-            const double *rp = tiles0 + (size_t)w2 * rows * TS + (m.aOff[L - 1] + k) * TS;
-            const int t1 = min(e - TW * w2, TW);
-            for (int t = max(b - TW * w2, 0); t < t1; t++) ek += rp[t];
+          if (uni) {
+            for (int i = b + lane; i < e; i += 32) ek += tiles0[(size_t)(i >> 4) * rows * TS + rowk + (i & 15)];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ek += __shfl_xor_sync(0xffffffffu, ek, o);
+          } else if (mine) {
+            for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {          // tile by tile, in atom order
+              const double *rp = tiles0 + (size_t)w2 * rows * TS + rowk;
+              const int t1 = min(e - TW * w2, TW);
+              for (int t = max(b - TW * w2, 0); t < t1; t++) ek += rp[t];
+            }
           }
-          const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
-          dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
-          if (lead) {
-            Es[(size_t)nG * lgStruct + k] = ek;
-            switch (lossId) {
-              case FNETGPU_LOSS_MAE: ss += fabs(tv - ek); break;
-              case FNETGPU_LOSS_MAPE: ss += fabs((tv - ek) / tv); break;
-              default: ss += (tv - ek) * (tv - ek);
+          if (mine) {
+            const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
+            dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
+            if (lead) {
+              Es[(size_t)nG * lgStruct + k] = ek;
+              switch (lossId) {
+                case FNETGPU_LOSS_MAE: ss += fabs(tv - ek); break;
+                case FNETGPU_LOSS_MAPE: ss += fabs((tv - ek) / tv); break;
+                default: ss += (tv - ek) * (tv - ek);
+              }
             }
           }
         }
@@ -531,9 +544,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           lossPart[2 * (size_t)lgStruct] = lgW * sw * lg;
           lossPart[2 * (size_t)lgStruct + 1] = lgW * sw;
         }
-      } else if (warp < nIn && lane < TA) {
-        double *dL = T + m.dOff[L - 1] * TS;
-        for (int k = 0; k < net.nOut; k++) dL[k * TS + lane] = 0.0;    // padding atoms
+        if (!mine && lane < TA)
+          for (int k = 0; k < net.nOut; k++) dL[k * TS + lane] = 0.0;  // padding atoms
       }
     }
     if (warp < nIn) {
