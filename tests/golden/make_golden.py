@@ -271,6 +271,40 @@ def main():
     with open(os.path.join(HERE, "index.json"), "w") as fh:
         json.dump(index, fh, indent=1)
     print("datasets:", len(os.listdir(os.path.join(HERE, "datasets"))), "cases:", len(index))
+    # ---- fresh-training cases (RANLUX initialisation, no stored input netstat): the golden OUTPUT
+    #      netstat + the HSD settings; replayed by tests/test_oracle_fresh_training.py with tests/ranlux.py
+    os.makedirs(os.path.join(HERE, "fresh"), exist_ok=True)
+    fresh = []
+    for case in cases:
+        cdir = os.path.join(REF, case)
+        hsdp = os.path.join(cdir, "fortnet_in.hsd")
+        if not os.path.isfile(hsdp) or not os.path.isfile(os.path.join(cdir, "_fortnet.hdf5")):
+            continue
+        hsd = parse_hsd(open(hsdp).read())
+        opt = hsd.get("options", {})
+        mode = str(opt.get("mode", "train")).lower()
+        if mode != "train" or yes(opt.get("readnetstats", "no")) or "driver" in hsd:
+            continue
+        tr = hsd.get("training")
+        if not isinstance(tr, dict):
+            continue
+        data = hsd.get("data", {})
+        meta = dict(case=case, mode=mode, fresh=True, seed=int(opt.get("randomseed", 0)),
+                    dataset=os.path.basename(str(data.get("dataset", "")))[:-5])
+        meta["training"] = {k: v for k, v in tr.items() if not isinstance(v, dict)}
+        meta["training"]["type"] = tr.get("_type")
+        if isinstance(tr.get("regularization"), dict):
+            meta["training"]["regularization"] = tr["regularization"]
+        arrays, nmeta = convert_netstat(os.path.join(cdir, "_fortnet.hdf5"), "ref_")
+        meta["netstat"] = nmeta
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        fname = case.replace("/", "__") + ".npz"
+        np.savez_compressed(os.path.join(HERE, "fresh", fname), **arrays)
+        fresh.append(dict(case=case, file=fname, dataset=meta["dataset"], training=meta["training"]["type"],
+                          niterations=int(meta["training"].get("niterations", 0)), seed=meta["seed"]))
+    with open(os.path.join(HERE, "index_fresh.json"), "w") as fh:
+        json.dump(fresh, fh, indent=1)
+    print("fresh-training cases:", len(fresh))
 
 
 if __name__ == "__main__":

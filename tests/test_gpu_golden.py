@@ -107,3 +107,40 @@ def test_features_and_zscore_statistics(fb, entry, path):
         zo = orc.zscore_apply(ref, *orc.zscore_stats(ds.offsets, ref, ds.weights))
         assert np.allclose(z, zo, rtol=1e-9, atol=1e-10), gio.maxdiff(z, zo)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# fresh-training goldens (RANLUX initialisation restated in tests/ranlux.py)
+# ---------------------------------------------------------------------------------------------
+import json as _json
+import os as _os
+
+with open(_os.path.join(gio.GOLD, "index_fresh.json")) as _fh:
+    _FRESH = [e for e in _json.load(_fh) if e["training"] == "sd" and e["niterations"] == 1]
+
+
+@pytest.mark.parametrize("entry", _FRESH, ids=[e["case"] for e in _FRESH])
+def test_fresh_sd_training_step(fb, entry):
+    """seed -> theta0 (harness) -> ACSF + statistics + gradient on the GPU -> SD step -> golden _fortnet.hdf5"""
+    import ranlux
+    from test_oracle_fresh_training import FreshCase
+    case = FreshCase(entry)
+    ds = case.dataset
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=case.zmeans is not None, ext_indices=case.ext_indices)
+    acsf.calculate(0)                                   # statistics from the training set, as the reference does
+    if case.zmeans is not None:
+        assert gio.allclose(acsf.zprec[0], case.zmeans) and gio.allclose(acsf.zprec[1], case.zsigmas)
+    nsp = len(case.atomic_numbers)
+    net = fb.Bpnn(ctx, case.dims, nsp, case.activation)
+    wb0 = ranlux.initial_parameters(case.seed, case.dims, nsp)
+    net.set_params(wb0)
+    dd, _loss = net.update_gradients(0, loss=case.loss_name())
+    wb1, _ = case.sd_update(wb0, dd)
+    ref = case.wb("ref_")
+    nW = case.n_weights()
+    keep = np.ones(wb1.shape[1], bool)
+    keep[nW - int(case.dims[-1]):nW] = False           # the unused ww(d_L, 1) is not in the netstat file
+    assert gio.allclose(wb1[:, keep], ref[:, keep]), gio.maxdiff(wb1[:, keep], ref[:, keep])
+    ctx.close()
