@@ -91,6 +91,94 @@ class Case:
             new[sp] = wb[sp] + (step if mx <= maxd else (maxd / mx) * step)
         return new, float(np.sqrt(np.sum(dd ** 2)))
 
+    # --- first FIRE step (lib_dftbp/fire.F90:137-185; initprogram.F90:1175-1182) -----------------
+    def fire_update(self, wb, dd):
+        """One iteration from rest: v = 0 -> the velocity mixing is a no-op, v = -dt g, x = x0 + v dt with
+        dt = dt_init = 0.1 * MaxDisplacement; one optimiser per species (bpnn.F90:761-774)."""
+        tr = self.training
+        nW = self.n_weights()
+        dd = dd.copy()
+        regu = tr.get("regularization")
+        if regu:
+            kind = regu.get("_type")
+            lam = float(regu.get("strength", 0.0))
+            alpha = {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
+            w = wb[:, :nW]
+            dd[:, :nW] += lam / nW * ((1.0 - alpha) * w + alpha * np.sign(w))
+        dd /= float(np.sum(self.dataset.weights))
+        dt = 0.1 * float(tr["maxdisplacement"])
+        thr = float(tr.get("threshold", 0.0))
+        new = wb.copy()
+        for sp in range(wb.shape[0]):
+            if np.max(np.abs(dd[sp])) < thr:
+                continue
+            new[sp] = wb[sp] + (-dt * dd[sp]) * dt
+        return new
+
+    # --- first conjugate-gradient step (lib_dftbp/conjgrad.F90, linemin.F90 reset + state 1) ----------
+    def cg_update(self, wb, dd):
+        """First iteration: search direction d0 = -g/|g|, trial step 5 |g| limited to
+        MaxDisplacement / max|d0| (linemin.F90 reset / next_local state st_1), x1 = x0 + step d0."""
+        tr = self.training
+        nW = self.n_weights()
+        dd = dd.copy()
+        regu = tr.get("regularization")
+        if regu:
+            kind = regu.get("_type")
+            lam = float(regu.get("strength", 0.0))
+            alpha = {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
+            w = wb[:, :nW]
+            dd[:, :nW] += lam / nW * ((1.0 - alpha) * w + alpha * np.sign(w))
+        dd /= float(np.sum(self.dataset.weights))
+        maxd = float(tr["maxdisplacement"])
+        thr = float(tr.get("threshold", 0.0))
+        new = wb.copy()
+        for sp in range(wb.shape[0]):
+            g = dd[sp]
+            if np.max(np.abs(g)) < thr:
+                continue
+            gn = np.sqrt(np.sum(g ** 2))
+            d0 = -g / gn
+            first = 5.0 * gn
+            max_x = maxd / np.max(np.abs(d0))
+            x = first if abs(first) <= max_x else max_x
+            new[sp] = wb[sp] + x * d0
+        return new
+
+    # --- first L-BFGS step (lib_dftbp/lbfgs.F90:283-359, 387-403; line minimiser linemin.F90) ----------
+    def lbfgs_update(self, wb, dd):
+        """First iteration: no history -> direction -g; with Linemin = Yes (the default) a trial step of
+        length 1 along -g/|g| capped by MaxDisplacement / max|d0|, else the direction itself rescaled so
+        that its largest component is at most MaxDisplacement."""
+        tr = self.training
+        nW = self.n_weights()
+        dd = dd.copy()
+        regu = tr.get("regularization")
+        if regu:
+            kind = regu.get("_type")
+            lam = float(regu.get("strength", 0.0))
+            alpha = {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
+            w = wb[:, :nW]
+            dd[:, :nW] += lam / nW * ((1.0 - alpha) * w + alpha * np.sign(w))
+        dd /= float(np.sum(self.dataset.weights))
+        maxd = float(tr["maxdisplacement"])
+        thr = float(tr.get("threshold", 0.0))
+        linemin = str(tr.get("linemin", "yes")).strip("'\"").lower() in ("yes", "true", ".true.")
+        new = wb.copy()
+        for sp in range(wb.shape[0]):
+            g = dd[sp]
+            if np.max(np.abs(g)) < thr:
+                continue
+            if linemin:
+                d0 = -g / np.sqrt(np.sum(g ** 2))
+                max_x = maxd / np.max(np.abs(d0))
+                new[sp] = wb[sp] + (1.0 if 1.0 <= max_x else max_x) * d0
+            else:
+                d = -g
+                mx = np.max(np.abs(d))
+                new[sp] = wb[sp] + (d * maxd / mx if (maxd > 0.0 and mx > maxd) else d)
+        return new
+
     def assemble_features(self, acsf_vals):
         """features.F90:200-265: [ACSF ; ext(indices)]"""
         parts = []

@@ -52,7 +52,12 @@ def test_predictions_and_forces(fb, entry, path):
     ctx.close()
 
 
-SD = gio.cases(mode=("train",), training=("sd",))
+SD = gio.cases(mode=("train",), training=("sd", "cg", "lbfgs", "fire"))   # the first iteration of each optimiser (golden_io)
+
+
+def _update(case, kind, wb0, dd):
+    return {"fire": case.fire_update, "cg": case.cg_update, "lbfgs": case.lbfgs_update}.get(
+        kind, lambda w, d: case.sd_update(w, d)[0])(wb0, dd)
 
 
 @pytest.mark.parametrize("mlp", ["auto", "nofuse", "legacy"])   # DMMA kernels (+ fused per-structure sums where they apply) / register-tiled kernels
@@ -65,7 +70,7 @@ def test_sd_training_step(fb, entry, mlp):
     ds = case.dataset
     wb0 = case.wb()
     dd, loss = net.update_gradients(0, loss=case.loss_name())
-    wb1, _ = case.sd_update(wb0, dd)
+    wb1 = _update(case, entry["training"], wb0, dd)
     ref = case.wb("ref_")
     assert gio.allclose(wb1, ref), gio.maxdiff(wb1, ref)
     # loss value and raw gradient against the oracle on the same features
@@ -116,7 +121,7 @@ import json as _json
 import os as _os
 
 with open(_os.path.join(gio.GOLD, "index_fresh.json")) as _fh:
-    _FRESH = [e for e in _json.load(_fh) if e["training"] == "sd" and e["niterations"] == 1]
+    _FRESH = [e for e in _json.load(_fh) if e["niterations"] == 1]
 
 
 @pytest.mark.parametrize("entry", _FRESH, ids=[e["case"] for e in _FRESH])
@@ -137,7 +142,7 @@ def test_fresh_sd_training_step(fb, entry):
     wb0 = ranlux.initial_parameters(case.seed, case.dims, nsp)
     net.set_params(wb0)
     dd, _loss = net.update_gradients(0, loss=case.loss_name())
-    wb1, _ = case.sd_update(wb0, dd)
+    wb1 = _update(case, entry["training"], wb0, dd)
     ref = case.wb("ref_")
     nW = case.n_weights()
     keep = np.ones(wb1.shape[1], bool)

@@ -16,7 +16,7 @@ from oracle import oracle as orc
 
 with open(os.path.join(gio.GOLD, "index_fresh.json")) as _fh:
     FRESH = json.load(_fh)
-SD1 = [e for e in FRESH if e["training"] == "sd" and e["niterations"] == 1]
+SD1 = [e for e in FRESH if e["training"] in ("sd", "fire", "cg", "lbfgs") and e["niterations"] == 1]
 
 
 class FreshCase(gio.Case):
@@ -72,7 +72,8 @@ def test_fresh_sd_training_step(entry):
     wb0 = ranlux.initial_parameters(case.seed, case.dims, nsp)
     dd, _raw = orc.grad(ds.offsets, feats, ds.globalsp, case.dims, case.activation, wb0, case.loss_name(),
                         ds.weights, ds.atomic_weights, ds.gtargets, ds.atargets)
-    wb1, _ = case.sd_update(wb0, dd)
+    wb1 = {"fire": case.fire_update, "cg": case.cg_update, "lbfgs": case.lbfgs_update}.get(
+        entry["training"], lambda w, d: case.sd_update(w, d)[0])(wb0, dd)
     ref = case.wb("ref_")
     # the unused last-layer array ww(d_L, 1) is drawn (and keeps its random values) but is not part of
     # the netstat file: compare everything else

@@ -58,6 +58,27 @@ def test_sd_training_step(entry):
         assert gio.allclose(case.zmeans, case.arr["ref_zmeans"])
 
 
+FIRE = [e for e in gio.cases(mode=("train",), training=("fire", "cg", "lbfgs"))]
+
+
+@pytest.mark.parametrize("entry", FIRE, ids=[e["case"] for e in FIRE])
+def test_fire_cg_lbfgs_training_step(entry):
+    """first FIRE iteration from rest: theta1 = theta0 - dt^2 g, dt = 0.1 MaxDisplacement (fire.F90:137-185);
+    first conjugate-gradient iteration: trial step 5 |g| along -g, capped by MaxDisplacement (conjgrad.F90, linemin.F90);
+    first L-BFGS iteration: unit trial step along -g/|g| (lbfgs.F90:283-359)"""
+    case = gio.Case(entry)
+    if int(case.training.get("niterations", 1)) != 1:
+        pytest.skip("only the first iteration is restated")
+    ds = case.dataset
+    feats = _features(case)
+    wb0 = case.wb()
+    dd, _raw = orc.grad(ds.offsets, feats, ds.globalsp, case.dims, case.activation, wb0,
+                        case.loss_name(), ds.weights, ds.atomic_weights, ds.gtargets, ds.atargets)
+    wb1 = {"fire": case.fire_update, "cg": case.cg_update, "lbfgs": case.lbfgs_update}[entry["training"]](wb0, dd)
+    ref = case.wb("ref_")
+    assert gio.allclose(wb1, ref), gio.maxdiff(wb1, ref)
+
+
 ZS = gio.cases(mode=("train",))
 
 
