@@ -18,6 +18,7 @@ SYMBOLS = [
     "fnetgpu_launch_count", "fnetgpu_profile", "fnetgpu_profile_get", "fnetgpu_kernel_name",
     "fnetgpu_max_neighbors", "fnetgpu_acsf_path_set", "fnetgpu_acsf_path_get",
     "fnetgpu_mlp_path_set", "fnetgpu_mlp_path_get", "fnetgpu_socket_step", "fnetgpu_acsf_update_calculate",
+    "fnetgpu_acsf_kernel_set", "fnetgpu_acsf_kernel_get",
 ]
 
 

@@ -39,7 +39,7 @@ class Context:
     whole-structure / minimum-image neighbour search, else the cell list) or "cells"; mlp "auto"
     (precision 64: DMMA kernels when the network fits) or "legacy" (register-tiled FMA kernels)."""
 
-    def __init__(self, device=-1, precision=64, deterministic=True, acsf_path="auto", mlp="auto"):
+    def __init__(self, device=-1, precision=64, deterministic=True, acsf_path="auto", mlp="auto", acsf_kernel="auto"):
         self._lib = lib()
         h = C.c_void_p()
         rc = self._lib.fnetgpu_init(C.byref(h), C.c_int(device), C.c_int(precision), C.c_int(int(deterministic)))
@@ -51,6 +51,10 @@ class Context:
             raise ValueError("acsf_path must be 'auto' or 'cells'")
         if acsf_path == "cells":
             self._check(self._lib.fnetgpu_acsf_path_set(self._h, C.c_int(1)))
+        if acsf_kernel not in ("auto", "generic"):
+            raise ValueError("acsf_kernel must be 'auto' or 'generic'")
+        if acsf_kernel == "generic":
+            self._check(self._lib.fnetgpu_acsf_kernel_set(self._h, C.c_int(1)))
         if mlp not in ("auto", "legacy", "nofuse"):
             raise ValueError("mlp must be 'auto', 'legacy' or 'nofuse'")
         if mlp != "auto":
@@ -136,6 +140,10 @@ class Context:
     def acsf_path(self, slot):
         """path of the last ACSF launch: 0/1 cell list (direct/staged), 2 whole structure, -1 none"""
         return int(self._lib.fnetgpu_acsf_path_get(self._h, C.c_int(slot)))
+
+    def acsf_kernel(self):
+        """1: the configured ACSF run through k_acsf_lean (automatic-scheme configurations), 0: k_acsf, -1: none"""
+        return int(self._lib.fnetgpu_acsf_kernel_get(self._h))
 
     def max_neighbors(self, slot):
         m, mean = C.c_int(), C.c_double()

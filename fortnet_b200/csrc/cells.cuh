@@ -294,7 +294,8 @@ __device__ __forceinline__ void for_each_candidate_direct(const StructInfo &S, c
 struct __align__(16) StructGeom {
   double lat[9];     // lat[3*k+c]: component c of lattice vector k
   double inv[9];     // fractional s_k = sum_c inv[3*k+c] * d_c
-  int periodic, pad;
+  int periodic;
+  int diag;          // orthorhombic cell along the axes: the minimum image decouples per component
 };
 
 __device__ __forceinline__ int stage_structure(int st, int beg, int nAt, const double *__restrict__ coords,
@@ -331,8 +332,10 @@ __device__ __forceinline__ int stage_structure(int st, int beg, int nAt, const d
         if (!(bn2 * (4.0 * rc * rc) * (1.0 + 1e-9) <= 1.0)) ok = false;
       }
       if (!ok) atomicOr(&flags[4], 1);
+      g->diag = (m[0][1] == 0.0 && m[0][2] == 0.0 && m[1][0] == 0.0 && m[1][2] == 0.0 && m[2][0] == 0.0 && m[2][1] == 0.0) ? 1 : 0;
     } else {
       for (int e = 0; e < 9; e++) { g->lat[e] = 0.0; g->inv[e] = 0.0; }
+      g->diag = 0;
     }
   }
   __syncthreads();
@@ -345,6 +348,7 @@ __device__ __forceinline__ void for_each_candidate_struct(const CRec *__restrict
                                                           Visit visit) {
   const int lane = threadIdx.x & 31;
   const bool per = g->periodic != 0;
+  const bool diag = g->diag != 0;
   for (int base = 0; base < total; base += 32) {
     const int t = base + lane;
     const bool valid = t < total;
@@ -352,8 +356,15 @@ __device__ __forceinline__ void for_each_candidate_struct(const CRec *__restrict
     r.x = me.x; r.y = me.y; r.z = me.z; r.idx = -1; r.zs = 0;
     if (valid) r = cand[t];
     double dx = r.x - me.x, dy = r.y - me.y, dz = r.z - me.z;
-    if (per) {
-      const double magic = 6755399441055744.0;         // 1.5 * 2^52: rint() through the adder
+    const double magic = 6755399441055744.0;           // 1.5 * 2^52: rint() through the adder
+    if (diag) {                                        // same arithmetic as below with the zero terms dropped
+      const double n0 = (g->inv[0] * dx + magic) - magic;
+      const double n1 = (g->inv[4] * dy + magic) - magic;
+      const double n2 = (g->inv[8] * dz + magic) - magic;
+      dx -= n0 * g->lat[0];
+      dy -= n1 * g->lat[4];
+      dz -= n2 * g->lat[8];
+    } else if (per) {
       const double n0 = (g->inv[0] * dx + g->inv[1] * dy + g->inv[2] * dz + magic) - magic;
       const double n1 = (g->inv[3] * dx + g->inv[4] * dy + g->inv[5] * dz + magic) - magic;
       const double n2 = (g->inv[6] * dx + g->inv[7] * dy + g->inv[8] * dz + magic) - magic;

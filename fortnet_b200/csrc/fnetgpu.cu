@@ -4,6 +4,7 @@
 #include "internal.h"
 #include "cells.cuh"
 #include "acsf.cuh"
+#include "acsf_lean.cuh"
 #include "acsf_force.cuh"
 #include "mlp.cuh"
 #include "mlp_mma.cuh"
@@ -60,6 +61,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
   { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0;
     ctx->mlpNoFuse = (pm && strcmp(pm, "nofuse") == 0) ? 1 : 0; }
+  { const char *pm = getenv("FNETGPU_ACSF_KERNEL"); ctx->acsfGeneric = (pm && strcmp(pm, "generic") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
   return 0;
@@ -81,7 +83,7 @@ extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) free_slot(ctx->slots[i]);
   cudaFree(ctx->d_rgroups); cudaFree(ctx->d_rfeat); cudaFree(ctx->d_rp1); cudaFree(ctx->d_rp2);
-  cudaFree(ctx->d_apasses); cudaFree(ctx->d_extIdx); cudaFree(ctx->d_zprec); cudaFree(ctx->d_wb);
+  cudaFree(ctx->d_apasses); cudaFree(ctx->d_lrad); cudaFree(ctx->d_lpass); cudaFree(ctx->d_powtab); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_extIdx); cudaFree(ctx->d_zprec); cudaFree(ctx->d_wb);
   cudaFree(ctx->d_wb64); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->comm && ctx->nccl) {
@@ -336,7 +338,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       while (beg < m.size()) {
         size_t run = 1;
         while (beg + run < m.size() && eta[m[beg + run]] == eta[m[beg]]) run++;
-        bool lad = run >= 3;
+        bool lad = run >= 2;
         const double r0 = rs[m[beg]], d = lad ? rs[m[beg + 1]] - r0 : 0.0;
         lad = lad && d > 0.0;
         for (size_t q = 0; q < run && lad; q++) {
@@ -429,6 +431,135 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
     if (ns == 4) rows = 0;                       // 32 angular values per lane use the shuffle butterfly
     for (const RadialGroup &G : ctx->h_rgroups) if (G.ladder) rows = std::max(rows, 8 * G.nChunksP2);
     T.redRows = rows;
+  }
+  // ---- lean kernel tables (acsf_lean.cuh): every radial group a G2 ladder, every angular key a set of
+  // lambda-groups that are fresh xi-ladders from xi = 1 with ONE common step delta (the automatic scheme,
+  // acsf.F90:276-363, also after the species-resolved expansion), no atom-id scaling ----
+  ctx->leanOK = false;
+  std::vector<LeanRadial> lrad; std::vector<LeanPass> lpass;
+  double leanDelta = 0.0;
+  {
+    bool ok = F > 0 && !anyAtomId;
+    int maxChunks = 1;
+    for (const RadialGroup &G : ctx->h_rgroups) {
+      if (!G.ladder) { ok = false; break; }
+      LeanRadial R; memset(&R, 0, sizeof(R));
+      R.code = G.code; R.fBeg = G.fBeg; R.fCnt = G.fCnt; R.nch = G.nChunksP2;
+      R.lgn = G.nChunksP2 == 1 ? 0 : (G.nChunksP2 == 2 ? 1 : 2);
+      R.rc = G.rc; R.invrc = 1.0 / G.rc; R.eta = G.eta; R.rs0 = G.rs0; R.drs = G.drs;
+      for (int q = 0; q < FNET_RCHUNK - 1; q++) R.kk[q] = G.kk[q];
+      maxChunks = std::max(maxChunks, G.nChunksP2);
+      lrad.push_back(R);
+    }
+    // lambda-groups per key
+    struct LamGroup { double lam; std::vector<int> m; };
+    std::vector<std::vector<LamGroup>> keyGroups(akeys.size());
+    bool haveDelta = false;
+    size_t maxM = 1; size_t maxGroups = 1;
+    for (size_t g = 0; g < akeys.size() && ok; g++) {
+      if (std::get<0>(akeys[g]) != FNETGPU_G5) { ok = false; break; }
+      std::vector<int> m = amembers[g];
+      std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
+        if (lambda[a] != lambda[b]) return lambda[a] > lambda[b];
+        return xi[a] < xi[b];
+      });
+      for (size_t p = 0; p < m.size();) {
+        LamGroup L; L.lam = lambda[m[p]];
+        size_t q = p;
+        while (q < m.size() && lambda[m[q]] == L.lam) L.m.push_back(m[q++]);
+        if (!(L.lam >= -1.0) || xi[L.m[0]] != 1.0) { ok = false; break; }
+        for (size_t f = 1; f < L.m.size() && ok; f++) {
+          const double d = (xi[L.m[f]] - 1.0) / (double)f;
+          if (!haveDelta) { leanDelta = d; haveDelta = true; }
+          if (!(d > 0.0) || fabs(d - leanDelta) > 1e-12 * std::max(1.0, fabs(leanDelta))) ok = false;
+        }
+        maxM = std::max(maxM, L.m.size());
+        keyGroups[g].push_back(L);
+        p = q;
+      }
+      maxGroups = std::max(maxGroups, keyGroups[g].size());
+    }
+    if (ok && haveDelta) {   // degree-5 binomial series of (1 + r)^delta, |r| <= 2^-9: truncation binom(delta, 6) 2^-54
+      long double b6 = 1.0L;
+      for (int k = 0; k < 6; k++) b6 *= ((long double)leanDelta - k) / (long double)(k + 1);
+      if (fabsl(b6) > 18.0L) ok = false;
+    }
+    if (ok) {
+      const int NC = maxM <= 8 ? 1 : (maxM <= 16 ? 2 : 4);
+      const int NL = NC == 4 ? 1 : 2;
+      (void)maxGroups;
+      const int blk = FNET_LADDER * NC;
+      for (size_t g = 0; g < akeys.size(); g++) {
+        const std::vector<LamGroup> &LG = keyGroups[g];
+        for (size_t l0 = 0; l0 < LG.size(); l0 += NL) {
+          size_t longest = 0;
+          for (int l = 0; l < NL && l0 + l < LG.size(); l++) longest = std::max(longest, LG[l0 + l].m.size());
+          for (size_t m0 = 0; m0 < longest; m0 += blk) {
+            LeanPass P; memset(&P, 0, sizeof(P));
+            P.code1 = std::get<4>(akeys[g]); P.code2 = std::get<5>(akeys[g]);
+            P.same = (P.code1 == P.code2) ? 1 : 0;
+            P.rc = std::get<1>(akeys[g]); P.invrc = 1.0 / P.rc; P.eta = std::get<2>(akeys[g]);
+            P.m0 = (int)m0;
+            for (int e = 0; e < FNET_LEAN_MAXACC; e++) P.feat[e] = -1;
+            for (int l = 0; l < NL; l++) {
+              if (l0 + l >= LG.size()) { P.lam[l] = 0.0; continue; }
+              const LamGroup &L = LG[l0 + l];
+              P.lam[l] = L.lam;
+              for (int f = 0; f < blk; f++) {
+                const size_t mi = m0 + f;
+                if (mi >= L.m.size()) break;
+                const int a = L.m[mi], e = l * blk + f;
+                const double x = xi[a], pre = pow(2.0, 1.0 - x);        // acsf.F90:1434,1490
+                P.feat[e] = a;
+                P.pref[e] = P.same ? 2.0 * pre : pre;
+                if (P.same) {   // diagonal j == k: cos = 1 - eps (acsf_lean.cuh)
+                  if (L.lam > -1.0) { P.dA[e] = pre * pow(1.0 + L.lam, x); P.dB[e] = -P.dA[e] * x * L.lam / (1.0 + L.lam); }
+                  else { P.dA[e] = 0.0; P.dB[e] = (x == 1.0) ? pre : 0.0; }
+                }
+              }
+            }
+            const bool first = lpass.empty();
+            P.recomp = (!first && (P.rc != lpass.back().rc || P.eta != lpass.back().eta)) ? 1 : 0;
+            lpass.push_back(P);
+          }
+        }
+      }
+      ctx->leanNL = NL; ctx->leanNC = NC;
+      ctx->leanSorted = T.nCodes > 0;
+      LeanTables &LT = ctx->lean;
+      memset(&LT, 0, sizeof(LT));
+      LT.nRadial = (int)lrad.size(); LT.nPasses = (int)lpass.size();
+      LT.redRows = std::max(FNET_LADDER * NL * NC, FNET_RCHUNK * maxChunks);
+      if (!lpass.empty()) { LT.rcShared = lpass[0].rc; LT.etaShared = lpass[0].eta; }
+      else { LT.rcShared = lrad.empty() ? rcMax : lrad[0].rc; LT.etaShared = 0.0; }
+      LT.invrcShared = 1.0 / LT.rcShared;
+      for (LeanRadial &R : lrad) R.sharedFc = (R.rc == LT.rcShared) ? 1 : 0;
+      {
+        long double c = 1.0L;
+        for (int k = 1; k <= 5; k++) { c *= ((long double)leanDelta - (k - 1)) / (long double)k; LT.powC[k - 1] = (double)c; }
+      }
+      std::vector<double> pt(FNET_POW_DOUBLES);
+      for (int i = 0; i < FNET_POW_TAB_N; i++) {
+        const long double mid = 1.0L + ((long double)i + 0.5L) / (long double)FNET_POW_TAB_N;
+        const double invc = (double)(1.0L / mid);
+        pt[2 * i] = invc;
+        pt[2 * i + 1] = (double)powl(1.0L / (long double)invc, (long double)leanDelta);
+      }
+      for (int k = FNET_POW_KMIN; k <= 1; k++) pt[2 * FNET_POW_TAB_N + (k - FNET_POW_KMIN)] = (double)powl(2.0L, (long double)k * (long double)leanDelta);
+      std::vector<unsigned short> pairs(FNET_PAIR_TAB_N);
+      for (int k = 1; k <= FNET_PAIR_TAB_MAXN; k++)
+        for (int j = 0; j < k; j++) {
+          const int p = k * (k - 1) / 2 + j;
+          if (p < FNET_PAIR_TAB_N) pairs[p] = (unsigned short)(j | (k << 8));
+        }
+      if (dev_upload(ctx, &ctx->d_lrad, lrad.data(), lrad.size())) return 1;
+      if (dev_upload(ctx, &ctx->d_lpass, lpass.data(), lpass.size())) return 1;
+      if (dev_upload(ctx, &ctx->d_powtab, pt.data(), pt.size())) return 1;
+      if (dev_upload(ctx, &ctx->d_pairtab, pairs.data(), pairs.size())) return 1;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors above are stack-lifetime
+      LT.rad = ctx->d_lrad; LT.pass = ctx->d_lpass; LT.powtab = ctx->d_powtab; LT.pairtab = ctx->d_pairtab;
+      ctx->leanOK = true;
+    }
   }
   T.nRadialGroups = (int)ctx->h_rgroups.size();
   T.nAngularPasses = (int)ctx->h_apasses.size();
@@ -591,7 +722,7 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
 }
 
 // launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
-struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; };
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; bool lean = false; };
 // the whole-structure path (cells.cuh): small structures, lattice check passed so far
 static bool use_struct_path(const fnetgpu_ctx *ctx, const Slot &s) {
   return !ctx->acsfPathCells && s.structPath && s.maxAtoms <= FNET_STRUCT_MAX_ATOMS && s.d_coords && s.d_lat;
@@ -607,12 +738,12 @@ static GeomArgs geom_args(const Slot &s) {
   g.stBase = 0;
   return g;
 }
-static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
+static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L, int cap = -1, size_t extraCta = 0) {
   L.path = FNET_PATH_STRUCT; L.staged = false;
-  L.cap = struct_cap(s);
+  L.cap = cap > 0 ? cap : struct_cap(s);
   L.capC = (s.maxAtoms + 31) & ~31;
   L.wpb = 4;
-  const size_t prefix = acsf_cta_prefix_bytes(L.capC, 2);
+  const size_t prefix = acsf_cta_prefix_bytes(L.capC, 2) + extraCta;
   L.smem = prefix + warpBytes * L.wpb;
   while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
   if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
@@ -627,16 +758,16 @@ static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes,
   L.grid = dim3(s.nStruct, L.nSplit);
   return 0;
 }
-static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L) {
-  L.cap = std::max(32, (s.maxNeigh + 31) & ~31);
+static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L, int cap = -1, size_t extraCta = 0) {
+  L.cap = cap > 0 ? cap : std::max(32, (s.maxNeigh + 31) & ~31);
   L.staged = s.maxCells <= FNET_MAX_NCELLS && s.maxCand >= 0 && s.maxCand <= 1536;
   L.capC = L.staged ? ((s.maxCand + s.maxCand / 8 + 31) & ~31) : 0;
   L.wpb = 4;
-  const size_t prefix = L.staged ? acsf_cta_prefix_bytes(L.capC) : acsf_cta_prefix_bytes(0, 0);
+  const size_t prefix = (L.staged ? acsf_cta_prefix_bytes(L.capC) : acsf_cta_prefix_bytes(0, 0)) + extraCta;
   L.smem = prefix + warpBytes * L.wpb;
   while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
-  if (L.smem > 220 * 1024 && L.staged) { L.staged = false; L.capC = 0; L.wpb = 4; L.smem = acsf_cta_prefix_bytes(0, 0) + warpBytes * L.wpb;
-    while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = acsf_cta_prefix_bytes(0, 0) + warpBytes * L.wpb; } }
+  if (L.smem > 220 * 1024 && L.staged) { L.staged = false; L.capC = 0; L.wpb = 4; L.smem = acsf_cta_prefix_bytes(0, 0) + extraCta + warpBytes * L.wpb;
+    while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = acsf_cta_prefix_bytes(0, 0) + extraCta + warpBytes * L.wpb; } }
   if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
   // atoms of a bin are split over blockIdx.y so that a CTA sees ~4 rounds of its warps and the
   // grid still fills the GPU when a structure has few, crowded bins
@@ -650,11 +781,42 @@ static int plan_acsf_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, A
   return 0;
 }
 
+// launch plan of the VALUE kernel: the lean kernel (acsf_lean.cuh) when the configuration is an
+// automatic-scheme one and the candidates can be staged, else k_acsf
+static bool use_lean(const fnetgpu_ctx *ctx) { return ctx->leanOK && !ctx->acsfGeneric; }
+static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLaunch &L) {
+  const AcsfTables &T = ctx->acsf;
+  if (use_lean(ctx)) {
+    const int hint = s.maxNeigh > 0 ? s.maxNeigh : 32;   // + 1: the dummy neighbour of the pair walk
+    const int cap = structPath ? std::max(32, (std::min(hint, std::max(s.maxAtoms - 1, 1)) + 1 + 31) & ~31)
+                               : std::max(32, (s.maxNeigh + 1 + 31) & ~31);
+    AcsfLaunch Q;
+    const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows), extra = lean_cta_extra_bytes(T.F);
+    const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
+    if (rc == 0 && Q.path != FNET_PATH_DIRECT) { L = Q; L.lean = true; return 0; }
+    ctx->err.clear();
+  }
+  L.lean = false;
+  if (structPath) return plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F, T.redRows), L);
+  return plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F, T.redRows), L);
+}
+
 extern "C" int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode) {
   CHECK_CTX(ctx);
   if (mode != 0 && mode != 1) FNET_FAIL(ctx, "acsf_path_set: mode must be 0 (auto) or 1 (cell list)");
   ctx->acsfPathCells = mode;
   return 0;
+}
+extern "C" int fnetgpu_acsf_kernel_set(fnetgpu_ctx *ctx, int mode) {
+  CHECK_CTX(ctx);
+  if (mode != 0 && mode != 1) FNET_FAIL(ctx, "acsf_kernel_set: mode must be 0 (auto: lean kernel for automatic-scheme configurations) or 1 (always k_acsf)");
+  ctx->acsfGeneric = mode;
+  return 0;
+}
+// 1: the value kernel of the current configuration is k_acsf_lean, 0: k_acsf, -1: no configuration
+extern "C" int fnetgpu_acsf_kernel_get(const fnetgpu_ctx *ctx) {
+  if (!ctx || !ctx->acsfSet) return -1;
+  return (ctx->leanOK && !ctx->acsfGeneric) ? 1 : 0;
 }
 extern "C" int fnetgpu_mlp_path_set(fnetgpu_ctx *ctx, int mode) {
   CHECK_CTX(ctx);
@@ -758,6 +920,27 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   } while (0)
 #define FNET_ACSF_LAUNCH_NS(PATH)                                                                              \
   do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
+  if (L.lean) {
+    const LeanTables &LT = ctx->lean;
+#define FNET_LEAN_LAUNCH(NL, NC, PATH, SORTED)                                                                 \
+  do {                                                                                                         \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<real, NL, NC, PATH, SORTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF, (k_acsf_lean<real, NL, NC, PATH, SORTED><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(  \
+                            L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, feat, nFeat, zp, nExtSel,    \
+                            ctx->d_extIdx, ctx->d_flags)));                                                    \
+  } while (0)
+#define FNET_LEAN_LAUNCH_S(NL, NC, PATH)                                                                       \
+  do { if (ctx->leanSorted) FNET_LEAN_LAUNCH(NL, NC, PATH, true); else FNET_LEAN_LAUNCH(NL, NC, PATH, false); } while (0)
+#define FNET_LEAN_LAUNCH_P(NL, NC)                                                                             \
+  do { if (L.path == FNET_PATH_STRUCT) FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STRUCT); else FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STAGED); } while (0)
+    if (ctx->leanNC == 1) FNET_LEAN_LAUNCH_P(2, 1);
+    else if (ctx->leanNC == 2) FNET_LEAN_LAUNCH_P(2, 2);
+    else FNET_LEAN_LAUNCH_P(1, 4);
+#undef FNET_LEAN_LAUNCH_P
+#undef FNET_LEAN_LAUNCH_S
+#undef FNET_LEAN_LAUNCH
+    return 0;
+  }
   const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);
   if (L.path == FNET_PATH_STRUCT) FNET_ACSF_LAUNCH_NS(FNET_PATH_STRUCT);
   else if (L.path == FNET_PATH_STAGED) FNET_ACSF_LAUNCH_NS(FNET_PATH_STAGED);
@@ -804,7 +987,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       AcsfLaunch L;
       const bool sp = use_struct_path(ctx, s);
       if (sp) {
-        if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), F, T.redRows), L)) return 1;
+        if (plan_values(ctx, s, true, L)) return 1;
       } else {
         if (h_coords) {                         // the cell list is built from the device copy: plain upload first
           CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, h_coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -812,7 +995,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
         }
         if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
         if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
-        if (plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), F, T.redRows), L)) return 1;
+        if (plan_values(ctx, s, false, L)) return 1;
       }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (h_coords && sp) {
@@ -843,6 +1026,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       s.lastPath = L.path;
+      if (L.lean && sp && h[4] == 0 && h[1] == 0 && h[7] == 0 && h[0] > 0) s.maxNeigh = h[0];   // exact maximum of this geometry
       if (sp) {
         if (h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; continue; }   // a lattice is too small for the minimum image: cell list
         if (h[1] == 0 && h[7] == 0) break;
@@ -1448,7 +1632,7 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
       s.cellRc = -1.0; s.neighStale = true;
       const double *zp = s.zscored ? ctx->d_zprec : nullptr;
       AcsfLaunch Lv, Lf;
-      if (plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F, T.redRows), Lv)) return 1;
+      if (plan_values(ctx, s, true, Lv)) return 1;
       if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), Lf)) return 1;
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;

@@ -92,6 +92,47 @@ struct AcsfTables {           // device pointers + sizes, passed by value to ker
   double rcMax;
 };
 
+// ---- lean ACSF kernel (acsf_lean.cuh): tables of the automatic parameter scheme ----
+#define FNET_POW_TAB_N 256                 // mantissa intervals of the power table
+#define FNET_POW_KMIN (-62)                // smallest binary exponent with an own 2^(k delta) entry (b <= 2 -> k <= 1)
+#define FNET_POW_NK (2 - FNET_POW_KMIN)    // 64 entries
+#define FNET_POW_DOUBLES (2 * FNET_POW_TAB_N + FNET_POW_NK)
+#define FNET_PAIR_TAB_MAXN 64              // strict-triangle pair table covers lists of <= 64 neighbours
+#define FNET_PAIR_TAB_N (FNET_PAIR_TAB_MAXN * (FNET_PAIR_TAB_MAXN - 1) / 2 + 1)
+#define FNET_LEAN_MAXACC 32                // accumulators per lane and pass
+
+struct LeanRadial {            // G2 group on an arithmetic rs-ladder with one eta (auto scheme, acsf.F90:320-336)
+  int code;                    // species code of the neighbour list, -1 = all neighbours
+  int fBeg, fCnt;              // slice of AcsfTables::rfeat
+  int nch, lgn;                // chunks of 8 functions padded to a power of two, and its log2
+  int sharedFc;                // rc equals LeanTables::rcShared: the per-neighbour cutoff values are reused
+  double rc, invrc, eta, rs0, drs;
+  double kk[FNET_RCHUNK - 1];  // kk[m] = exp(-eta drs^2 (2m+1))
+};
+
+struct LeanPass {              // NL lambda-groups x NC chained 8-function slots of one xi-ladder each
+  int code1, code2, same;
+  int recomp;                  // (rc, eta) differ from the previous pass: per-neighbour factors are recomputed
+  int m0;                      // first ladder index of this pass: xi = 1 + (m0 + f) delta
+  double rc, invrc, eta;
+  double lam[2];
+  int feat[FNET_LEAN_MAXACC];      // output feature of accumulator e = (l * NC + chunk) * 8 + f, -1 = unused
+  double pref[FNET_LEAN_MAXACC];   // 2^(1 - xi) (x 2 for identical lists: unordered pairs)
+  double dA[FNET_LEAN_MAXACC];     // diagonal of identical lists: value += dA * sum fcE^2 + dB * sum fcE^2 eps
+  double dB[FNET_LEAN_MAXACC];
+};
+
+struct LeanTables {            // passed by value (kernel parameter space = constant bank)
+  int nRadial, nPasses;
+  const LeanRadial *rad;       // device
+  const LeanPass *pass;        // device
+  const double *powtab;        // device: (1/c_i, c_i^delta) x 256, then 2^(k delta), k = KMIN .. 1
+  const unsigned short *pairtab;   // device: p -> j | k << 8 of the strict triangle, entry p = k (k-1)/2 + j
+  double powC[5];              // binom(delta, 1..5)
+  int redRows;                 // rows of the per-warp reduction scratch: max(8 NL NC, 8 * radial chunks)
+  double rcShared, invrcShared, etaShared;   // (rc, eta) of the per-neighbour factors formed right after the gather
+};
+
 struct NetTables {
   int nSpecies, L, act, nTot, nOut;
   int dims[FNET_MAX_LAYERS];
@@ -183,6 +224,13 @@ struct fnetgpu_ctx {
   int maxSlots = 1;                 // largest nSlots of any angular pass (selects the kernel instantiation)
   RadialGroup *d_rgroups = nullptr; int *d_rfeat = nullptr; double *d_rp1 = nullptr, *d_rp2 = nullptr;
   AngularPass *d_apasses = nullptr;
+  // lean kernel (acsf_lean.cuh): the configuration is an automatic-scheme one
+  bool leanOK = false;
+  int leanNL = 2, leanNC = 1;       // accumulator shape of the instantiation: lambda-groups x chained 8-function slots
+  bool leanSorted = false;          // species-resolved functions present
+  LeanTables lean;                  // device pointers inside
+  LeanRadial *d_lrad = nullptr; LeanPass *d_lpass = nullptr; double *d_powtab = nullptr; unsigned short *d_pairtab = nullptr;
+  int acsfGeneric = 0;              // FNETGPU_ACSF_KERNEL=generic / acsf_kernel_set(1): always k_acsf (tests, A/B)
   std::vector<int> extIdx;          // 0-based rows of ext appended to the features
   int *d_extIdx = nullptr;
   double *d_zprec = nullptr;        // [2F] means, sigmas

@@ -154,6 +154,14 @@ int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode);
 /* path the last ACSF value / force launch of this slot took: 0 cell list (direct), 1 cell list
  * (candidates staged per bin), 2 whole structure; -1 before the first launch */
 int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot);
+/* ACSF value kernel.  mode 0 (default): configurations of the automatic parameter scheme
+ * (TGFunctions_fromAutoScheme, acsf.F90:276-363: G2 on an arithmetic rs-ladder, G5 on xi-ladders from
+ * xi = 1 with one common step, also after the species-resolved expansion, no atom-id scaling) run
+ * k_acsf_lean (table-driven powers, closed-form diagonal), everything else k_acsf; mode 1: always
+ * k_acsf (tests, A/B).  FNETGPU_ACSF_KERNEL=generic selects mode 1 at fnetgpu_init. */
+int fnetgpu_acsf_kernel_set(fnetgpu_ctx *ctx, int mode);
+/* 1: the configured functions run through k_acsf_lean, 0: k_acsf, -1: no configuration */
+int fnetgpu_acsf_kernel_get(const fnetgpu_ctx *ctx);
 /* Subnetwork kernels in precision 64.  mode 0 (default): FP64 tensor-core (DMMA) kernels when the
  * network fits their limits (sum of layer widths <= 128, <= 72 8x8 weight-gradient tiles, shared
  * memory), else the register-tiled DFMA kernels -- and, for single-species datasets with <= 64

@@ -42,11 +42,11 @@ STRUCT, CELLS = (2,), (0, 1)   # values of Context.acsf_path()
 
 
 def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3, acsf_path="auto",
-                expect_path=None, mlp="auto", expect_mlp=None):
+                expect_path=None, mlp="auto", expect_mlp=None, acsf_kernel="auto", expect_lean=None):
     """features (raw + z-scored), statistics, predictions, loss, gradient and forces vs the oracle"""
     fd = funcs.asdicts()
     nt = _nthreads()
-    ctx = fb.Context(acsf_path=acsf_path, mlp=mlp)
+    ctx = fb.Context(acsf_path=acsf_path, mlp=mlp, acsf_kernel=acsf_kernel)
     ctx.upload(0, ds)
     a_raw = fb.Acsf(ctx, funcs, standardize=False)
     a_raw.calculate(0)
@@ -54,6 +54,10 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
         expect_path = CELLS
     if expect_path is not None:
         assert ctx.acsf_path(0) in expect_path, ctx.acsf_path(0)
+    if acsf_kernel == "generic":
+        expect_lean = 0
+    if expect_lean is not None:
+        assert ctx.acsf_kernel() == expect_lean, ctx.acsf_kernel()
     vals = a_raw.features(0)
     ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, fd, ext=ds.ext, nthreads=nt)
     assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
@@ -113,7 +117,48 @@ def test_c2_si_bulk(fb, orc, path, mlp):
     from fortnet_b200 import synthetic
     ds = synthetic.si_bulk(n_struct=12, seed=20260001)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
-    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1)
+    _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1,
+                expect_lean=1)
+
+
+KERNELS = ["auto", "generic"]   # ACSF value kernel: k_acsf_lean for automatic-scheme configurations, or always k_acsf
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("wl", ["c2", "c3", "c3_unresolved", "cluster"])
+def test_value_kernels(fb, orc, wl, path, kernel):
+    """both ACSF value kernels on the BASELINE shapes (and a ragged cluster batch) through both neighbour paths"""
+    from fortnet_b200 import synthetic
+    if wl == "c2":
+        ds = synthetic.si_bulk(n_struct=5, seed=77)
+        funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+    elif wl == "c3":
+        ds = synthetic.tio2(n_struct=2, seed=78)
+        funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
+    elif wl == "c3_unresolved":
+        ds = synthetic.tio2(n_struct=2, seed=79)
+        funcs = fb.GFunctions.from_auto_scheme(5.0 * fb.BOHR_PER_AA, 12, 24)
+    else:
+        rng = np.random.default_rng(80)
+        natoms = [1, 2, 40, 9, 33]
+        coords = np.concatenate([rng.uniform(0.0, 6.0 + 2.0 * n ** (1 / 3), size=(n, 3)) for n in natoms])
+        N = sum(natoms)
+        ds = fb.Dataset.build(natoms, coords, np.zeros(len(natoms), np.int32), np.zeros((len(natoms), 3, 3)),
+                              rng.choice([1, 8], size=N).astype(np.int32), gtargets=np.zeros((len(natoms), 1)),
+                              atomic_numbers=[1, 8])
+        funcs = fb.GFunctions.from_auto_scheme(6.0, 7, 10).resolve_species([1, 8])
+    ctx = fb.Context(acsf_path=path, acsf_kernel=kernel)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=False)
+    assert ctx.acsf_kernel() == (1 if kernel == "auto" else 0)
+    acsf.calculate(0)
+    vals = acsf.features(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
+    assert np.allclose(vals, ref, rtol=1e-10, atol=1e-12), _md(vals, ref)
+    acsf.calculate(0)                                    # second launch: capacities from the first one
+    assert np.array_equal(acsf.features(0), vals)
+    ctx.close()
 
 
 @pytest.mark.parametrize("mlp", MLPS)
@@ -158,18 +203,21 @@ def test_large_and_small_structures_in_one_batch(fb, orc):
     _full_check(fb, orc, ds, funcs, [12, 6, 1], expect_path=CELLS)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("nrad,nang", [(24, 4), (3, 40), (17, 18), (32, 34), (9, 2)])
-def test_auto_scheme_sizes(fb, orc, nrad, nang, path):
+@pytest.mark.parametrize("nrad,nang", [(24, 4), (3, 40), (17, 18), (32, 34), (9, 2), (2, 72), (5, 8)])
+def test_auto_scheme_sizes(fb, orc, nrad, nang, path, kernel):
     """auto-scheme sizes that exercise every shape of the kernels' function grouping: 1 / 2 / 4 radial
     chunks of 8 (shared-memory reduction with 8 / 16 / 32 rows), 1 / 2 / 4 ladder slots per angular
     pass, continuing ladders (more than 8 functions per lambda) and partially filled ladders"""
     from fortnet_b200 import synthetic
     ds = synthetic.si_bulk(n_struct=2, seed=13)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, nrad, nang)
-    ctx = fb.Context(acsf_path=path)
+    ctx = fb.Context(acsf_path=path, acsf_kernel=kernel)
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, funcs, standardize=False)
+    # nang = 4: xi step 15 -> the degree-5 power series is not accurate enough, k_acsf takes it
+    assert ctx.acsf_kernel() == (1 if kernel == "auto" and nang != 4 else 0)
     acsf.calculate(0)
     vals = acsf.features(0)
     ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
@@ -190,13 +238,14 @@ def test_subnetwork_shapes(fb, orc, dims, expect):
     _full_check(fb, orc, ds, funcs, dims, forces=True, expect_mlp=expect)
 
 
-def test_c5_dense_liquid_values(fb, orc):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_c5_dense_liquid_values(fb, orc, kernel):
     """C5 shape at oracle size: rc = 8 A, ~150 neighbours, 128 G5 on the auto ladder; box edge
     (12.2 A) < 2 rc, so atoms see several periodic images of the same neighbour."""
     from fortnet_b200 import synthetic
     ds = synthetic.dense_liquid(n_atoms=128, density_aa3=0.070, seed=99, n_struct=1)
     funcs = fb.GFunctions.from_auto_scheme(8.0 * fb.BOHR_PER_AA, 2, 128)
-    ctx = fb.Context()
+    ctx = fb.Context(acsf_kernel=kernel)
     ctx.upload(0, ds)
     acsf = fb.Acsf(ctx, funcs, standardize=False)
     acsf.calculate(0)
