@@ -21,43 +21,36 @@
 //   * the pair index -> (j, k) map of the strict triangle, p = k (k - 1) / 2 + j, does not depend on
 //     the neighbour count: one 16-bit table for every atom; consecutive lanes read consecutive j
 //     (conflict-free) and mostly the same k (broadcast);
-//   * per neighbour: unit vectors, sqrt(1e-13) / r, fc and fc exp(-eta r^2) are formed once (rsqrt +
-//     one third-order Newton step instead of sqrt and a division) and shared by the radial groups and
-//     all angular passes with the same (rc, eta); invalid lanes of the last sweep are routed to a
-//     dummy neighbour with fc = 0, so the pair loop has no predicate at all;
+//   * per neighbour: fc and fc exp(-eta r^2) are formed once (rsqrt + one third-order Newton step
+//     instead of sqrt and a division) and shared by the radial groups and all angular passes with the
+//     same (rc, eta), and the unit vector is stored as u' = u (1 - eps / 2), eps = 1e-13 / r^2: then
+//     u'_j . u'_k = cos (1 - (eps_j + eps_k) / 2) reproduces d_j . d_k / (r_j r_k + 1e-13) =
+//     cos (1 - sqrt(eps_j eps_k)) up to cos (sqrt(eps_j) - sqrt(eps_k))^2 / 2 < 1e-14 -- the regulariser
+//     itself is 1e-13 -- and costs no arithmetic in the pair loop; one 48-byte record per neighbour
+//     (u'_x, u'_y | u'_z, fc E | r, fc), two 16-byte loads per pair member; invalid lanes of the last
+//     sweep are routed to a dummy neighbour with fc = 0, so the pair loop has no predicate at all;
+//   * G = 1, 2 or 4 central atoms per warp (32 / G lanes each), chosen from the neighbour count: for the
+//     ~16 neighbours of bulk Si every per-atom step (candidate sweep, per-neighbour factors, radial
+//     sums, the cross-lane reductions, table loads) then fills the warp instead of half of it;
 //   * the z-score is applied as (g - mu) * (1 / sigma) with the reciprocals formed once per CTA.
 // Everything that is not a fresh xi-ladder from xi = 1 with one common delta (explicit function
 // lists, G1 / G3 / G4, atom-id scaling, lam < -1) runs through k_acsf.
 #pragma once
 #include "acsf.cuh"
 
-struct LeanWarp {
-  double *ux, *uy, *uz, *w, *fcE, *r, *fc;
-  int *seg;
-  double *outv, *red;
-};
 
-__host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows) {
-  size_t b = (size_t)cap * 7 * sizeof(double);
-  b += (FNET_MAX_CODES + 4) * sizeof(int);
-  b = (b + 15) & ~(size_t)15;
-  b += (size_t)((F + 1) & ~1) * sizeof(double);
-  b += (size_t)redRows * FNET_RED_STRIDE * sizeof(double);
+__host__ __device__ inline size_t lean_group_bytes(int cap, int F, bool sorted) {   // cap: multiple of 8
+  size_t b = (size_t)cap * 6 * sizeof(double);                         // neighbour records
+  if (sorted) b += (size_t)cap * (3 * sizeof(double) + sizeof(int));   // unsorted displacements + species codes
+  b += (size_t)((FNET_MAX_CODES + 4 + 3) & ~3) * sizeof(int);          // list segments
+  b += (size_t)((F + 1) & ~1) * sizeof(double);                        // feature row
   return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t lean_cta_extra_bytes(int F) {   // power tables + (mu, 1/sigma)
-  return ((size_t)(FNET_POW_DOUBLES + 2 * ((F + 1) & ~1)) * sizeof(double) + 15) & ~(size_t)15;
+__host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows, bool sorted, int G) {
+  return (size_t)G * lean_group_bytes(cap, F, sorted) + (((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15);
 }
-__device__ __forceinline__ LeanWarp lean_carve(unsigned char *base, int cap, int F) {
-  LeanWarp w;
-  double *d = (double *)base;
-  w.ux = d; w.uy = d + cap; w.uz = d + 2 * cap; w.w = d + 3 * cap; w.fcE = d + 4 * cap; w.r = d + 5 * cap; w.fc = d + 6 * cap;
-  w.seg = (int *)(d + 7 * cap);
-  size_t off = (size_t)cap * 7 * sizeof(double) + (FNET_MAX_CODES + 4) * sizeof(int);
-  off = (off + 15) & ~(size_t)15;
-  w.outv = (double *)(base + off);
-  w.red = w.outv + ((F + 1) & ~1);
-  return w;
+__host__ __device__ inline size_t lean_cta_extra_bytes(int F) {   // power tables + (mu, 1/sigma) + atomic number -> species code
+  return ((size_t)(FNET_POW_DOUBLES + 2 * ((F + 1) & ~1)) * sizeof(double) + 128 + 15) & ~(size_t)15;
 }
 
 // b^delta for b in [0, 2] (header comment); b <= 2^-62 (and a last-bit negative b) returns a finite
@@ -92,6 +85,7 @@ __device__ __forceinline__ void lean_rsqrt(double d2, double &rinv, double &r) {
   rinv = y; r = rr;
 }
 
+// species list = segment(code) followed by the self-image segment (the last one, ending at n)
 __device__ __forceinline__ NbList lean_list(const AcsfTables &tab, const int *__restrict__ seg, int code, int n) {
   NbList l;
   if (code < 0) { l.s0 = 0; l.n0 = n; l.s1 = n; l.n1 = 0; }
@@ -101,67 +95,6 @@ __device__ __forceinline__ NbList lean_list(const AcsfTables &tab, const int *__
     l.s1 = seg[self]; l.n1 = seg[self + 1] - l.s1;
   }
   return l;
-}
-
-// Gathers the neighbours of `me` into (ux, uy, uz) as raw displacements (sorted by species code
-// when SORTED: [code 0 .. | other | self-images], acsf.F90:754-760); returns n or -needed.
-template <int PATH, bool SORTED>
-__device__ __forceinline__ int lean_gather(const CRec &me, const CtaGeom &cg, const AcsfTables &tab, int cap,
-                                           LeanWarp &w) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const double rc2 = tab.rcMax * tab.rcMax;
-  double *gx = SORTED ? w.fcE : w.ux, *gy = SORTED ? w.r : w.uy, *gz = SORTED ? w.fc : w.uz;
-  int *gc = (int *)w.w;
-  int n = 0;
-  auto take = [&](bool valid, double dx, double dy, double dz, int j, int zs) {
-    const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, j, zs, me.idx);
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    const int pos = n + __popc(m & lt);
-    if (ok && pos < cap - 1) {
-      gx[pos] = dx; gy[pos] = dy; gz[pos] = dz;
-      if (SORTED) gc[pos] = (j == me.idx) ? tab.nCodes + 1 : species_code(tab, zs & ~FNET_SHIFT_FLAG);
-    }
-    n += __popc(m);
-  };
-  if (PATH == FNET_PATH_STRUCT) for_each_candidate_struct(cg.cand, cg.nCand, cg.sg, me, take);
-  else if (PATH == FNET_PATH_STAGED) for_each_candidate_staged(cg.cand, cg.nCand, me, take);
-  else for_each_candidate_direct(*cg.S, cg.bp, cg.cellStart, cg.crec, me, take);
-  if (n > cap - 1) return -(n + 1);          // one slot is the dummy neighbour
-  __syncwarp();
-  if (SORTED) {
-    const int nc = tab.nCodes + 2;  // + other + self
-    int mycount = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int t = base + lane;
-      const int code = (t < n) ? gc[t] : -1;
-      for (int c = 0; c < nc; c++) {
-        const unsigned m = __ballot_sync(0xffffffffu, code == c);
-        if (lane == c) mycount += __popc(m);
-      }
-    }
-    int incl = mycount;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    int mybase = incl - mycount;
-    if (lane <= nc) w.seg[lane] = (lane < nc) ? mybase : n;
-    for (int base = 0; base < n; base += 32) {
-      const int t = base + lane;
-      int code = -1;
-      double x = 0, y = 0, z = 0;
-      if (t < n) { x = gx[t]; y = gy[t]; z = gz[t]; code = gc[t]; }
-      int pos = -1;
-      for (int c = 0; c < nc; c++) {
-        const unsigned m = __ballot_sync(0xffffffffu, code == c);
-        const int b = __shfl_sync(0xffffffffu, mybase, c);
-        if (code == c) pos = b + __popc(m & lt);
-        if (lane == c) mybase += __popc(m);
-      }
-      if (pos >= 0) { w.ux[pos] = x; w.uy[pos] = y; w.uz[pos] = z; }
-    }
-    __syncwarp();
-  }
-  return n;
 }
 
 // per-neighbour factor fc(r) exp(-eta r^2) (0 beyond rc) for one (rc, eta)
@@ -189,77 +122,258 @@ __device__ __forceinline__ void lean_tri_decode(int p, int &j, int &k) {
   j = p - tri; k = kk;
 }
 
-template <typename real, int NL, int NC, int PATH, bool SORTED>
+// Sums of the M per-lane partial values over the LPA lanes of each group through the warp-wide
+// scratch red[M][33] (column = lane: conflict-free stores; lane (g, sl) then reads rows sl, sl + LPA, ...
+// over its group's columns, bank (row + column) mod 16: conflict-free as well).
+//   M >= LPA: lane sl returns the totals of rows sl + i LPA in out[i], i < M / LPA
+//   M <  LPA: LPA / M lanes share row sl % M (M columns each, combined by xor shuffles), total in out[0]
+template <int M, int LPA>
+__device__ __forceinline__ void lean_group_reduce(const double (&v)[M], int lane, double *__restrict__ red,
+                                                  double (&out)[(M >= LPA ? M / LPA : 1)]) {
+  const int sl = lane & (LPA - 1), gcol = lane & ~(LPA - 1);
+  __syncwarp();
+#pragma unroll
+  for (int f = 0; f < M; f++) red[f * FNET_RED_STRIDE + lane] = v[f];
+  __syncwarp();
+  if (M >= LPA) {
+#pragma unroll
+    for (int i = 0; i < (M >= LPA ? M / LPA : 1); i++) {
+      const double *rp = red + (sl + i * LPA) * FNET_RED_STRIDE + gcol;
+      double r = 0.0;
+#pragma unroll
+      for (int c = 0; c < LPA; c++) r += rp[c];
+      out[i] = r;
+    }
+  } else {
+    const int row = sl & (M - 1), part = sl / M;
+    const double *rp = red + row * FNET_RED_STRIDE + gcol + part * M;
+    double r = 0.0;
+#pragma unroll
+    for (int c = 0; c < M; c++) r += rp[c];
+#pragma unroll
+    for (int off = M; off < LPA; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    out[0] = r;
+  }
+}
+
+// One angular pass over the pairs of (l1, l2).  KIND 0: identical lists, strict triangle through the
+// pair table; 1: identical lists, computed triangle index (lists longer than the table); 2: two lists.
+template <int NL, int NC, int LPA, bool SORTED, int KIND>
+__device__ __forceinline__ void lean_pair_loop(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
+                                               const NbList &l1, const NbList &l2, int n1, int n2, int m0,
+                                               const double (&lam)[NL], const double *__restrict__ pt,
+                                               const LeanTables &lt, int sl) {
+  const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
+  const float invW = (KIND == 2 && n2 > 0) ? 1.0f / (float)n2 : 0.0f;
+  for (int p0 = 0; p0 < nP; p0 += LPA) {
+    const int p = min(p0 + sl, nP);              // p = nP: (0, n1) resp. (n1, 0) -> the dummy neighbour
+    int j, k;
+    if (KIND == 0) { const unsigned jk = __ldg(&lt.pairtab[p]); j = jk & 255; k = jk >> 8; }
+    else if (KIND == 1) lean_tri_decode(p, j, k);
+    else {
+      j = (int)(((float)p + 0.5f) * invW);
+      if (j * n2 > p) j--;
+      else if ((j + 1) * n2 <= p) j++;
+      k = p - j * n2;
+    }
+    const int a = SORTED ? list_at(l1, j) : j, b = SORTED ? list_at(l2, k) : k;
+    const double2 a0 = *(const double2 *)(rec + 6 * a), a1 = *(const double2 *)(rec + 6 * a + 2);
+    const double2 b0 = *(const double2 *)(rec + 6 * b), b1 = *(const double2 *)(rec + 6 * b + 2);
+    const double base = a1.y * b1.y;
+    double c = a0.x * b0.x;                      // d_a . d_b / (r_a r_b + 1e-13), acsf.F90:1173-1174 (header comment)
+    c = fma(a0.y, b0.y, c);
+    c = fma(a1.x, b1.x, c);
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const double bb = fma(lam[l], c, 1.0);
+      const double q = lean_pow(bb, pt, lt);
+      double pw = bb * base;
+      const double q2 = q * q, q4 = q2 * q2;
+      if (m0 > 0) {                              // later 8 NC-function blocks of a long ladder: b q^m0, m0 a multiple of 8
+        double qm = 1.0, qb = q4 * q4;
+        for (int t = m0 >> 3; t; t >>= 1) { if (t & 1) qm *= qb; qb *= qb; }
+        pw *= qm;
+      }
+#pragma unroll
+      for (int ch = 0; ch < NC; ch++) {
+        lean_ladder8(&acc[(l * NC + ch) * FNET_LADDER], pw, q, q2, q4);
+        if (ch + 1 < NC) pw = (pw * q4) * q4;
+      }
+    }
+  }
+}
+
+template <int NL, int NC, int PATH, bool SORTED, int G>
 __global__ void __launch_bounds__(128, (NL * NC <= 2 ? 5 : 3))
 k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, LeanTables lt, int cap,
-            int capC, real *__restrict__ feat, int nFeat, const double *__restrict__ zprec, int nExtSel,
+            int capC, void *__restrict__ featv, int f32, int nFeat, const double *__restrict__ zprec, int nExtSel,
             const int *__restrict__ extIdx, int *__restrict__ flags) {
   constexpr int M = NL * NC * FNET_LADDER;          // accumulators per lane
+  constexpr int LPA = 32 / G;                       // lanes per central atom
+  constexpr int RA = M >= LPA ? M / LPA : 1;        // finished angular values per lane after a reduction
+  constexpr int RR = FNET_RCHUNK >= LPA ? FNET_RCHUNK / LPA : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int grp = lane / LPA, sl = lane & (LPA - 1), gshift = grp * LPA;
+  const unsigned lowmask = LPA == 32 ? 0xffffffffu : ((1u << LPA) - 1u);
+  const unsigned ltmask = (1u << sl) - 1u;
   CtaGeom cg;
   unsigned char *wbase;
   if (!acsf_cta_prologue<PATH>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;
   const int F = tab.F, Fp = (F + 1) & ~1;
   double *pt = (double *)wbase;                     // power tables
   double *zmu = pt + FNET_POW_DOUBLES, *zis = zmu + Fp;
+  unsigned char *zcode = (unsigned char *)(zis + Fp);   // atomic number -> species code (SORTED)
   for (int e = threadIdx.x; e < FNET_POW_DOUBLES; e += blockDim.x) pt[e] = lt.powtab[e];
   for (int a = threadIdx.x; a < F; a += blockDim.x) {
     double mu = 0.0, is = 1.0;
     if (zprec) { const double sg = zprec[F + a]; if (!(sg < 1e-08)) { mu = zprec[a]; is = 1.0 / sg; } }   // acsf.F90:505-507
     zmu[a] = mu; zis[a] = is;
   }
+  if (SORTED) for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
   __syncthreads();
   wbase += lean_cta_extra_bytes(F);
   const int a0 = cg.a0, a1 = cg.a1;
-  LeanWarp w = lean_carve(wbase + (size_t)wib * lean_warp_smem_bytes(cap, F, lt.redRows), cap, F);
+  const size_t gbytes = lean_group_bytes(cap, F, SORTED);
+  unsigned char *wb = wbase + (size_t)wib * lean_warp_smem_bytes(cap, F, lt.redRows, SORTED, G);
+  unsigned char *gb = wb + (size_t)grp * gbytes;
+  double *rec = (double *)gb;                                        // [cap][6]: u'_x, u'_y | u'_z, fc E | r, fc
+  double *gx = rec + 6 * cap, *gy = gx + cap, *gz = gy + cap;        // SORTED: unsorted displacements
+  int *gc = (int *)(gz + cap);                                       //         and species codes
+  int *seg = SORTED ? gc + cap : (int *)(rec + 6 * cap);
+  double *outv = (double *)(seg + ((FNET_MAX_CODES + 4 + 3) & ~3));
+  double *red = (double *)(wb + (size_t)G * gbytes);
   const double *ftab = cg.ftab;
-  const double sq13 = 3.1622776601683794e-07;       // sqrt(1e-13)
   int nmaxW = 0;
-  for (int slot = a0 + wib; slot < a1; slot += nw) {
-    const CRec me = central_atom<PATH>(cg, slot);
+  for (int s0 = a0 + wib * G; s0 < a1; s0 += nw * G) {
+    const int slot = s0 + grp;
+    bool act = slot < a1;
+    const CRec me = central_atom<PATH>(cg, act ? slot : a0);
     const int i = me.idx;
-    const int n = lean_gather<PATH, SORTED>(me, cg, tab, cap, w);
-    if (n < 0) { if (lane == 0) atomicMax(&flags[1], -n); continue; }
+    // ---------------- neighbours of each group's central atom: candidates -> compacted displacements ----------------
+    int n = 0;
+    {
+      const double rc2 = tab.rcMax * tab.rcMax;
+      const bool per = PATH == FNET_PATH_STRUCT && cg.sg->periodic != 0;
+      const bool diag = PATH == FNET_PATH_STRUCT && cg.sg->diag != 0;
+      const StructGeom *__restrict__ sg = cg.sg;
+      for (int base = 0; base < cg.nCand; base += LPA) {
+        const int t = base + sl;
+        const bool valid = act && t < cg.nCand;
+        CRec r;
+        r.x = me.x; r.y = me.y; r.z = me.z; r.idx = -1; r.zs = 0;
+        if (valid) r = cg.cand[t];
+        double dx = r.x - me.x, dy = r.y - me.y, dz = r.z - me.z;
+        if (PATH == FNET_PATH_STRUCT) {                      // minimum image (cells.cuh for_each_candidate_struct)
+          const double magic = 6755399441055744.0;
+          if (diag) {
+            const double n0 = (sg->inv[0] * dx + magic) - magic;
+            const double n1 = (sg->inv[4] * dy + magic) - magic;
+            const double n2 = (sg->inv[8] * dz + magic) - magic;
+            dx -= n0 * sg->lat[0]; dy -= n1 * sg->lat[4]; dz -= n2 * sg->lat[8];
+          } else if (per) {
+            const double n0 = (sg->inv[0] * dx + sg->inv[1] * dy + sg->inv[2] * dz + magic) - magic;
+            const double n1 = (sg->inv[3] * dx + sg->inv[4] * dy + sg->inv[5] * dz + magic) - magic;
+            const double n2 = (sg->inv[6] * dx + sg->inv[7] * dy + sg->inv[8] * dz + magic) - magic;
+            dx -= n0 * sg->lat[0] + n1 * sg->lat[3] + n2 * sg->lat[6];
+            dy -= n0 * sg->lat[1] + n1 * sg->lat[4] + n2 * sg->lat[7];
+            dz -= n0 * sg->lat[2] + n1 * sg->lat[5] + n2 * sg->lat[8];
+          }
+        }
+        const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, i);
+        const unsigned mg = (__ballot_sync(0xffffffffu, ok) >> gshift) & lowmask;
+        const int pos = n + __popc(mg & ltmask);
+        if (ok && pos < cap - 1) {
+          if (SORTED) {
+            gx[pos] = dx; gy[pos] = dy; gz[pos] = dz;
+            gc[pos] = (r.idx == i) ? tab.nCodes + 1 : (int)zcode[(r.zs & ~FNET_SHIFT_FLAG) & 127];
+          } else {
+            rec[6 * pos] = dx; rec[6 * pos + 1] = dy; rec[6 * pos + 2] = dz;
+          }
+        }
+        n += __popc(mg);
+      }
+    }
+    if (n > cap - 1) {                                       // one slot is the dummy neighbour
+      if (sl == 0) atomicMax(&flags[1], n + 1);
+      act = false; n = 0;
+    }
     nmaxW = max(nmaxW, n);
-    // ---------------- per-neighbour quantities; entry n is the dummy neighbour ----------------
-    for (int t = lane; t <= n; t += 32) {
-      double ux = 0.0, uy = 0.0, uz = 0.0, ww = 0.0, fe = 0.0, rr = 2.0 * tab.rcMax, fc = 0.0;
+    __syncwarp();
+    if (SORTED) {   // stable counting sort by species code: [code 0 .. | other | self-images] (acsf.F90:754-760)
+      const int nc = tab.nCodes + 2;
+      int nAll = n;
+#pragma unroll
+      for (int o = 16; o >= LPA; o >>= 1) nAll = max(nAll, __shfl_xor_sync(0xffffffffu, nAll, o));
+      int mycount = 0;
+      for (int base = 0; base < nAll; base += LPA) {
+        const int t = base + sl;
+        const int code = (t < n) ? gc[t] : -1;
+        for (int c = 0; c < nc; c++) {
+          const unsigned mg = (__ballot_sync(0xffffffffu, code == c) >> gshift) & lowmask;
+          if (sl == c) mycount += __popc(mg);
+        }
+      }
+      int incl = mycount;
+#pragma unroll
+      for (int o = 1; o < LPA; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o, LPA); if (sl >= o) incl += y; }
+      int mybase = incl - mycount;
+      if (sl < nc) seg[sl] = mybase;
+      if (sl == 0) seg[nc] = n;
+      for (int base = 0; base < nAll; base += LPA) {
+        const int t = base + sl;
+        int code = -1;
+        double x = 0, y = 0, z = 0;
+        if (t < n) { x = gx[t]; y = gy[t]; z = gz[t]; code = gc[t]; }
+        int pos = -1;
+        for (int c = 0; c < nc; c++) {
+          const unsigned mg = (__ballot_sync(0xffffffffu, code == c) >> gshift) & lowmask;
+          const int b = __shfl_sync(0xffffffffu, mybase, c, LPA);
+          if (code == c) pos = b + __popc(mg & ltmask);
+          if (sl == c) mybase += __popc(mg);
+        }
+        if (pos >= 0) { rec[6 * pos] = x; rec[6 * pos + 1] = y; rec[6 * pos + 2] = z; }
+      }
+      __syncwarp();
+    }
+    // ---------------- per-neighbour record; entry n is the dummy neighbour ----------------
+    for (int t = sl; t <= n; t += LPA) {
+      double ux = 0.0, uy = 0.0, uz = 0.0, fe = 0.0, rr = 2.0 * tab.rcMax, fc = 0.0;
       if (t < n) {
-        const double dx = w.ux[t], dy = w.uy[t], dz = w.uz[t];
+        const double dx = rec[6 * t], dy = rec[6 * t + 1], dz = rec[6 * t + 2];
         double ri;
         lean_rsqrt(dx * dx + dy * dy + dz * dz, ri, rr);   // dynneighlist.F90:311
-        ux = dx * ri; uy = dy * ri; uz = dz * ri;          // acsf.F90:1565
-        ww = ri * sq13;
+        const double sc = ri * fma(ri * ri, -0.5e-13, 1.0);  // u (1 - eps / 2), eps = 1e-13 / r^2
+        ux = dx * sc; uy = dy * sc; uz = dz * sc;          // acsf.F90:1565
         fe = lean_fce(rr, lt.rcShared, lt.invrcShared, lt.etaShared, ftab, fc);
       }
-      w.ux[t] = ux; w.uy[t] = uy; w.uz[t] = uz; w.w[t] = ww; w.fcE[t] = fe; w.r[t] = rr; w.fc[t] = fc;
+      *(double2 *)(rec + 6 * t) = make_double2(ux, uy);
+      *(double2 *)(rec + 6 * t + 2) = make_double2(uz, fe);
+      *(double2 *)(rec + 6 * t + 4) = make_double2(rr, fc);
     }
-    if (!SORTED && lane == 0) { w.seg[0] = 0; w.seg[1] = n; w.seg[2] = n; }
     __syncwarp();
-    // ---------------- radial ladder groups (acsf.F90:1287-1373) ----------------
+    // ---------------- radial ladder groups (acsf.F90:1287-1373): lanes = neighbours, 8 functions per sweep ----------------
     for (int g = 0; g < lt.nRadial; g++) {
-      const LeanRadial *__restrict__ G = &lt.rad[g];
-      const int nch = G->nch, lgn = G->lgn, fCnt = G->fCnt;
-      const NbList l = lean_list(tab, w.seg, SORTED ? G->code : -1, n);
+      const LeanRadial *__restrict__ R = &lt.rad[g];
+      const int fCnt = R->fCnt;
+      const NbList l = lean_list(tab, seg, SORTED ? R->code : -1, n);
       const int nl = l.n0 + l.n1;
-      const int per = 32 >> lgn;
-      const int mychunk = lane & (nch - 1), sub = lane >> lgn;
-      const int fcnt = min(max(fCnt - mychunk * FNET_RCHUNK, 0), FNET_RCHUNK);
-      const double rc = G->rc, invrc = G->invrc, eta = G->eta, drs = G->drs;
-      const double rsf = G->rs0 + (double)(mychunk * FNET_RCHUNK) * drs;
-      const bool shared = G->sharedFc != 0;
-      double acc[FNET_RCHUNK], kk[FNET_RCHUNK - 1];
+      const double rc = R->rc, invrc = R->invrc, eta = R->eta, drs = R->drs, rs0 = R->rs0;
+      const bool shared = R->sharedFc != 0;
+      double kk[FNET_RCHUNK - 1];
 #pragma unroll
-      for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
+      for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = R->kk[m];
+      for (int ch = 0; ch * FNET_RCHUNK < fCnt; ch++) {
+        const double rsf = rs0 + (double)(ch * FNET_RCHUNK) * drs;
+        double acc[FNET_RCHUNK];
 #pragma unroll
-      for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = G->kk[m];
-      if (fcnt > 0)
-        for (int t = sub; t < nl; t += per) {
+        for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
+        for (int t = sl; t < nl; t += LPA) {
           const int a = SORTED ? list_at(l, t) : t;
-          const double rr = w.r[a];
-          const double fc = shared ? w.fc[a] : ((rr > rc) ? 0.0 : cutoff_fn(rr, 1.0, invrc));
+          const double2 rf = *(const double2 *)(rec + 6 * a + 4);
+          const double rr = rf.x;
+          const double fc = shared ? rf.y : ((rr > rc) ? 0.0 : cutoff_fn(rr, 1.0, invrc));
           const double u = rr - rsf;
           const double e0 = eta * u * u, a1 = 2.0 * eta * drs * u;
           if (e0 < 690.0 && fabs(a1) < 690.0) {         // g_0 and the ratio stay normal numbers
@@ -278,96 +392,85 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
             }
           }
         }
-      const double v = reduce_smem<FNET_RCHUNK>(acc, lane, nch, w.red);
-      const int f = (lane >> lgn) & (FNET_RCHUNK - 1);
-      if (lane < nch * FNET_RCHUNK && f < fcnt) w.outv[tab.rfeat[G->fBeg + mychunk * FNET_RCHUNK + f]] = v;
+        double v[RR];
+        lean_group_reduce<FNET_RCHUNK, LPA>(acc, lane, red, v);
+#pragma unroll
+        for (int q = 0; q < RR; q++) {
+          const int f = ch * FNET_RCHUNK + (FNET_RCHUNK >= LPA ? sl + q * LPA : sl);
+          if ((FNET_RCHUNK >= LPA || sl < FNET_RCHUNK) && f < fCnt) outv[tab.rfeat[R->fBeg + f]] = v[q];
+        }
+      }
     }
     // ---------------- angular passes (acsf.F90:1377-1492) ----------------
     for (int pi_ = 0; pi_ < lt.nPasses; pi_++) {
       const LeanPass *__restrict__ P = &lt.pass[pi_];
       const int same = P->same, m0 = P->m0;
-      const NbList l1 = lean_list(tab, w.seg, SORTED ? P->code1 : -1, n);
-      const NbList l2 = (!SORTED || same) ? l1 : lean_list(tab, w.seg, P->code2, n);
+      const NbList l1 = lean_list(tab, seg, SORTED ? P->code1 : -1, n);
+      const NbList l2 = (!SORTED || same) ? l1 : lean_list(tab, seg, P->code2, n);
       const int n1 = l1.n0 + l1.n1, n2 = l2.n0 + l2.n1;
       __syncwarp();
       if (P->recomp) {
         const double rc = P->rc, invrc = P->invrc, eta = P->eta;
-        for (int t = lane; t < n; t += 32) { double fc; w.fcE[t] = lean_fce(w.r[t], rc, invrc, eta, ftab, fc); }
+        for (int t = sl; t < n; t += LPA) { double fc; rec[6 * t + 3] = lean_fce(rec[6 * t + 4], rc, invrc, eta, ftab, fc); }
         __syncwarp();
       }
-      // prefetch the epilogue's per-function constants (lane e of the pass)
-      const int e = lane & (M - 1);
-      const int ofeat = __ldg(&P->feat[e]);
-      const double opref = __ldg(&P->pref[e]), odA = __ldg(&P->dA[e]), odB = __ldg(&P->dB[e]);
       double lam[NL];
 #pragma unroll
       for (int l = 0; l < NL; l++) lam[l] = P->lam[l];
       double acc[M];
 #pragma unroll
       for (int f = 0; f < M; f++) acc[f] = 0.0;
-      const int nP = same ? (n1 * (n1 - 1)) >> 1 : n1 * n2;
-      const float invW = n2 > 0 ? 1.0f / (float)n2 : 0.0f;
-      const bool useTab = same && n1 <= FNET_PAIR_TAB_MAXN;
-      for (int p0 = 0; p0 < nP; p0 += 32) {
-        const int p = min(p0 + lane, nP);            // p = nP: (0, n1) resp. (n1, 0) -> the dummy neighbour
-        int j, k;
-        if (same) {
-          if (useTab) { const unsigned jk = __ldg(&lt.pairtab[p]); j = jk & 255; k = jk >> 8; }
-          else lean_tri_decode(p, j, k);
-        } else {
-          j = (int)(((float)p + 0.5f) * invW);
-          if (j * n2 > p) j--;
-          else if ((j + 1) * n2 <= p) j++;
-          k = p - j * n2;
-        }
-        const int a = SORTED ? list_at(l1, j) : j, b = SORTED ? list_at(l2, k) : k;
-        const double base = w.fcE[a] * w.fcE[b];
-        double dot = w.ux[a] * w.ux[b];
-        dot = fma(w.uy[a], w.uy[b], dot);
-        dot = fma(w.uz[a], w.uz[b], dot);
-        const double c = fma(-dot, w.w[a] * w.w[b], dot);   // dot / (r_a r_b + 1e-13), acsf.F90:1173-1174
+      if (same) {
+        int nmaxG = n1;                              // the table covers lists of <= FNET_PAIR_TAB_MAXN neighbours: warp-uniform choice
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-          const double bb = fma(lam[l], c, 1.0);
-          const double q = lean_pow(bb, pt, lt);
-          double pw = bb * base;
-          const double q2 = q * q, q4 = q2 * q2;
-          if (m0 > 0) {                                      // later 8 NC-function blocks of a long ladder: b q^m0
-            double qm = 1.0, qb = q4 * q4;                   // m0 is a multiple of 8
-            for (int t = m0 >> 3; t; t >>= 1) { if (t & 1) qm *= qb; qb *= qb; }
-            pw *= qm;
-          }
-#pragma unroll
-          for (int ch = 0; ch < NC; ch++) {
-            lean_ladder8(&acc[(l * NC + ch) * FNET_LADDER], pw, q, q2, q4);
-            if (ch + 1 < NC) pw = (pw * q4) * q4;
-          }
-        }
+        for (int o = 16; o > 0; o >>= 1) nmaxG = max(nmaxG, __shfl_xor_sync(0xffffffffu, nmaxG, o));
+        if (nmaxG <= FNET_PAIR_TAB_MAXN) lean_pair_loop<NL, NC, LPA, SORTED, 0>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
+        else lean_pair_loop<NL, NC, LPA, SORTED, 1>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
+      } else {
+        lean_pair_loop<NL, NC, LPA, SORTED, 2>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
       }
-      // diagonal of identical lists: S0 = sum fcE^2, S1 = sum fcE^2 eps, eps = 1e-13 / r^2
+      // diagonal of identical lists: S0 = sum fcE^2, S1 = sum fcE^2 eps, eps = 1e-13 / r^2 (a 1e-14 correction: FP32 reciprocal)
       double S0 = 0.0, S1 = 0.0;
       if (same) {
-        for (int t = lane; t < n1; t += 32) {
+        for (int t = sl; t < n1; t += LPA) {
           const int a = SORTED ? list_at(l1, t) : t;
-          const double fe = w.fcE[a], ww = w.w[a];
+          const double fe = rec[6 * a + 3], rr = rec[6 * a + 4];
           const double e2 = fe * fe;
-          S0 += e2; S1 = fma(e2, ww * ww, S1);
+          const float rf = (float)rr;
+          S0 += e2; S1 = fma(e2, (double)__fdividef(1e-13f, rf * rf), S1);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = LPA / 2; o > 0; o >>= 1) {
           S0 += __shfl_xor_sync(0xffffffffu, S0, o);
           S1 += __shfl_xor_sync(0xffffffffu, S1, o);
         }
       }
-      const double v = reduce_smem<M>(acc, lane, 1, w.red);
-      if (lane < M && ofeat >= 0) w.outv[ofeat] = fma(opref, v, fma(odA, S0, odB * S1));
+      double v[RA];
+      lean_group_reduce<M, LPA>(acc, lane, red, v);
+#pragma unroll
+      for (int q = 0; q < RA; q++) {
+        const int e = M >= LPA ? sl + q * LPA : (sl & (M - 1));
+        const int ofeat = __ldg(&P->feat[e]);
+        if ((M >= LPA || sl < M) && ofeat >= 0)
+          outv[ofeat] = fma(__ldg(&P->pref[e]), v[q], fma(__ldg(&P->dA[e]), S0, __ldg(&P->dB[e]) * S1));
+      }
     }
     __syncwarp();
-    // ---------------- coalesced feature write (+ z-score, + external features) ----------------
-    real *out = feat + (size_t)nFeat * i;
-    for (int a = lane; a < F; a += 32) out[a] = (real)((w.outv[a] - zmu[a]) * zis[a]);
-    for (int e = lane; e < nExtSel; e += 32) out[F + e] = (real)ext[(size_t)nExt * i + extIdx[e]];
+    // ---------------- feature row write (+ z-score, + external features) ----------------
+    if (act) {
+      if (f32) {
+        float *out = (float *)featv + (size_t)nFeat * i;
+        for (int a = sl; a < F; a += LPA) out[a] = (float)((outv[a] - zmu[a]) * zis[a]);
+        for (int e = sl; e < nExtSel; e += LPA) out[F + e] = (float)ext[(size_t)nExt * i + extIdx[e]];
+      } else {
+        double *out = (double *)featv + (size_t)nFeat * i;
+        for (int a = sl; a < F; a += LPA) out[a] = (outv[a] - zmu[a]) * zis[a];
+        for (int e = sl; e < nExtSel; e += LPA) out[F + e] = ext[(size_t)nExt * i + extIdx[e]];
+      }
+    }
     __syncwarp();
   }
+#pragma unroll
+  for (int o = 16; o >= LPA; o >>= 1) nmaxW = max(nmaxW, __shfl_xor_sync(0xffffffffu, nmaxW, o));
   if (lane == 0 && nmaxW > 0) atomicMax(&flags[0], nmaxW);   // exact capacity hint for the next launch
 }

@@ -529,7 +529,8 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       LeanTables &LT = ctx->lean;
       memset(&LT, 0, sizeof(LT));
       LT.nRadial = (int)lrad.size(); LT.nPasses = (int)lpass.size();
-      LT.redRows = std::max(FNET_LADDER * NL * NC, FNET_RCHUNK * maxChunks);
+      LT.redRows = std::max(FNET_LADDER * NL * NC, FNET_RCHUNK);
+      (void)maxChunks;
       if (!lpass.empty()) { LT.rcShared = lpass[0].rc; LT.etaShared = lpass[0].eta; }
       else { LT.rcShared = lrad.empty() ? rcMax : lrad[0].rc; LT.etaShared = 0.0; }
       LT.invrcShared = 1.0 / LT.rcShared;
@@ -722,7 +723,7 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
 }
 
 // launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
-struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; bool lean = false; };
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; bool lean = false; int G = 1; };
 // the whole-structure path (cells.cuh): small structures, lattice check passed so far
 static bool use_struct_path(const fnetgpu_ctx *ctx, const Slot &s) {
   return !ctx->acsfPathCells && s.structPath && s.maxAtoms <= FNET_STRUCT_MAX_ATOMS && s.d_coords && s.d_lat;
@@ -787,14 +788,22 @@ static bool use_lean(const fnetgpu_ctx *ctx) { return ctx->leanOK && !ctx->acsfG
 static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLaunch &L) {
   const AcsfTables &T = ctx->acsf;
   if (use_lean(ctx)) {
-    const int hint = s.maxNeigh > 0 ? s.maxNeigh : 32;   // + 1: the dummy neighbour of the pair walk
-    const int cap = structPath ? std::max(32, (std::min(hint, std::max(s.maxAtoms - 1, 1)) + 1 + 31) & ~31)
-                               : std::max(32, (s.maxNeigh + 1 + 31) & ~31);
-    AcsfLaunch Q;
-    const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows), extra = lean_cta_extra_bytes(T.F);
-    const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
-    if (rc == 0 && Q.path != FNET_PATH_DIRECT) { L = Q; L.lean = true; return 0; }
-    ctx->err.clear();
+    // capacity: neighbours + the dummy neighbour of the pair walk, in steps of 8; central atoms per warp from
+    // the neighbour count (FNETGPU_LEAN_G overrides: A/B)
+    int hint = s.maxNeigh > 0 ? s.maxNeigh : 32;
+    if (structPath) hint = std::min(hint, std::max(s.maxAtoms - 1, 1));
+    const int cap = std::max(8, (hint + 1 + 7) & ~7);
+    static const int gEnv = [] { const char *e = getenv("FNETGPU_LEAN_G"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
+    int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
+    if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
+    const size_t extra = lean_cta_extra_bytes(T.F);
+    for (; G >= 1; G >>= 1) {
+      AcsfLaunch Q;
+      const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows, ctx->leanSorted, G);
+      const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
+      if (rc == 0 && Q.path != FNET_PATH_DIRECT && Q.wpb == 4) { L = Q; L.lean = true; L.G = G; return 0; }
+      ctx->err.clear();
+    }
   }
   L.lean = false;
   if (structPath) return plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F, T.redRows), L);
@@ -922,15 +931,21 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
   if (L.lean) {
     const LeanTables &LT = ctx->lean;
-#define FNET_LEAN_LAUNCH(NL, NC, PATH, SORTED)                                                                 \
+    const int f32 = std::is_same<real, float>::value ? 1 : 0;
+#define FNET_LEAN_LAUNCH(NL, NC, PATH, SORTED, G)                                                              \
   do {                                                                                                         \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<real, NL, NC, PATH, SORTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
-    LAUNCH(ctx, K_ACSF, (k_acsf_lean<real, NL, NC, PATH, SORTED><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(  \
-                            L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, feat, nFeat, zp, nExtSel,    \
-                            ctx->d_extIdx, ctx->d_flags)));                                                    \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<NL, NC, PATH, SORTED, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF, (k_acsf_lean<NL, NC, PATH, SORTED, G><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(     \
+                            L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, (void *)feat, f32, nFeat, zp, \
+                            nExtSel, ctx->d_extIdx, ctx->d_flags)));                                           \
   } while (0)
 #define FNET_LEAN_LAUNCH_S(NL, NC, PATH)                                                                       \
-  do { if (ctx->leanSorted) FNET_LEAN_LAUNCH(NL, NC, PATH, true); else FNET_LEAN_LAUNCH(NL, NC, PATH, false); } while (0)
+  do {                                                                                                         \
+    if (ctx->leanSorted) { if (L.G == 2) FNET_LEAN_LAUNCH(NL, NC, PATH, true, 2); else FNET_LEAN_LAUNCH(NL, NC, PATH, true, 1); } \
+    else if (L.G == 4) FNET_LEAN_LAUNCH(NL, NC, PATH, false, 4);                                               \
+    else if (L.G == 2) FNET_LEAN_LAUNCH(NL, NC, PATH, false, 2);                                               \
+    else FNET_LEAN_LAUNCH(NL, NC, PATH, false, 1);                                                             \
+  } while (0)
 #define FNET_LEAN_LAUNCH_P(NL, NC)                                                                             \
   do { if (L.path == FNET_PATH_STRUCT) FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STRUCT); else FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STAGED); } while (0)
     if (ctx->leanNC == 1) FNET_LEAN_LAUNCH_P(2, 1);
