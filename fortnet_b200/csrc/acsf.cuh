@@ -76,16 +76,16 @@ struct CtaGeom {                      // per-CTA view produced by acsf_cta_prolo
 
 // Splits the CTA's bin (or structure) over blockIdx.y and stages the candidates.  Returns false
 // when this CTA has nothing to do (or on overflow, flagged for the host).
-template <int PATH>
+template <int PATH, bool EXPONLY = false>
 __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit, double rcMax, int capC,
                                                   unsigned char *smem_raw, int *__restrict__ flags, CtaGeom &c,
                                                   unsigned char *&wbase) {
   {   // tables first; the barriers of the staging below (or the explicit one of PATH 0) publish them
     double *ft = (double *)smem_raw;
-    for (int e = threadIdx.x; e < FNET_TAB_DOUBLES; e += blockDim.x)
+    for (int e = threadIdx.x; e < (EXPONLY ? FNET_EXP_TAB_N : FNET_TAB_DOUBLES); e += blockDim.x)
       ft[e] = e < FNET_EXP_TAB_N ? fnet_exp_tab_d[e] : fnet_log_tab_d[e - FNET_EXP_TAB_N];
     c.ftab = ft;
-    smem_raw += FNET_FTAB_BYTES;
+    smem_raw += EXPONLY ? FNET_EXP_TAB_N * sizeof(double) : FNET_FTAB_BYTES;
   }
   c.S = nullptr; c.cellStart = G.cellStart; c.crec = G.crec; c.cand = (const CRec *)smem_raw; c.nCand = 0; c.sg = nullptr;
   c.first = 0;

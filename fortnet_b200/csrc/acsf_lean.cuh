@@ -49,8 +49,21 @@ __host__ __device__ inline size_t lean_group_bytes(int cap, int F, bool sorted) 
 __host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows, bool sorted, int G) {
   return (size_t)G * lean_group_bytes(cap, F, sorted) + (((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15);
 }
-__host__ __device__ inline size_t lean_cta_extra_bytes(int F) {   // power tables + (mu, 1/sigma) + atomic number -> species code
-  return ((size_t)(FNET_POW_DOUBLES + 2 * ((F + 1) & ~1)) * sizeof(double) + 128 + 15) & ~(size_t)15;
+__host__ __device__ inline int lean_pair_entries(int cap) {        // staged part of the strict-triangle pair table
+  const int need = cap * (cap - 1) / 2 + 1;
+  return need < FNET_PAIR_TAB_N ? need : FNET_PAIR_TAB_N;
+}
+// power tables + (mu, 1/sigma) + atomic number -> species code + pass / radial tables + pair table
+__host__ __device__ inline size_t lean_cta_tables_bytes(int F, int cap, int stageBytes) {
+  size_t b = (size_t)(FNET_POW_DOUBLES + 2 * ((F + 1) & ~1)) * sizeof(double) + 128;
+  b += (size_t)((stageBytes + 15) & ~15);
+  b += ((size_t)lean_pair_entries(cap) * sizeof(unsigned short) + 15) & ~(size_t)15;
+  return (b + 15) & ~(size_t)15;
+}
+// what the CTA prefix grows by against k_acsf's: the tables above minus the log table, which the lean
+// kernel does not stage (acsf_cta_prologue<PATH, true>); may be "negative" (unsigned wrap-around is intended)
+__host__ __device__ inline size_t lean_cta_extra_bytes(int F, int cap, int stageBytes) {
+  return lean_cta_tables_bytes(F, cap, stageBytes) - 2 * FNET_LOG_TAB_N * sizeof(double);
 }
 
 // b^delta for b in [0, 2] (header comment); b <= 2^-62 (and a last-bit negative b) returns a finite
@@ -156,55 +169,83 @@ __device__ __forceinline__ void lean_group_reduce(const double (&v)[M], int lane
   }
 }
 
-// One angular pass over the pairs of (l1, l2).  KIND 0: identical lists, strict triangle through the
-// pair table; 1: identical lists, computed triangle index (lists longer than the table); 2: two lists.
-template <int NL, int NC, int LPA, bool SORTED, int KIND>
-__device__ __forceinline__ void lean_pair_loop(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
-                                               const NbList &l1, const NbList &l2, int n1, int n2, int m0,
-                                               const double (&lam)[NL], const double *__restrict__ pt,
-                                               const LeanTables &lt, int sl) {
-  const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
-  const float invW = (KIND == 2 && n2 > 0) ? 1.0f / (float)n2 : 0.0f;
-  for (int p0 = 0; p0 < nP; p0 += LPA) {
-    const int p = min(p0 + sl, nP);              // p = nP: (0, n1) resp. (n1, 0) -> the dummy neighbour
-    int j, k;
-    if (KIND == 0) { const unsigned jk = __ldg(&lt.pairtab[p]); j = jk & 255; k = jk >> 8; }
-    else if (KIND == 1) lean_tri_decode(p, j, k);
-    else {
-      j = (int)(((float)p + 0.5f) * invW);
-      if (j * n2 > p) j--;
-      else if ((j + 1) * n2 <= p) j++;
-      k = p - j * n2;
+// One pair of the angular pass: records a, b -> the NL x NC ladders
+template <int NL, int NC>
+__device__ __forceinline__ void lean_pair_eval(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec, int a, int b,
+                                               int m0, const double (&lam)[NL], const double *__restrict__ pt,
+                                               const LeanTables &lt) {
+  const double2 a0 = *(const double2 *)(rec + 6 * a), a1 = *(const double2 *)(rec + 6 * a + 2);
+  const double2 b0 = *(const double2 *)(rec + 6 * b), b1 = *(const double2 *)(rec + 6 * b + 2);
+  const double base = a1.y * b1.y;
+  double c = a0.x * b0.x;                      // d_a . d_b / (r_a r_b + 1e-13), acsf.F90:1173-1174 (header comment)
+  c = fma(a0.y, b0.y, c);
+  c = fma(a1.x, b1.x, c);
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double bb = fma(lam[l], c, 1.0);
+    const double q = lean_pow(bb, pt, lt);
+    double pw = bb * base;
+    const double q2 = q * q, q4 = q2 * q2;
+    if (m0 > 0) {                              // later 8 NC-function blocks of a long ladder: b q^m0, m0 a multiple of 8
+      double qm = 1.0, qb = q4 * q4;
+      for (int t = m0 >> 3; t; t >>= 1) { if (t & 1) qm *= qb; qb *= qb; }
+      pw *= qm;
     }
-    const int a = SORTED ? list_at(l1, j) : j, b = SORTED ? list_at(l2, k) : k;
-    const double2 a0 = *(const double2 *)(rec + 6 * a), a1 = *(const double2 *)(rec + 6 * a + 2);
-    const double2 b0 = *(const double2 *)(rec + 6 * b), b1 = *(const double2 *)(rec + 6 * b + 2);
-    const double base = a1.y * b1.y;
-    double c = a0.x * b0.x;                      // d_a . d_b / (r_a r_b + 1e-13), acsf.F90:1173-1174 (header comment)
-    c = fma(a0.y, b0.y, c);
-    c = fma(a1.x, b1.x, c);
 #pragma unroll
-    for (int l = 0; l < NL; l++) {
-      const double bb = fma(lam[l], c, 1.0);
-      const double q = lean_pow(bb, pt, lt);
-      double pw = bb * base;
-      const double q2 = q * q, q4 = q2 * q2;
-      if (m0 > 0) {                              // later 8 NC-function blocks of a long ladder: b q^m0, m0 a multiple of 8
-        double qm = 1.0, qb = q4 * q4;
-        for (int t = m0 >> 3; t; t >>= 1) { if (t & 1) qm *= qb; qb *= qb; }
-        pw *= qm;
-      }
-#pragma unroll
-      for (int ch = 0; ch < NC; ch++) {
-        lean_ladder8(&acc[(l * NC + ch) * FNET_LADDER], pw, q, q2, q4);
-        if (ch + 1 < NC) pw = (pw * q4) * q4;
-      }
+    for (int ch = 0; ch < NC; ch++) {
+      lean_ladder8(&acc[(l * NC + ch) * FNET_LADDER], pw, q, q2, q4);
+      if (ch + 1 < NC) pw = (pw * q4) * q4;
     }
   }
 }
 
+// pair index -> neighbour slots.  KIND 0: identical lists, strict triangle through the pair table;
+// 1: identical lists, computed triangle index (lists longer than the table); 2: two lists.
+template <bool SORTED, int KIND>
+__device__ __forceinline__ void lean_pair_index(int p, const unsigned short *__restrict__ ptab, const NbList &l1, const NbList &l2,
+                                                int n2, float invW, int &a, int &b) {
+  int j, k;
+  if (KIND == 0) { const unsigned jk = ptab[p]; j = jk & 255; k = jk >> 8; }
+  else if (KIND == 1) lean_tri_decode(p, j, k);
+  else {
+    j = (int)(((float)p + 0.5f) * invW);
+    if (j * n2 > p) j--;
+    else if ((j + 1) * n2 <= p) j++;
+    k = p - j * n2;
+  }
+  a = SORTED ? list_at(l1, j) : j; b = SORTED ? list_at(l2, k) : k;
+}
+
+// pairs per lane and loop iteration for the 16-accumulator shapes: two independent pairs hide the latency of the
+// dependent table-lookup / DFMA chains at 16 resident warps per SM (measured on C2 / C3: 0.91 -> 0.83 ms,
+// 18.4 -> 16.7 ms with 128 registers and 4 CTAs per SM; 5 CTAs at 96 registers spill and lose)
+#ifndef FNET_LEAN_UNROLL
+#define FNET_LEAN_UNROLL 2
+#endif
+// One angular pass over the pairs of (l1, l2); index p = nP maps to (0, n1) resp. (n1, 0): the dummy neighbour
+template <int NL, int NC, int LPA, bool SORTED, int KIND>
+__device__ __forceinline__ void lean_pair_loop(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
+                                               const NbList &l1, const NbList &l2, int n1, int n2, int m0,
+                                               const double (&lam)[NL], const double *__restrict__ pt,
+                                               const unsigned short *__restrict__ ptab, const LeanTables &lt, int sl) {
+  const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
+  const float invW = (KIND == 2 && n2 > 0) ? 1.0f / (float)n2 : 0.0f;
+  constexpr int U = NL * NC <= 2 ? FNET_LEAN_UNROLL : 1;
+  for (int p0 = 0; p0 < nP; p0 += U * LPA) {
+    int a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      lean_pair_index<SORTED, KIND>(min(p0 + u * LPA + sl, nP), ptab, l1, l2, n2, invW, a[u], b[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++) lean_pair_eval<NL, NC>(acc, rec, a[u], b[u], m0, lam, pt, lt);
+  }
+}
+
+#ifndef FNET_LEAN_MINB
+#define FNET_LEAN_MINB 4
+#endif
 template <int NL, int NC, int PATH, bool SORTED, int G>
-__global__ void __launch_bounds__(128, (NL * NC <= 2 ? 5 : 3))
+__global__ void __launch_bounds__(128, (NL * NC <= 2 ? FNET_LEAN_MINB : 3))
 k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, LeanTables lt, int cap,
             int capC, void *__restrict__ featv, int f32, int nFeat, const double *__restrict__ zprec, int nExtSel,
             const int *__restrict__ extIdx, int *__restrict__ flags) {
@@ -220,7 +261,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   const unsigned ltmask = (1u << sl) - 1u;
   CtaGeom cg;
   unsigned char *wbase;
-  if (!acsf_cta_prologue<PATH>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;
+  if (!acsf_cta_prologue<PATH, true>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;   // exp table only
   const int F = tab.F, Fp = (F + 1) & ~1;
   double *pt = (double *)wbase;                     // power tables
   double *zmu = pt + FNET_POW_DOUBLES, *zis = zmu + Fp;
@@ -232,8 +273,26 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     zmu[a] = mu; zis[a] = is;
   }
   if (SORTED) for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
+  // pass / radial tables (when small) and the used part of the pair table: shared-memory latency instead of L1's
+  unsigned char *stage = zcode + 128;
+  const LeanPass *passes = lt.pass;
+  const LeanRadial *rads = lt.rad;
+  if (lt.stageBytes > 0) {
+    const int nw8 = lt.stageBytes >> 3, np8 = (int)((lt.nPasses * sizeof(LeanPass)) >> 3);
+    double *dst = (double *)stage;
+    const double *srcP = (const double *)lt.pass, *srcR = (const double *)lt.rad;
+    for (int e = threadIdx.x; e < nw8; e += blockDim.x) dst[e] = e < np8 ? srcP[e] : srcR[e - np8];
+    passes = (const LeanPass *)stage;
+    rads = (const LeanRadial *)(stage + (size_t)np8 * 8);
+  }
+  unsigned short *ptab = (unsigned short *)(stage + ((lt.stageBytes + 15) & ~15));
+  {
+    const int ne2 = (lean_pair_entries(cap) + 1) >> 1;                 // 32-bit copies
+    const unsigned *src = (const unsigned *)lt.pairtab;
+    for (int e = threadIdx.x; e < ne2; e += blockDim.x) ((unsigned *)ptab)[e] = src[e];
+  }
   __syncthreads();
-  wbase += lean_cta_extra_bytes(F);
+  wbase += lean_cta_tables_bytes(F, cap, lt.stageBytes);
   const int a0 = cg.a0, a1 = cg.a1;
   const size_t gbytes = lean_group_bytes(cap, F, SORTED);
   unsigned char *wb = wbase + (size_t)wib * lean_warp_smem_bytes(cap, F, lt.redRows, SORTED, G);
@@ -355,7 +414,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     __syncwarp();
     // ---------------- radial ladder groups (acsf.F90:1287-1373): lanes = neighbours, 8 functions per sweep ----------------
     for (int g = 0; g < lt.nRadial; g++) {
-      const LeanRadial *__restrict__ R = &lt.rad[g];
+      const LeanRadial *__restrict__ R = &rads[g];
       const int fCnt = R->fCnt;
       const NbList l = lean_list(tab, seg, SORTED ? R->code : -1, n);
       const int nl = l.n0 + l.n1;
@@ -403,7 +462,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     }
     // ---------------- angular passes (acsf.F90:1377-1492) ----------------
     for (int pi_ = 0; pi_ < lt.nPasses; pi_++) {
-      const LeanPass *__restrict__ P = &lt.pass[pi_];
+      const LeanPass *__restrict__ P = &passes[pi_];
       const int same = P->same, m0 = P->m0;
       const NbList l1 = lean_list(tab, seg, SORTED ? P->code1 : -1, n);
       const NbList l2 = (!SORTED || same) ? l1 : lean_list(tab, seg, P->code2, n);
@@ -424,10 +483,10 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         int nmaxG = n1;                              // the table covers lists of <= FNET_PAIR_TAB_MAXN neighbours: warp-uniform choice
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nmaxG = max(nmaxG, __shfl_xor_sync(0xffffffffu, nmaxG, o));
-        if (nmaxG <= FNET_PAIR_TAB_MAXN) lean_pair_loop<NL, NC, LPA, SORTED, 0>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
-        else lean_pair_loop<NL, NC, LPA, SORTED, 1>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
+        if (nmaxG <= FNET_PAIR_TAB_MAXN) lean_pair_loop<NL, NC, LPA, SORTED, 0>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
+        else lean_pair_loop<NL, NC, LPA, SORTED, 1>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
       } else {
-        lean_pair_loop<NL, NC, LPA, SORTED, 2>(acc, rec, l1, l2, n1, n2, m0, lam, pt, lt, sl);
+        lean_pair_loop<NL, NC, LPA, SORTED, 2>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
       }
       // diagonal of identical lists: S0 = sum fcE^2, S1 = sum fcE^2 eps, eps = 1e-13 / r^2 (a 1e-14 correction: FP32 reciprocal)
       double S0 = 0.0, S1 = 0.0;
@@ -450,9 +509,8 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
 #pragma unroll
       for (int q = 0; q < RA; q++) {
         const int e = M >= LPA ? sl + q * LPA : (sl & (M - 1));
-        const int ofeat = __ldg(&P->feat[e]);
-        if ((M >= LPA || sl < M) && ofeat >= 0)
-          outv[ofeat] = fma(__ldg(&P->pref[e]), v[q], fma(__ldg(&P->dA[e]), S0, __ldg(&P->dB[e]) * S1));
+        const int ofeat = P->feat[e];
+        if ((M >= LPA || sl < M) && ofeat >= 0) outv[ofeat] = fma(P->pref[e], v[q], fma(P->dA[e], S0, P->dB[e] * S1));
       }
     }
     __syncwarp();

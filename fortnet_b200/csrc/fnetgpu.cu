@@ -530,6 +530,8 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       memset(&LT, 0, sizeof(LT));
       LT.nRadial = (int)lrad.size(); LT.nPasses = (int)lpass.size();
       LT.redRows = std::max(FNET_LADDER * NL * NC, FNET_RCHUNK);
+      { const size_t tb = lpass.size() * sizeof(LeanPass) + lrad.size() * sizeof(LeanRadial);
+        LT.stageBytes = tb <= 8192 ? (int)tb : 0; }
       (void)maxChunks;
       if (!lpass.empty()) { LT.rcShared = lpass[0].rc; LT.etaShared = lpass[0].eta; }
       else { LT.rcShared = lrad.empty() ? rcMax : lrad[0].rc; LT.etaShared = 0.0; }
@@ -547,7 +549,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
         pt[2 * i + 1] = (double)powl(1.0L / (long double)invc, (long double)leanDelta);
       }
       for (int k = FNET_POW_KMIN; k <= 1; k++) pt[2 * FNET_POW_TAB_N + (k - FNET_POW_KMIN)] = (double)powl(2.0L, (long double)k * (long double)leanDelta);
-      std::vector<unsigned short> pairs(FNET_PAIR_TAB_N);
+      std::vector<unsigned short> pairs(FNET_PAIR_TAB_N + 1);
       for (int k = 1; k <= FNET_PAIR_TAB_MAXN; k++)
         for (int j = 0; j < k; j++) {
           const int p = k * (k - 1) / 2 + j;
@@ -796,7 +798,7 @@ static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
     static const int gEnv = [] { const char *e = getenv("FNETGPU_LEAN_G"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
     int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
     if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
-    const size_t extra = lean_cta_extra_bytes(T.F);
+    const size_t extra = lean_cta_extra_bytes(T.F, cap, ctx->lean.stageBytes);
     for (; G >= 1; G >>= 1) {
       AcsfLaunch Q;
       const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows, ctx->leanSorted, G);

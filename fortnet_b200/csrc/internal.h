@@ -129,7 +129,8 @@ struct LeanTables {            // passed by value (kernel parameter space = cons
   const double *powtab;        // device: (1/c_i, c_i^delta) x 256, then 2^(k delta), k = KMIN .. 1
   const unsigned short *pairtab;   // device: p -> j | k << 8 of the strict triangle, entry p = k (k-1)/2 + j
   double powC[5];              // binom(delta, 1..5)
-  int redRows;                 // rows of the per-warp reduction scratch: max(8 NL NC, 8 * radial chunks)
+  int redRows;                 // rows of the per-warp reduction scratch: max(8 NL NC, 8)
+  int stageBytes;              // pass + radial tables are copied to shared memory per CTA when they are this small (else 0)
   double rcShared, invrcShared, etaShared;   // (rc, eta) of the per-neighbour factors formed right after the gather
 };
 
