@@ -63,6 +63,7 @@ class Context:
         self.n_atoms = {}
         self.n_struct = {}
         self.n_global = {}
+        self.n_out = None            # output width of the configured network (set by Bpnn)
 
     def _check(self, rc):
         if rc != 0:
@@ -95,9 +96,16 @@ class Context:
         self._check(self._lib.fnetgpu_coords_update(self._h, C.c_int(slot), _p(_d(coords)),
                                                     _p(_d(latvecs)) if latvecs is not None else None))
 
-    def socket_step(self, slot, coords, latvecs=None, n_out=1, forces=True):
+    def socket_step(self, slot, coords, latvecs=None, n_out=None, forces=True):
         """one MD / i-PI step (predictForSocketComm, fortnet.F90:503-609): new geometry in ->
-        (global predictions [nStruct, nOut], atomic predictions [N, nOut], forces [N, 3*nOut])"""
+        (global predictions [nStruct, nOut], atomic predictions [N, nOut], forces [N, 3*nOut]).
+        The buffers are sized from the network's output width (recorded by ``Bpnn``); a caller-supplied
+        n_out must agree with it -- the library writes nOut values per atom whatever the caller assumes."""
+        if self.n_out is None:
+            raise FnetGpuError("socket_step: no network configured (create a Bpnn on this context first)")
+        if n_out is not None and int(n_out) != self.n_out:
+            raise FnetGpuError("socket_step: n_out=%d does not match the network's output width %d" % (n_out, self.n_out))
+        n_out = self.n_out
         N, nS = self.n_atoms[slot], self.n_struct[slot]
         glob = np.zeros((nS, n_out)); raw = np.zeros((N, n_out))
         frc = np.zeros((N, 3 * n_out)) if forces else None
@@ -220,6 +228,7 @@ class Bpnn:
                                             C.c_int(ACTIVATIONS.index(activation))))
         self.n_tot = int(ctx._lib.fnetgpu_ntot(ctx._h))
         self.n_out = int(self.dims[-1])
+        ctx.n_out = self.n_out
 
     def serial_weights_and_biases_fillup(self, wb):
         """``serialWeightsAndBiasesFillup`` (bpnn.F90:782-797): wb is (nSpecies, nTot)."""

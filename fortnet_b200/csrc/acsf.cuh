@@ -593,13 +593,19 @@ __global__ void k_zstat(int N, int F, int nFeat, const real *__restrict__ feat,
   }
 }
 
-// out[f] = sum_b part[b][f]  (sequential over blocks: fixed order)
-__global__ void k_zstat_final(int nBlocks, int F, const double *__restrict__ part, double *__restrict__ out) {
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
+// out[f] = sum_b part[b][f]: one CTA per feature, strided partial sums + a fixed-shape tree (deterministic)
+__global__ void __launch_bounds__(256) k_zstat_final(int nBlocks, int F, const double *__restrict__ part, double *__restrict__ out) {
+  __shared__ double sh[256];
+  const int f = blockIdx.x;
   double s = 0.0;
-  for (int b = 0; b < nBlocks; b++) s += part[(size_t)b * F + f];
-  out[f] = s;
+  for (int b = threadIdx.x; b < nBlocks; b += 256) s += part[(size_t)b * F + f];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[f] = sh[0];
 }
 
 template <typename real>

@@ -56,9 +56,20 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   cudaGetDeviceProperties(&prop, device);
   ctx->nSM = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_err = "stream creation failed"; delete ctx; return 1; }
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-  cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
-  cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
+  {   // every allocation of the context is checked: a half-built context would fail later, far from the cause
+    cudaError_t ce = cudaEventCreate(&ctx->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ctx->ev1);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(int));   // [0..7] per-launch flags, [8..15] cell-list statistics
+    if (ce == cudaSuccess) ce = cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
+    if (ce != cudaSuccess) {
+      g_err = std::string("fnetgpu_init: ") + cudaGetErrorString(ce);
+      if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+      if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+      cudaFree(ctx->d_flags); cudaStreamDestroy(ctx->stream);
+      delete ctx;
+      return 1;
+    }
+  }
   { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0;
     ctx->mlpNoFuse = (pm && strcmp(pm, "nofuse") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_KERNEL"); ctx->acsfGeneric = (pm && strcmp(pm, "generic") == 0) ? 1 : 0; }
@@ -84,7 +95,7 @@ extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) free_slot(ctx->slots[i]);
   cudaFree(ctx->d_rgroups); cudaFree(ctx->d_rfeat); cudaFree(ctx->d_rp1); cudaFree(ctx->d_rp2);
   cudaFree(ctx->d_apasses); cudaFree(ctx->d_lrad); cudaFree(ctx->d_lpass); cudaFree(ctx->d_powtab); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_extIdx); cudaFree(ctx->d_zprec); cudaFree(ctx->d_wb);
-  cudaFree(ctx->d_wb64); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_wb64); cudaFree(ctx->d_conv); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->comm && ctx->nccl) {
     typedef int (*destroy_t)(void *);
@@ -179,11 +190,21 @@ extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, c
   CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
   if (nStruct <= 0 || !offsets || !atnum || !globalsp) FNET_FAIL(ctx, "dataset_upload: missing arrays");
   cudaSetDevice(ctx->device);
-  Slot &s = ctx->slots[slot];
-  free_slot(s);
   const int N = offsets[nStruct];
   if (N <= 0 || offsets[0] != 0) FNET_FAIL(ctx, "dataset_upload: offsets must start at 0 and end at N > 0");
-  s.used = true; s.nStruct = nStruct; s.N = N; s.nG = nG; s.nA = nA; s.nExt = nExt;
+  // validate everything before the slot is touched: a failed upload leaves the previous contents usable
+  for (int st = 0; st < nStruct; st++)
+    if (offsets[st + 1] <= offsets[st]) FNET_FAIL(ctx, "dataset_upload: empty structure");
+  for (int i = 0; i < N; i++)
+    if (globalsp[i] < 1) FNET_FAIL(ctx, "dataset_upload: globalsp must be 1-based");
+  if (nG < 0 || nA < 0 || nExt < 0) FNET_FAIL(ctx, "dataset_upload: negative target / feature count");
+  if (nG > 0 && !gTargets) FNET_FAIL(ctx, "gTargets missing");
+  if (nA > 0 && !aTargets) FNET_FAIL(ctx, "aTargets missing");
+  if (nExt > 0 && !ext) FNET_FAIL(ctx, "ext missing");
+  Slot &s = ctx->slots[slot];
+  free_slot(s);
+  struct SlotGuard { Slot &s; bool ok; ~SlotGuard() { if (!ok) free_slot(s); } } guard{s, false};   // CUDA failures below: slot left empty
+  s.nStruct = nStruct; s.N = N; s.nG = nG; s.nA = nA; s.nExt = nExt;
   s.h_offsets.assign(offsets, offsets + nStruct + 1);
   s.h_periodic.assign(nStruct, 0);
   if (periodic) s.h_periodic.assign(periodic, periodic + nStruct);
@@ -228,6 +249,7 @@ extern "C" int fnetgpu_dataset_upload(fnetgpu_ctx *ctx, int slot, int nStruct, c
   if (nA > 0) { if (!aTargets) FNET_FAIL(ctx, "aTargets missing"); if (dev_upload(ctx, &s.d_at, aTargets, (size_t)nA * N)) return 1; }
   if (nExt > 0) { if (!ext) FNET_FAIL(ctx, "ext missing"); if (dev_upload(ctx, &s.d_ext, ext, (size_t)nExt * N)) return 1; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  s.used = true; guard.ok = true;
   return 0;
 }
 
@@ -241,8 +263,12 @@ extern "C" int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *c
   CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (latvecs) {
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);   // overlaps the copies above
-    s.structPath = 1;
+    // the whole-structure path is re-tried only when a lattice actually changed (an MD driver passes the same
+    // cell every step: a slot that was sent to the cell list stays there)
+    if (s.h_lat.size() != (size_t)9 * s.nStruct || memcmp(s.h_lat.data(), latvecs, (size_t)9 * s.nStruct * sizeof(double)) != 0) {
+      s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);   // overlaps the copies above
+      s.structPath = 1;
+    }
   }
   s.cellRc = -1.0; s.neighStale = true; s.featValid = false;   // maxNeigh stays as a capacity hint
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffer on return
@@ -1081,7 +1107,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     double *h = ctx->h_pinned;
     for (int pass = 0; pass < 2; pass++) {
       LAUNCH(ctx, K_ZSTAT, (k_zstat<real><<<nb, 128, 0, ctx->stream>>>(s.N, F, nFeat, feat, s.d_structOf, s.d_dsw, pass ? ctx->d_zprec : nullptr, apb, part)));
-      LAUNCH(ctx, K_ZSTAT_FINAL, (k_zstat_final<<<(F + 127) / 128, 128, 0, ctx->stream>>>(nb, F, part, sums)));
+      LAUNCH(ctx, K_ZSTAT_FINAL, (k_zstat_final<<<F, 256, 0, ctx->stream>>>(nb, F, part, sums)));
       if (pass == 0) {
         // append the weighted atom count so one all-reduce carries both
         CUDA_TRY(ctx, cudaMemcpyAsync(sums + F, &wN, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1138,8 +1164,10 @@ extern "C" int fnetgpu_acsf_update_calculate(fnetgpu_ctx *ctx, int slot, const d
   if (dev_reserve(ctx, &s.d_coords, &s.capCoords, (size_t)3 * s.N)) return 1;
   if (latvecs) {
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
-    s.structPath = 1;
+    if (s.h_lat.size() != (size_t)9 * s.nStruct || memcmp(s.h_lat.data(), latvecs, (size_t)9 * s.nStruct * sizeof(double)) != 0) {
+      s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
+      s.structPath = 1;
+    }
   }
   s.cellRc = -1.0; s.neighStale = true; s.featValid = false;
   have_zprec = have_zprec ? 1 : 0;
@@ -1161,12 +1189,10 @@ static int download_real(fnetgpu_ctx *ctx, const void *d_src, size_t n, double *
   if (ctx->precision == 64) {
     CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   } else {
-    double *tmp = nullptr;
-    CUDA_TRY(ctx, cudaMalloc((void **)&tmp, n * sizeof(double)));
+    if (dev_reserve(ctx, &ctx->d_conv, &ctx->convN, n)) return 1;     // grow-only conversion buffer of the context
+    double *tmp = ctx->d_conv;
     LAUNCH(ctx, K_MISC, (k_convert_out<float><<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(n, (const float *)d_src, tmp)));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -1524,6 +1550,20 @@ extern "C" int fnetgpu_loss(fnetgpu_ctx *ctx, int slot, int lossId, double *loss
 // ------------------------------------------------------------------------------------------
 // forces
 // ------------------------------------------------------------------------------------------
+// dE/dG [N][nOut][F] and forces [N][3 nOut] of a slot: grow-only, sized for the CURRENT ACSF / network
+// configuration (a later fnetgpu_acsf_set / fnetgpu_net_set with a larger F or nOut re-allocates)
+static int ensure_force_buffers(fnetgpu_ctx *ctx, Slot &s, size_t realBytes) {
+  const size_t needD = (size_t)s.N * ctx->net.nOut * ctx->acsf.F * realBytes;
+  if (!s.d_dEdG || s.capDEdGBytes < needD) {
+    cudaFree(s.d_dEdG); s.d_dEdG = nullptr; s.capDEdGBytes = 0;
+    CUDA_TRY(ctx, cudaMalloc(&s.d_dEdG, std::max<size_t>(needD, 8)));
+    s.capDEdGBytes = needD;
+  }
+  size_t capF = s.capForces;
+  if (dev_reserve(ctx, &s.d_forces, &capF, (size_t)3 * ctx->net.nOut * s.N)) return 1;
+  s.capForces = capF;
+  return 0;
+}
 // one launch of the fused force kernel for the planned geometry path (no flag read-back)
 static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, const double *dEdG64, const double *zp) {
   const AcsfTables &T = ctx->acsf;
@@ -1553,7 +1593,7 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   if (!ctx->acsfSet || T.F == 0) FNET_FAIL(ctx, "forces: need an ACSF configuration");
   if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "forces: not defined with external features (initprogram.F90:1543-1548)");
   // (1) dE_k/dG for every atom and output: one reverse sweep per output
-  if (!s.d_dEdG) { real *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
+  if (ensure_force_buffers(ctx, s, sizeof(real))) return 1;
   {
     const BpnnLaunch B = plan_bpnn<real>(ctx, s, 1);
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
@@ -1572,7 +1612,6 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
     LAUNCH(ctx, K_MISC, (k_convert_out<float><<<(int)((nD + 255) / 256), 256, 0, ctx->stream>>>(nD, (const float *)s.d_dEdG, tmp64)));
     dEdG64 = tmp64;
   }
-  if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, (size_t)3 * n.nOut * s.N)) return 1; }
   const double *zp = s.zscored ? ctx->d_zprec : nullptr;
   int h[16];
   for (int attempt = 0; attempt < 4; attempt++) {
@@ -1656,7 +1695,7 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
       s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
       if (check_ready<double>(ctx, s, false)) return 1;
       if (run_forward<double>(ctx, s)) return 1;
-      if (!s.d_dEdG) { double *p = nullptr; if (dev_alloc(ctx, &p, (size_t)s.N * n.nOut * T.F)) return 1; s.d_dEdG = p; }
+      if (ensure_force_buffers(ctx, s, sizeof(double))) return 1;
       {
         const BpnnLaunch B = plan_bpnn<double>(ctx, s, 1);
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
@@ -1665,7 +1704,6 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
                                       s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
                                       nullptr, (double *)s.d_dEdG, (double *)nullptr)));
       }
-      if (!s.d_forces) { if (dev_alloc(ctx, &s.d_forces, nFrc)) return 1; }
       CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));
       if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
       if (ensure_pinned(ctx, nRaw + nFrc + 16)) return 1;

@@ -196,7 +196,9 @@ struct Slot {
   double *d_Es = nullptr;           // [nStruct][nG]
   double *d_lossPart = nullptr;     // [nStruct][2]
   void *d_dEdG = nullptr;           // [N][nG][F] real
+  size_t capDEdGBytes = 0;
   double *d_forces = nullptr;       // [N][3*nOut]
+  size_t capForces = 0;
 };
 
 struct fnetgpu_ctx {
@@ -241,6 +243,7 @@ struct fnetgpu_ctx {
   NetTables net;
   void *d_wb = nullptr;             // [nSpecies][nTot] real
   double *d_wb64 = nullptr;
+  double *d_conv = nullptr; size_t convN = 0;   // FP32 mode: device-side float -> double staging of downloads
   bool paramsSet = false;
   // gradient work
   double *d_partials = nullptr; size_t partialsN = 0;

@@ -258,7 +258,7 @@ def test_c5_dense_liquid_values(fb, orc, kernel):
     ctx.close()
 
 
-@pytest.mark.parametrize("act", ["gaussian", "relu", "lrelu", "softplus", "bent", "atan", "sigmoid", "tanh", "linear"])
+@pytest.mark.parametrize("act", ["gaussian", "relu", "lrelu", "softplus", "bent", "atan", "sigmoid", "heaviside", "tanh", "linear"])
 @pytest.mark.parametrize("loss", ["mse", "rms", "mae", "mape"])
 def test_activations_and_losses(fb, orc, act, loss):
     """every transfer function (transfer.F90) x every loss (loss.F90:217-281) on one small batch"""
@@ -267,6 +267,35 @@ def test_activations_and_losses(fb, orc, act, loss):
     ds.gtargets[:] = np.random.default_rng(5).uniform(1.0, 2.0, size=ds.gtargets.shape)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 5, 4)
     _full_check(fb, orc, ds, funcs, [9, 7, 5, 1], act=act, loss=loss, forces=(loss == "mse"))
+
+
+def test_reconfigure_with_larger_features_and_outputs(fb, orc):
+    """a live slot is re-configured with MORE ACSF functions and a wider output layer: the per-slot dE/dG and
+    force buffers of the first configuration must be re-sized (they were allocated once), forces vs oracle"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=3, seed=21)
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    rng = np.random.default_rng(22)
+    for nrad, nang, nout in [(3, 2, 1), (9, 10, 3)]:
+        funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, nrad, nang)
+        dims = [len(funcs), 6, nout]
+        acsf = fb.Acsf(ctx, funcs, standardize=False)
+        acsf.calculate(0)
+        net = fb.Bpnn(ctx, dims, 1, "tanh")
+        wb = rng.uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+        net.set_params(wb)
+        f = net.forces(0)
+        glob, raw, frc = ctx.socket_step(0, ds.coords, ds.latvecs)
+        feats = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=_nthreads())
+        f_o = orc.forces(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), feats, ds.globalsp, dims,
+                         "tanh", wb, nthreads=_nthreads())
+        assert f.shape == (ds.n_atoms, 3 * nout) and frc.shape == f.shape and raw.shape == (ds.n_atoms, nout)
+        assert np.allclose(f, f_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(f_o).max())), _md(f, f_o)
+        assert np.allclose(frc, f_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(f_o).max())), _md(frc, f_o)
+    with pytest.raises(fb.FnetGpuError):
+        ctx.socket_step(0, ds.coords, ds.latvecs, n_out=1)       # the network has three outputs
+    ctx.close()
 
 
 # ---------------------------------------------------------------------------------------------

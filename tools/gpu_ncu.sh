@@ -7,4 +7,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:$KR 
     python tools/e2e_breakdown.py $WL $NS > $O/$TAG.log 2>&1; echo "ncu rc=$?"
 ncu -i $O/$TAG.ncu-rep --page raw --csv > $O/$TAG.raw.csv 2>/dev/null
 ncu -i $O/$TAG.ncu-rep --page source --csv > $O/$TAG.source.csv 2>/dev/null
+rm -f $O/$TAG.ncu-rep   # the csv pages are what is read here; the merged output is limited to 64 MiB
 ls -la $O/$TAG.*
