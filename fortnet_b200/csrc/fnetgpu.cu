@@ -6,6 +6,7 @@
 #include "acsf.cuh"
 #include "acsf_lean.cuh"
 #include "acsf_force.cuh"
+#include "acsf_force_lean.cuh"
 #include "mlp.cuh"
 #include "mlp_mma.cuh"
 
@@ -751,7 +752,7 @@ static int ensure_neigh_count(fnetgpu_ctx *ctx, Slot &s) {
 }
 
 // launch geometry shared by the ACSF value and force kernels (one CTA per bin x split)
-struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; bool lean = false; int G = 1; };
+struct AcsfLaunch { int cap, capC, wpb, nSplit; bool staged; int path; size_t smem; dim3 grid; int stBase = 0; bool lean = false; int G = 1; bool local = false; };
 // the whole-structure path (cells.cuh): small structures, lattice check passed so far
 static bool use_struct_path(const fnetgpu_ctx *ctx, const Slot &s) {
   return !ctx->acsfPathCells && s.structPath && s.maxAtoms <= FNET_STRUCT_MAX_ATOMS && s.d_coords && s.d_lat;
@@ -767,7 +768,8 @@ static GeomArgs geom_args(const Slot &s) {
   g.stBase = 0;
   return g;
 }
-static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L, int cap = -1, size_t extraCta = 0) {
+static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L, int cap = -1, size_t extraCta = 0,
+                              bool wholeStructure = false) {
   L.path = FNET_PATH_STRUCT; L.staged = false;
   L.cap = cap > 0 ? cap : struct_cap(s);
   L.capC = (s.maxAtoms + 31) & ~31;
@@ -783,7 +785,7 @@ static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes,
   const long long want = 8LL * ctx->nSM;
   if ((long long)s.nStruct * nSplit < want)
     nSplit = (int)std::min<long long>((s.maxAtoms + L.wpb - 1) / L.wpb, (want + s.nStruct - 1) / s.nStruct);
-  L.nSplit = std::max(1, std::min(nSplit, 65535));
+  L.nSplit = wholeStructure ? 1 : std::max(1, std::min(nSplit, 65535));
   L.grid = dim3(s.nStruct, L.nSplit);
   return 0;
 }
@@ -836,6 +838,33 @@ static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
   L.lean = false;
   if (structPath) return plan_struct_launch(ctx, s, acsf_warp_smem_bytes(struct_cap(s), T.F, T.redRows), L);
   return plan_acsf_launch(ctx, s, acsf_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F, T.redRows), L);
+}
+
+// launch plan of the FORCE kernel: k_acsf_force_lean for automatic-scheme configurations (whole-structure
+// path: one CTA per structure, deterministic shared-memory accumulation), else k_acsf_force
+static int lean_M(const fnetgpu_ctx *ctx) { return FNET_LADDER * ctx->leanNL * ctx->leanNC; }
+static int plan_forces(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLaunch &L) {
+  const AcsfTables &T = ctx->acsf;
+  if (use_lean(ctx)) {
+    int hint = s.maxNeigh > 0 ? s.maxNeigh : 32;
+    if (structPath) hint = std::min(hint, std::max(s.maxAtoms - 1, 1));
+    const int cap = std::max(8, (hint + 1 + 7) & ~7);
+    static const int gEnv = [] { const char *e = getenv("FNETGPU_LEAN_G"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
+    int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
+    if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
+    const size_t extra = force_lean_cta_extra_bytes(ctx->lean.stageBytes);
+    const int localAtoms = structPath ? ((s.maxAtoms + 1) & ~1) : 0;
+    for (; G >= 1; G >>= 1) {
+      AcsfLaunch Q;
+      const size_t wb = force_lean_warp_bytes(cap, T.F, lean_M(ctx), ctx->leanSorted, G, localAtoms);
+      const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra, true) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
+      if (rc == 0 && Q.path != FNET_PATH_DIRECT && Q.wpb == 4) { L = Q; L.lean = true; L.G = G; L.local = structPath; return 0; }
+      ctx->err.clear();
+    }
+  }
+  L.lean = false; L.local = false;
+  if (structPath) return plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), L);
+  return plan_acsf_launch(ctx, s, force_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F), L);
 }
 
 extern "C" int fnetgpu_acsf_path_set(fnetgpu_ctx *ctx, int mode) {
@@ -1412,6 +1441,36 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
   return 0;
 }
 
+// dE_k/dG for every atom and output (nJacobian, bpnn.F90:904-997): one reverse sweep per output; precision 64: DMMA kernel
+template <typename real>
+static int run_ingrad(fnetgpu_ctx *ctx, Slot &s) {
+  const NetTables &n = ctx->net;
+  if constexpr (std::is_same<real, double>::value) {
+    if (use_mma<real>(ctx)) {
+      const MmaLaunch M = plan_mma(ctx, s, 1);
+#define FNET_MMA_ING(FCH)                                                                                         \
+      do {                                                                                                        \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<1, 1, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        const int fgrid = mma_grid(ctx, s, k_bpnn_mma<1, 1, FCH>, M.smem, M.grid);                                \
+        LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn_mma<1, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(    \
+                                      s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,       \
+                                      (const double *)ctx->d_wb, n, nullptr, nullptr, nullptr, nullptr, nullptr,  \
+                                      nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_dEdG)));                     \
+      } while (0)
+      if (n.dims[0] <= 32) FNET_MMA_ING(1); else FNET_MMA_ING(2);
+#undef FNET_MMA_ING
+      return 0;
+    }
+  }
+  const BpnnLaunch B = plan_bpnn<real>(ctx, s, 1);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<real, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
+                                s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
+                                s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
+                                nullptr, (real *)s.d_dEdG, (real *)nullptr)));
+  return 0;
+}
+
 template <typename real>
 static int run_struct_loss(fnetgpu_ctx *ctx, Slot &s, int lossId) {
   const NetTables &n = ctx->net;
@@ -1570,6 +1629,32 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   const NetTables &n = ctx->net;
   const dim3 g(L.grid.x, L.grid.y, n.nOut);
   const GeomArgs geo = geom_args(s);
+  if (L.lean) {
+    const LeanTables &LT = ctx->lean;
+    const int localAtoms = L.local ? ((s.maxAtoms + 1) & ~1) : 0;
+#define FNET_FLEAN(NL, NC, PATH, SORTED, G, LOCAL)                                                               \
+  do {                                                                                                          \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL><<<g, L.wpb * 32, L.smem, ctx->stream>>>( \
+                                  L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags))); \
+  } while (0)
+#define FNET_FLEAN_S(NL, NC, PATH, LOCAL)                                                                        \
+  do {                                                                                                          \
+    if (ctx->leanSorted) { if (L.G == 2) FNET_FLEAN(NL, NC, PATH, true, 2, LOCAL); else FNET_FLEAN(NL, NC, PATH, true, 1, LOCAL); } \
+    else if (L.G == 4) FNET_FLEAN(NL, NC, PATH, false, 4, LOCAL);                                                \
+    else if (L.G == 2) FNET_FLEAN(NL, NC, PATH, false, 2, LOCAL);                                                \
+    else FNET_FLEAN(NL, NC, PATH, false, 1, LOCAL);                                                              \
+  } while (0)
+#define FNET_FLEAN_P(NL, NC)                                                                                     \
+  do { if (L.path == FNET_PATH_STRUCT) FNET_FLEAN_S(NL, NC, FNET_PATH_STRUCT, true); else FNET_FLEAN_S(NL, NC, FNET_PATH_STAGED, false); } while (0)
+    if (ctx->leanNC == 1) FNET_FLEAN_P(2, 1);
+    else if (ctx->leanNC == 2) FNET_FLEAN_P(2, 2);
+    else FNET_FLEAN_P(1, 4);
+#undef FNET_FLEAN_P
+#undef FNET_FLEAN_S
+#undef FNET_FLEAN
+    return 0;
+  }
 #define FNET_FORCE_LAUNCH(PATH)                                                                                 \
   do {                                                                                                          \
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
@@ -1594,14 +1679,7 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
   if (!ctx->extIdx.empty()) FNET_FAIL(ctx, "forces: not defined with external features (initprogram.F90:1543-1548)");
   // (1) dE_k/dG for every atom and output: one reverse sweep per output
   if (ensure_force_buffers(ctx, s, sizeof(real))) return 1;
-  {
-    const BpnnLaunch B = plan_bpnn<real>(ctx, s, 1);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-    LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<real, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
-                                  s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
-                                  s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
-                                  nullptr, (real *)s.d_dEdG, (real *)nullptr)));
-  }
+  if (run_ingrad<real>(ctx, s)) return 1;
   // the force kernel contracts in FP64
   const double *dEdG64 = nullptr;
   double *tmp64 = nullptr;
@@ -1620,11 +1698,11 @@ static int forces_t(fnetgpu_ctx *ctx, Slot &s, double *forces) {
     AcsfLaunch L;
     const bool sp = use_struct_path(ctx, s);
     if (sp) {
-      if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), L)) return 1;
+      if (plan_forces(ctx, s, true, L)) return 1;
     } else {
       if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
       if (ensure_neigh_count(ctx, s)) return 1;
-      if (plan_acsf_launch(ctx, s, force_warp_smem_bytes(std::max(32, (s.maxNeigh + 31) & ~31), T.F), L)) return 1;
+      if (plan_forces(ctx, s, false, L)) return 1;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, (size_t)3 * n.nOut * s.N * sizeof(double), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
@@ -1689,21 +1767,14 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
       const double *zp = s.zscored ? ctx->d_zprec : nullptr;
       AcsfLaunch Lv, Lf;
       if (plan_values(ctx, s, true, Lv)) return 1;
-      if (plan_struct_launch(ctx, s, force_warp_smem_bytes(struct_cap(s), T.F), Lf)) return 1;
+      if (plan_forces(ctx, s, true, Lf)) return 1;
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;
       s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
       if (check_ready<double>(ctx, s, false)) return 1;
       if (run_forward<double>(ctx, s)) return 1;
       if (ensure_force_buffers(ctx, s, sizeof(double))) return 1;
-      {
-        const BpnnLaunch B = plan_bpnn<double>(ctx, s, 1);
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-        LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<double, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
-                                      s.nTiles, s.d_tiles, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, n,
-                                      s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
-                                      nullptr, (double *)s.d_dEdG, (double *)nullptr)));
-      }
+      if (run_ingrad<double>(ctx, s)) return 1;
       CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));
       if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
       if (ensure_pinned(ctx, nRaw + nFrc + 16)) return 1;

@@ -224,10 +224,11 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
   }
 }
 
-// backward layer of one warp tile: dl[i][t] = (sum_o W[o][i] dn[o][t]) * f'(z)[i][t]
-// (network.F90:282-288); dl holds f'(z) on entry
+// backward layer of one warp tile: dst[i][t] = (sum_o W[o][i] dn[o][t]) * f'(z)[i][t]
+// (network.F90:282-288); fp holds f'(z) (training: fp == dst, the delta replaces it; input-gradient
+// sweeps keep f' for the next output and put the delta elsewhere); fp == nullptr: no factor (input layer)
 __device__ __forceinline__ void mma_backward(int din, int dout, const double *__restrict__ W, int wS,
-                                             const double *__restrict__ dn, double *__restrict__ dl, int lane) {
+                                             const double *__restrict__ dn, const double *fp, double *dst, int lane) {
   const int g = lane >> 2, c = lane & 3;
   const int KT = fnet_ru4(dout) >> 2, NT = fnet_ru8(din) >> 3;
   for (int nt0 = 0; nt0 < NT; nt0 += 4) {
@@ -243,10 +244,7 @@ __device__ __forceinline__ void mma_backward(int din, int dout, const double *__
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int i = 8 * (nt0 + nc) + 2 * c + e;
-          if (i < din) {
-            double *p = dl + i * FNET_MMA_TS + g;
-            *p = acc[nc][e] * *p;
-          }
+          if (i < din) dst[i * FNET_MMA_TS + g] = fp ? acc[nc][e] * fp[i * FNET_MMA_TS + g] : acc[nc][e];
         }
       }
   }
@@ -282,7 +280,8 @@ struct MmaWgradDispatch<0, NSLOT> {
 };
 
 // ------------------------------------------------------------------------------------------
-// MODE 0: training gradient -> partials[cta][nSpecies*nTot]; MODE 2: forward only -> raw[atom][k].
+// MODE 0: training gradient -> partials[cta][nSpecies*nTot]; MODE 2: forward only -> raw[atom][k];
+// MODE 1: input gradients -> raw[atom][k][F] (the dE/dG of the analytic forces).
 // `tiles` holds the ROUNDS: (start, count <= 64, species) triples of the species-sorted atom
 // order; a CTA walks a contiguous range of rounds, warp w of the CTA takes atoms 8 w .. 8 w + 7.
 // smem: weights | tile 0 | .. | tile 3   (tile: rows a_0 .. a_{L-1} | delta_1 .. delta_{L-1} | scratch,
@@ -466,7 +465,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           for (int u = 0; u < TA; u++) T[f * TS + u] = v[u];
         }
       }
-      if (MODE == 2) load_features(atom1);             // next round's rows: in flight during the whole sweep
+      if (MODE != 0) load_features(atom1);             // next round's rows: in flight during the whole sweep
       __syncwarp();
       // ---- forward ----
       for (int l = 1; l < L; l++) {
@@ -567,7 +566,34 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         __syncwarp();
         // ---- hidden layers: delta_{l} = (W_l delta_{l+1}) * f'(z_l), l = L-2 .. 1 ----
         for (int l = L - 2; l >= 1; l--) {
-          mma_backward(net.dims[l], net.dims[l + 1], wsm + m.wOff[l], m.wS[l], T + m.dOff[l + 1] * TS, T + m.dOff[l] * TS, lane);
+          mma_backward(net.dims[l], net.dims[l + 1], wsm + m.wOff[l], m.wS[l], T + m.dOff[l + 1] * TS, T + m.dOff[l] * TS,
+                       T + m.dOff[l] * TS, lane);
+          __syncwarp();
+        }
+      }
+      if (MODE == 1) {
+        // ---- input gradients dE_k/dG (bpnn.F90:904-997 nJacobian, one reverse sweep per output k): f'(z_l) stays in
+        // the delta rows, the deltas of a sweep go to the activation rows (not needed after the forward sweep) ----
+        for (int sweep = 0; sweep < net.nOut; sweep++) {
+          double *dL = T + m.dOff[L - 1] * TS;
+          if (lane < TA)
+            for (int k = 0; k < net.nOut; k++) dL[k * TS + lane] = (k == sweep && lane < count) ? 1.0 : 0.0;
+          __syncwarp();
+          for (int l = L - 2; l >= 1; l--) {
+            const double *dn = (l == L - 2) ? dL : T + m.aOff[l + 1] * TS;
+            mma_backward(net.dims[l], net.dims[l + 1], wsm + m.wOff[l], m.wS[l], dn, T + m.dOff[l] * TS, T + m.aOff[l] * TS, lane);
+            __syncwarp();
+          }
+          mma_backward(d0, net.dims[1], wsm + m.wOff[0], m.wS[0], (L == 2) ? dL : T + m.aOff[1] * TS, nullptr, T + m.aOff[0] * TS, lane);
+          __syncwarp();
+          for (int f0 = 0; f0 < d0; f0 += 32) {
+            const int f = f0 + lane;
+#pragma unroll
+            for (int u = 0; u < TA; u++) {
+              const int atom = __shfl_sync(0xffffffffu, myAtom, u);
+              if (atom >= 0 && f < d0) raw[((size_t)net.nOut * atom + sweep) * d0 + f] = T[f * TS + u];
+            }
+          }
           __syncwarp();
         }
       }
@@ -591,7 +617,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       }
       __syncthreads();
     }
-    if (MODE == 2 && warp >= nIn) load_features(atom1);   // idle in this round (short last round of a species)
+    if (MODE != 0 && warp >= nIn) load_features(atom1);   // idle in this round (short last round of a species)
     {
       const int pa = __shfl_sync(0xffffffffu, atom2, lane & 7);
       if (pa >= 0) {

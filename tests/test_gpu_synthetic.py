@@ -203,6 +203,80 @@ def test_large_and_small_structures_in_one_batch(fb, orc):
     _full_check(fb, orc, ds, funcs, [12, 6, 1], expect_path=CELLS)
 
 
+def _force_workload(fb, wl):
+    from fortnet_b200 import synthetic
+    if wl == "c2":
+        return synthetic.si_bulk(n_struct=4, seed=91), fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16), [32, 10, 2]
+    if wl == "c3":
+        return (synthetic.tio2(n_struct=2, seed=92),
+                fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8]), [64, 12, 1])
+    if wl == "long_ladder":     # 36 xi per lambda: two chained blocks of 32 / 4 functions (start power q^32), odd neighbour counts
+        return synthetic.si_bulk(n_struct=2, seed=93), fb.GFunctions.from_auto_scheme(4.3 * fb.BOHR_PER_AA, 2, 72), [74, 6, 1]
+    if wl == "mid_ladder":      # 9 xi per lambda: 2 x 2 chained slots
+        return synthetic.tio2(n_struct=1, seed=94), fb.GFunctions.from_auto_scheme(3.6 * fb.BOHR_PER_AA, 17, 18), [35, 6, 1]
+    rng = np.random.default_rng(95)
+    natoms = [1, 2, 40, 9, 33, 3]
+    coords = np.concatenate([rng.uniform(0.0, 6.0 + 2.0 * n ** (1 / 3), size=(n, 3)) for n in natoms])
+    N = sum(natoms)
+    ds = fb.Dataset.build(natoms, coords, np.zeros(len(natoms), np.int32), np.zeros((len(natoms), 3, 3)),
+                          rng.choice([1, 8], size=N).astype(np.int32), gtargets=np.zeros((len(natoms), 1)),
+                          atomic_numbers=[1, 8])
+    funcs = fb.GFunctions.from_auto_scheme(6.0, 7, 10).resolve_species([1, 8])
+    return ds, funcs, [len(funcs), 8, 1]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("wl", ["c2", "c3", "long_ladder", "mid_ladder", "cluster"])
+def test_force_kernels(fb, orc, wl, path, kernel):
+    """both force kernels (k_acsf_force_lean for automatic-scheme configurations, k_acsf_force) through both
+    neighbour paths against the oracle's dense-tensor forces, z-scored features, one or two outputs"""
+    ds, funcs, dims = _force_workload(fb, wl)
+    nt = _nthreads()
+    ctx = fb.Context(acsf_path=path, acsf_kernel=kernel)
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    nsp = len(ds.atomic_numbers)
+    net = fb.Bpnn(ctx, dims, nsp, "tanh")
+    wb = np.random.default_rng(7).uniform(-0.5, 0.5, size=(nsp, _ntot(dims)))
+    net.set_params(wb)
+    f = net.forces(0)
+    ref = orc.acsf(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), nthreads=nt)
+    mu, sg = orc.zscore_stats(ds.offsets, ref, ds.weights)
+    zref = orc.zscore_apply(ref, mu, sg)
+    f_o = orc.forces(ds.offsets, ds.coords, ds.periodic, ds.latvecs, ds.atnum, funcs.asdicts(), zref, ds.globalsp, dims, "tanh",
+                     wb, sigmas=sg, nthreads=nt)
+    assert np.allclose(f, f_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(f_o).max())), _md(f, f_o)
+    f2 = net.forces(0)
+    if kernel == "auto" and path == "auto":
+        assert np.array_equal(f, f2), "forces of the whole-structure path must be bit-reproducible"
+    ctx.close()
+
+
+def test_forces_bit_reproducible_full_size(fb):
+    """10^5 atoms of C2 shape, two contexts: the deterministic force path gives identical bits"""
+    from fortnet_b200 import synthetic
+    ds = synthetic.si_bulk(n_struct=1500, seed=96)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
+    dims = [32, 20, 20, 1]
+    wb = np.random.default_rng(8).uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    out = []
+    for rep in range(2):
+        ctx = fb.Context()
+        ctx.upload(0, ds)
+        acsf = fb.Acsf(ctx, funcs, standardize=True)
+        acsf.calculate(0)
+        net = fb.Bpnn(ctx, dims, 1, "tanh")
+        net.set_params(wb)
+        out.append(net.forces(0))
+        out.append(net.forces(0))
+        ctx.close()
+    for f in out[1:]:
+        assert np.array_equal(out[0], f)
+    assert np.abs(out[0].reshape(1500, 64, 3).sum(1)).max() < 1e-9 * np.abs(out[0]).max() * 64   # sum rule per structure
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("nrad,nang", [(24, 4), (3, 40), (17, 18), (32, 34), (9, 2), (2, 72), (5, 8)])
