@@ -207,6 +207,42 @@ def cpu_baseline(name, target_seconds=12.0, threads=None):
             "serial_sample": "%d structures (%d atoms) on 1 thread, %.2f s" % (ds1.n_struct, ds1.n_atoms, t_ser)}
 
 
+def c4_forces(fb, n_struct=5209, steps=3):
+    """C4: 5209 TiO2-like structures x 192 atoms = 1 000 128 atoms; ACSF (statistics given) + energies + analytic
+    forces per step, results copied to the host; wall clock around the blocking API calls."""
+    import torch
+    ds, funcs, dims, wb, _ = workload("c3", n_struct, seed_shift=424242)
+    ctx = fb.Context(device=torch.cuda.current_device(), precision=64)
+    try:
+        ctx.upload(0, ds)
+        acsf = fb.Acsf(ctx, funcs, standardize=True)
+        acsf.calculate(0)
+        zp = np.stack(acsf.zprec)
+        net = fb.Bpnn(ctx, dims, len(ds.atomic_numbers), "tanh")
+        net.set_params(wb)
+        f = net.forces(0)                                   # warm-up (allocations, capacities)
+        ctx.profile(True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            acsf.calculate(0, zprec=zp)
+            raw = net.predict_batch(0)
+            f = net.forces(0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        fsum = np.add.reduceat(f, ds.offsets[:-1].astype(int), axis=0)
+        kms = {k: round(v["ms_total"] / steps, 3) for k, v in prof.items()}
+        return {"metric": "force_prediction_atoms_per_s", "value": ds.n_atoms / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                "atoms": ds.n_atoms, "device_atoms_per_s": ds.n_atoms / (sum(kms.values()) * 1e-3),
+                "kernel_ms_per_step": kms, "d2h_bytes_per_step": int(raw.nbytes + f.nbytes),
+                "max_abs_force_sum_per_structure": float(np.abs(fsum).max()), "deterministic": True,
+                "workload": "C4: %d TiO2-like structures x 192 atoms, 64 ACSF, 64-32-32-32-1, energies + analytic forces to the host" % n_struct}
+    finally:
+        ctx.close()
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
     if rank != 0:
@@ -256,6 +292,9 @@ def main():
     ap.add_argument("--structures", type=int, default=0, help="structures per GPU (default: 10000 c2 / 20000 c3)")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's structure count per GPU; strong: that count split over the GPUs")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 force-prediction line (extra key, N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,6 +318,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_struct = args.structures or (10000 if args.workload == "c2" else 20000)
+    if args.scaling == "strong":        # fixed total: contiguous blocks of structures (parallel.F90:43-54), remainder to the first ranks
+        n_struct = n_struct // world + (1 if rank < n_struct % world else 0)
     ds, funcs, dims, wb, label = workload(args.workload, n_struct, seed_shift=1000 * rank)
     N = ds.n_atoms
     F = len(funcs)
@@ -349,6 +390,19 @@ def main():
         barrier()
         ms_e2e = t_e2e / args.steps * 1e3
 
+    # C4 (BASELINE.json configs[3]): force-resolved prediction on 1 M atoms -- an extra key of the N = 1 line
+    c4 = None
+    if world == 1 and not args.no_c4:
+        try:
+            c4 = c4_forces(fb)
+        except Exception as e:              # never lose the headline line to the extra one
+            c4 = {"error": str(e)[:200]}
+    mean_neigh = None
+    try:
+        mean_neigh = ctx.max_neighbors(0)[1]          # builds the cell list once: outside every timed region
+    except Exception:
+        pass
+
     tms = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = tms.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -368,26 +422,50 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         a = prof.get("acsf", {"ms_total": float("nan"), "launches": 1})
         acsf_ms = a["ms_total"] / max(a["launches"], 1)
+        acsf_kernel_name = "k_acsf_lean" if ctx.acsf_kernel() == 1 else "k_acsf"
         sfeat = 8 if args.precision == 64 else 4
         bytes_per_atom = 3 * 8 + 4 + sfeat * F                   # coords + species + features
         alg_bytes = bytes_per_atom * N + 72 * ds.n_struct
         achieved = alg_bytes / (acsf_ms * 1e-3) / 1e9
         kshare = {k: v["ms_total"] / args.steps for k, v in prof.items()}
-        # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch,
-        # scaled by atoms when the launch size differs); None when no capture exists for this workload
+        # DRAM traffic of the same kernel: STATIC, from the committed ncu --set full capture of this build's
+        # kernel (per launch, scaled by atoms when the launch size differs) -- a run under ncu is never a bench
+        # run, so it cannot be measured here; None when no capture exists for this workload
         traffic, ncu_extra = None, {}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json"))).get(args.workload)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json"))).get(args.workload)
             if tr and args.precision == 64:
                 traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (N / tr["atoms_per_launch"])
-                ncu_extra = {"ncu_issue_active_pct": tr["issue_active_pct"], "ncu_fp64_pipe_active_pct": tr["fp64_pipe_active_pct"],
-                             "ncu_warp_inst_per_atom": tr["warp_inst_per_atom"], "ncu_source": tr["source"]}
+                ncu_extra = {"traffic_source": "static: " + tr["source"], "ncu_issue_active_pct": tr["issue_active_pct"],
+                             "ncu_fp64_pipe_active_pct": tr["fp64_pipe_active_pct"],
+                             "ncu_warp_inst_per_atom": tr["warp_inst_per_atom"], "ncu_kernel": tr["kernel"]}
+        except Exception:
+            pass
+        # FP64 roofline of the same kernel: SURVEY.md 8(d) algorithmic flop-equivalents per atom,
+        #   n (10 + 4 F_r) + n (n + 1) / 2 (25 + 4 F_a),  n = mean neighbours within rc,
+        # against the measured DFMA peak of this pool's B200 (tools/peaks.cu -> profiles/r01_measured_peaks.json)
+        roof64 = None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r01_measured_peaks.json")))
+            f_r = sum(1 for f in funcs.func if f.radial)
+            f_a = len(funcs.func) - f_r
+            if len(ds.atomic_numbers) > 1:      # species-resolved copies share the pair geometry: per atom every pair feeds ONE copy
+                f_r //= len(ds.atomic_numbers); f_a //= len(ds.atomic_numbers) * (len(ds.atomic_numbers) + 1) // 2
+            nbar = mean_neigh if mean_neigh else 0.0
+            flop_atom = nbar * (10 + 4 * f_r) + 0.5 * nbar * (nbar + 1) * (25 + 4 * f_a)
+            ach = flop_atom * N / (acsf_ms * 1e-3) / 1e12
+            peak64 = 2.0 * pk["dfma_tfma_s"]
+            roof64 = {"kernel": acsf_kernel_name, "bound": "fp64", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64,
+                      "algorithmic_flop_per_atom": flop_atom, "mean_neighbours": nbar,
+                      "peak_source": "measured DFMA issue peak, tools/peaks.cu (profiles/r01_measured_peaks.json: %.1f TFMA/s)" % pk["dfma_tfma_s"],
+                      "note": "flop-equivalents of SURVEY.md 8(d) (c_a = 4 per angular function and pair), not executed instructions: "
+                              "the kernel evaluates a whole xi-ladder from one table-driven power"}
         except Exception:
             pass
         out = {
             "metric": METRIC, "value": total_atoms / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
             "data": "synthetic",
             "config": {"workload": label, "atoms_per_gpu": N, "structures_per_gpu": ds.n_struct,
                        "parallelism": "structure-sharded dp%d, one NCCL all-reduce of [ddSerial|loss] per step" % world,
@@ -400,18 +478,32 @@ def main():
                     "path": "fnetgpu_acsf_update_calculate(coords + lattices from pinned host memory, copy chunks overlapped with the ACSF kernel) -> fnetgpu_grad -> ddSerial + loss on the host (wall clock)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_acsf", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": acsf_kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
                          "algorithmic_bytes_per_atom": bytes_per_atom, "algorithmic_bytes": alg_bytes,
                          "avg_launch_ms": acsf_ms, "peak_source": peak_src,
-                         "note": "FP64 angular ACSF is instruction-issue bound, not HBM bound (SURVEY.md 8d: ~45k FP64 "
-                                 "lane-ops per atom against 284 B); the HBM fraction is reported as the contract asks, "
-                                 "the binding figures are the ncu issue / FP64-pipe utilisation", **ncu_extra},
+                         "note": "FP64 angular ACSF is bound by FP64 issue, not by HBM (SURVEY.md 8d: ~13k flop-equivalents "
+                                 "per atom against 284 B); the HBM fraction is reported as the contract asks, the binding "
+                                 "figure is roofline_fp64 (and the ncu issue / FP64-pipe utilisation)", **ncu_extra},
+            "roofline_fp64": roof64,
             "kernel_ms_per_step": kshare,
             "loss": loss,
         }
+        if c4 is not None:
+            out["c4_force_prediction"] = c4
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.workload)
+            cb = cpu_baseline(args.workload)
+            out["cpu_baseline"] = cb
+            # the blended headline ratio hides two very different ones: quote them separately
+            grad_ms = sum(v for k, v in kshare.items() if k != "acsf")
+            out["speedup_vs_cpu_baseline"] = {
+                "cores": cb["cores"],
+                "step_device": out["value"] / cb["value"],
+                "step_e2e": out["e2e"]["value"] / cb["value"],
+                "acsf_only": (N / (acsf_ms * 1e-3)) / cb["acsf_atoms_per_s"],
+                "train_iteration_only": (N / (grad_ms * 1e-3)) / cb["train_iter_atoms_per_s"] if grad_ms > 0 else None,
+                "note": "acsf_only is mostly algorithmic (the CPU port keeps the reference's per-(atom, function) neighbour-list rebuild); "
+                        "train_iteration_only compares like with like (forward / backward / gradient reduction)"}
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -92,6 +92,7 @@ static void free_slot(Slot &s) {
 extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  if (ctx->arStream) { cudaStreamSynchronize(ctx->arStream); cudaStreamDestroy(ctx->arStream); cudaEventDestroy(ctx->evGrad); cudaEventDestroy(ctx->evAR); }
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) free_slot(ctx->slots[i]);
   cudaFree(ctx->d_rgroups); cudaFree(ctx->d_rfeat); cudaFree(ctx->d_rp1); cudaFree(ctx->d_rp2);
@@ -115,6 +116,7 @@ extern "C" const char *fnetgpu_last_error(const fnetgpu_ctx *ctx) { return ctx ?
 
 extern "C" int fnetgpu_synchronize(fnetgpu_ctx *ctx) {
   CHECK_CTX(ctx);
+  if (ctx->arPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evAR, 0)); ctx->arPending = false; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -271,7 +273,7 @@ extern "C" int fnetgpu_coords_update(fnetgpu_ctx *ctx, int slot, const double *c
       s.structPath = 1;
     }
   }
-  s.cellRc = -1.0; s.neighStale = true; s.featValid = false;   // maxNeigh stays as a capacity hint
+  s.cellRc = -1.0; s.neighStale = true; s.featValid = false; s.geomEpoch++;   // maxNeigh stays as a capacity hint
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffer on return
   return 0;
 }
@@ -603,7 +605,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   if (dev_alloc(ctx, &ctx->d_zprec, (size_t)2 * std::max(F, 1))) return 1;
   ctx->haveZ = false;
   ctx->acsfSet = true;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; ctx->slots[i].maxCand = -1; }
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; ctx->slots[i].maxCand = -1; ctx->slots[i].okEpoch = 0; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -955,11 +957,12 @@ extern "C" int fnetgpu_comm_init(fnetgpu_ctx *ctx, int nRanks, int rank, const c
 }
 
 // in-place sum all-reduce of n doubles on the library's stream (no-op for a single rank)
-static int allreduce_sum(fnetgpu_ctx *ctx, double *d_buf, size_t n) {
+static int allreduce_sum(fnetgpu_ctx *ctx, double *d_buf, size_t n, cudaStream_t stream = nullptr) {
   if (ctx->nRanks <= 1 || !ctx->comm) return 0;
-  nccl_allreduce_t f = (nccl_allreduce_t)dlsym(ctx->nccl, "ncclAllReduce");
+  static nccl_allreduce_t f = nullptr;
+  if (!f) f = (nccl_allreduce_t)dlsym(ctx->nccl, "ncclAllReduce");
   if (!f) FNET_FAIL(ctx, "ncclAllReduce not found");
-  int rc = f(d_buf, d_buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, ctx->stream);
+  int rc = f(d_buf, d_buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->comm, stream ? stream : ctx->stream);
   if (rc != 0) FNET_FAIL(ctx, "ncclAllReduce failed (" + std::to_string(rc) + ")");
   ctx->launches++;
   return 0;
@@ -1050,6 +1053,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_zprec, zprec, (size_t)2 * F * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->haveZ = true;
   }
+  bool verifiedRepeat = false;
   if (F > 0) {
     // buffer capacities (neighbours per atom, candidates per bin): counted once per slot; after a
     // geometry update the previous maxima are reused as hints and the kernel's overflow flags
@@ -1068,6 +1072,14 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
         if (ensure_cells(ctx, s, T.rcMax, nullptr)) return 1;
         if (s.maxNeigh < 0 || s.maxCand < 0) { if (ensure_neigh_count(ctx, s)) return 1; }
         if (plan_values(ctx, s, false, L)) return 1;
+      }
+      if (!h_coords && s.okEpoch == s.geomEpoch && L.cap == s.okCap && L.capC == s.okCapC && L.path == s.okPath &&
+          L.G == s.okG && (int)L.lean == s.okLean) {
+        // same plan on the geometry of a launch whose flags were clean: nothing to read back, nothing to wait for
+        if (launch_acsf_values<real>(ctx, s, L, useGiven ? ctx->d_zprec : nullptr)) return 1;
+        s.lastPath = L.path;
+        verifiedRepeat = true;
+        break;
       }
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
       if (h_coords && sp) {
@@ -1099,6 +1111,9 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       s.lastPath = L.path;
       if (L.lean && sp && h[4] == 0 && h[1] == 0 && h[7] == 0 && h[0] > 0) s.maxNeigh = h[0];   // exact maximum of this geometry
+      if (h[4] == 0 && h[1] == 0 && h[7] == 0) {
+        s.okEpoch = s.geomEpoch; s.okCap = L.cap; s.okCapC = L.capC; s.okPath = L.path; s.okG = L.G; s.okLean = (int)L.lean;
+      }
       if (sp) {
         if (h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; continue; }   // a lattice is too small for the minimum image: cell list
         if (h[1] == 0 && h[7] == 0) break;
@@ -1163,7 +1178,7 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     LAUNCH(ctx, K_ZAPPLY, (k_zapply<real><<<(int)((tot + 255) / 256), 256, 0, ctx->stream>>>((size_t)s.N, F, nFeat, feat, ctx->d_zprec)));
   }
   if (!standardize) ctx->haveZ = false;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!verifiedRepeat) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // (a verified repeat launch stays asynchronous: everything that reads the features is ordered on the same stream)
   s.featValid = true;
   s.zscored = standardize && F > 0;
   return 0;
@@ -1198,7 +1213,7 @@ extern "C" int fnetgpu_acsf_update_calculate(fnetgpu_ctx *ctx, int slot, const d
       s.structPath = 1;
     }
   }
-  s.cellRc = -1.0; s.neighStale = true; s.featValid = false;
+  s.cellRc = -1.0; s.neighStale = true; s.featValid = false; s.geomEpoch++;
   have_zprec = have_zprec ? 1 : 0;
   if (ctx->precision == 64) return acsf_calculate_t<double>(ctx, s, standardize, zprec, have_zprec, coords);
   return acsf_calculate_t<float>(ctx, s, standardize, zprec, have_zprec, coords);
@@ -1482,9 +1497,18 @@ static int run_struct_loss(fnetgpu_ctx *ctx, Slot &s, int lossId) {
   return 0;
 }
 
+// the main stream must not touch d_dd before a pending all-reduce (side stream) is done with it
+static int wait_allreduce(fnetgpu_ctx *ctx) {
+  if (!ctx->arPending) return 0;
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evAR, 0));
+  ctx->arPending = false;
+  return 0;
+}
+
 template <typename real>
 static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, double *loss, double *globalPred) {
   if (check_ready<real>(ctx, s, true)) return 1;
+  if (wait_allreduce(ctx)) return 1;
   const NetTables &n = ctx->net;
   const size_t nDD = (size_t)n.nTot * n.nSpecies;
   const bool mma = use_mma<real>(ctx);
@@ -1541,8 +1565,22 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
   }
   LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
   if (fused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
-  if (allreduce_sum(ctx, ctx->d_dd, nDD + 2)) return 1;   // gradient | loss numerator | denominator
+  if (ctx->nRanks > 1 && ctx->comm) {
+    // gradient | loss numerator | denominator: ONE all-reduce, on its own stream -- when the caller does not fetch the
+    // result now, it overlaps whatever comes next on the main stream (the next step's ACSF kernel)
+    if (!ctx->arStream) {
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->arStream, cudaStreamNonBlocking));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evGrad, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evAR, cudaEventDisableTiming));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evGrad, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->arStream, ctx->evGrad, 0));
+    if (allreduce_sum(ctx, ctx->d_dd, nDD + 2, ctx->arStream)) return 1;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evAR, ctx->arStream));
+    ctx->arPending = true;
+  }
   if (ddSerial || loss) {
+    if (wait_allreduce(ctx)) return 1;
     if (ensure_pinned(ctx, nDD + 8)) return 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dd, (nDD + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1586,6 +1624,7 @@ extern "C" int fnetgpu_predict(fnetgpu_ctx *ctx, int slot, double *raw) {
 template <typename real>
 static int loss_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *loss) {
   if (check_ready<real>(ctx, s, true)) return 1;
+  if (wait_allreduce(ctx)) return 1;
   const size_t nDD = (size_t)ctx->net.nTot * ctx->net.nSpecies;
   if (run_forward<real>(ctx, s)) return 1;
   if (run_struct_loss<real>(ctx, s, lossId)) return 1;
@@ -1763,7 +1802,7 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
         CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
       }
-      s.cellRc = -1.0; s.neighStale = true;
+      s.cellRc = -1.0; s.neighStale = true; s.geomEpoch++;
       const double *zp = s.zscored ? ctx->d_zprec : nullptr;
       AcsfLaunch Lv, Lf;
       if (plan_values(ctx, s, true, Lv)) return 1;
@@ -1819,3 +1858,5 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
       }
   return 0;
 }
+
+#include "multi.cuh"

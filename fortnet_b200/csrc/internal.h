@@ -172,6 +172,10 @@ struct Slot {
   int totalBins = 0;
   size_t capCoords = 0, capFpos = 0, capCrec = 0, capBinStruct = 0, capAtomCell = 0, capCellAtoms = 0, capCellStart = 0, capCellCount = 0, capSinfo = 0;
   bool neighStale = true;           // maxNeigh is only a hint for the current geometry
+  // a value launch whose overflow / lattice flags were read back and found clean: the same plan on the same geometry
+  // cannot trip them again, so the repeat launches of a resident slot need no flag read-back and no host synchronisation
+  unsigned long long geomEpoch = 1, okEpoch = 0;
+  int okCap = 0, okCapC = 0, okPath = -1, okG = 0, okLean = -1;
   double cellRc = -1.0;             // cutoff the cell list was built for
   double *d_dsw = nullptr;          // [nStruct] dataset weights as double
   double *d_aw = nullptr;           // [N]
@@ -207,6 +211,9 @@ struct fnetgpu_ctx {
   int deterministic = 1;
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;   // chunked host->device copies overlapped with the ACSF kernel (fnetgpu_acsf_update_calculate)
+  cudaStream_t arStream = nullptr;     // gradient all-reduce: overlaps whatever the caller enqueues next (the next step's ACSF kernel)
+  cudaEvent_t evGrad = nullptr, evAR = nullptr;
+  bool arPending = false;              // an all-reduce on arStream still owns d_dd
   cudaEvent_t evChunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ownStream = true;
   std::string err;

@@ -173,6 +173,38 @@ int fnetgpu_mlp_path_set(fnetgpu_ctx *ctx, int mode);
 /* 1 if fnetgpu_grad / fnetgpu_predict would take the DMMA kernels for the current network */
 int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx);
 
+/* ---- single-process multi-GPU layer: replaces the MPI structure-level parallelism for a driver that
+ *      stays ONE process -- getStartAndEndIndex (lib_common/parallel.F90:23-56) becomes a contiguous split of
+ *      the structures over the devices balanced by atom count, the per-structure mpifx_allreduce of
+ *      lib_nn/bpnn.F90:455-467 ONE ncclAllReduce of [ddSerial | loss terms] per iteration (communicators from
+ *      ncclCommInitAll), the z-score statistics (lib_descriptors/acsf.F90:618-636) two small all-reduces.
+ *      nDevicesRequested <= 0: all visible devices.  Arguments as for the per-device entry points, with the
+ *      arrays of the WHOLE dataset: the layer shards on upload and gathers predictions, forces and features;
+ *      gradient, loss and statistics come back replicated.  One host thread per device inside every call. ---- */
+typedef struct fnetgpu_mg fnetgpu_mg;
+int fnetgpu_mg_init(fnetgpu_mg **mg, int nDevicesRequested, int precision, int deterministic);
+int fnetgpu_mg_finalize(fnetgpu_mg *mg);
+const char *fnetgpu_mg_last_error(const fnetgpu_mg *mg);
+int fnetgpu_mg_device_count(const fnetgpu_mg *mg);
+fnetgpu_ctx *fnetgpu_mg_context(fnetgpu_mg *mg, int device);        /* per-device context (queries, tuning switches) */
+int fnetgpu_mg_shard(const fnetgpu_mg *mg, int slot, int device, int *st0, int *st1, int *a0, int *a1);
+int fnetgpu_mg_dataset_upload(fnetgpu_mg *mg, int slot, int nStruct, const int *offsets, const double *coords,
+                              const int *periodic, const double *latvecs, const int *atnum, const int *globalsp,
+                              const int *dsWeights, const double *atomicWeights, int nG, const double *gTargets, int nA,
+                              const double *aTargets, int nExt, const double *ext);
+int fnetgpu_mg_coords_update(fnetgpu_mg *mg, int slot, const double *coords, const double *latvecs);
+int fnetgpu_mg_acsf_set(fnetgpu_mg *mg, int F, const int *type, const double *rcut, const double *kappa, const double *rs,
+                        const double *eta, const double *lambda, const double *xi, const int *atomid, const int *atomicnumbers);
+int fnetgpu_mg_features_config(fnetgpu_mg *mg, int nExtSel, const int *extIndices);
+int fnetgpu_mg_acsf_calculate(fnetgpu_mg *mg, int slot, int standardize, double *zprec, int have_zprec);
+int fnetgpu_mg_features_get(fnetgpu_mg *mg, int slot, double *out);
+int fnetgpu_mg_net_set(fnetgpu_mg *mg, int nSpecies, int nLayers, const int *dims, int activationId);
+int fnetgpu_mg_params_set(fnetgpu_mg *mg, const double *wb);
+int fnetgpu_mg_grad(fnetgpu_mg *mg, int slot, int lossId, const int *shuffle, double *ddSerial, double *loss, double *globalPred);
+int fnetgpu_mg_loss(fnetgpu_mg *mg, int slot, int lossId, double *loss);
+int fnetgpu_mg_predict(fnetgpu_mg *mg, int slot, double *raw);
+int fnetgpu_mg_forces(fnetgpu_mg *mg, int slot, double *forces);
+
 #ifdef __cplusplus
 }
 #endif
