@@ -305,6 +305,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE line, the JSON: everything libraries print while the bench runs (NCCL's version
+    # banner, torchrun warnings of child imports) is sent to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import fortnet_b200 as fb
@@ -504,7 +510,10 @@ def main():
                 "train_iteration_only": (N / (grad_ms * 1e-3)) / cb["train_iter_atoms_per_s"] if grad_ms > 0 else None,
                 "note": "acsf_only is mostly algorithmic (the CPU port keeps the reference's per-(atom, function) neighbour-list rebuild); "
                         "train_iteration_only compares like with like (forward / backward / gradient reduction)"}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

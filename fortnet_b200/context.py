@@ -153,6 +153,13 @@ class Context:
         """1: the configured ACSF run through k_acsf_lean (automatic-scheme configurations), 0: k_acsf, -1: none"""
         return int(self._lib.fnetgpu_acsf_kernel_get(self._h))
 
+    def acsf_launch_info(self, slot):
+        """what the last ACSF value launch used: dict(lean, atoms_per_warp, cap, cap_candidates, path, smem_bytes)"""
+        info = (C.c_int * 6)()
+        if self._lib.fnetgpu_acsf_launch_info(self._h, C.c_int(slot), info) != 0:
+            raise FnetGpuError("acsf_launch_info: empty slot")
+        return dict(zip(["lean", "atoms_per_warp", "cap", "cap_candidates", "path", "smem_bytes"], [int(v) for v in info]))
+
     def max_neighbors(self, slot):
         m, mean = C.c_int(), C.c_double()
         self._check(self._lib.fnetgpu_max_neighbors(self._h, C.c_int(slot), C.byref(m), C.byref(mean)))

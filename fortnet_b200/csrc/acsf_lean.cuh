@@ -36,18 +36,20 @@
 // Everything that is not a fresh xi-ladder from xi = 1 with one common delta (explicit function
 // lists, G1 / G3 / G4, atom-id scaling, lam < -1) runs through k_acsf.
 #pragma once
+#include <type_traits>
 #include "acsf.cuh"
 
 
-__host__ __device__ inline size_t lean_group_bytes(int cap, int F, bool sorted) {   // cap: multiple of 8
+__host__ __device__ inline size_t lean_group_bytes(int cap, int F, bool sorted, bool f32a = false) {   // cap: multiple of 8
   size_t b = (size_t)cap * 6 * sizeof(double);                         // neighbour records
+  if (f32a) b += (size_t)cap * 4 * sizeof(float);                      // FP32 pair arithmetic: (u'_x, u'_y, u'_z, fc E) as float4
   if (sorted) b += (size_t)cap * (3 * sizeof(double) + sizeof(int));   // unsorted displacements + species codes
   b += (size_t)((FNET_MAX_CODES + 4 + 3) & ~3) * sizeof(int);          // list segments
   b += (size_t)((F + 1) & ~1) * sizeof(double);                        // feature row
   return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows, bool sorted, int G) {
-  return (size_t)G * lean_group_bytes(cap, F, sorted) + (((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15);
+__host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows, bool sorted, int G, bool f32a = false) {
+  return (size_t)G * lean_group_bytes(cap, F, sorted, f32a) + (((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15);
 }
 __host__ __device__ inline int lean_pair_entries(int cap) {        // staged part of the strict-triangle pair table
   const int need = cap * (cap - 1) / 2 + 1;
@@ -171,7 +173,8 @@ __device__ __forceinline__ void lean_group_reduce(const double (&v)[M], int lane
 
 // One pair of the angular pass: records a, b -> the NL x NC ladders
 template <int NL, int NC>
-__device__ __forceinline__ void lean_pair_eval(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec, int a, int b,
+__device__ __forceinline__ void lean_pair_eval(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
+                                               const float4 *__restrict__, int a, int b,
                                                int m0, const double (&lam)[NL], const double *__restrict__ pt,
                                                const LeanTables &lt) {
   const double2 a0 = *(const double2 *)(rec + 6 * a), a1 = *(const double2 *)(rec + 6 * a + 2);
@@ -198,53 +201,107 @@ __device__ __forceinline__ void lean_pair_eval(double (&acc)[NL * NC * FNET_LADD
     }
   }
 }
-
-// pair index -> neighbour slots.  KIND 0: identical lists, strict triangle through the pair table;
-// 1: identical lists, computed triangle index (lists longer than the table); 2: two lists.
-template <bool SORTED, int KIND>
-__device__ __forceinline__ void lean_pair_index(int p, const unsigned short *__restrict__ ptab, const NbList &l1, const NbList &l2,
-                                                int n2, float invW, int &a, int &b) {
-  int j, k;
-  if (KIND == 0) { const unsigned jk = ptab[p]; j = jk & 255; k = jk >> 8; }
-  else if (KIND == 1) lean_tri_decode(p, j, k);
-  else {
-    j = (int)(((float)p + 0.5f) * invW);
-    if (j * n2 > p) j--;
-    else if ((j + 1) * n2 <= p) j++;
-    k = p - j * n2;
+// precision 32: the same pair in FP32 -- one 16-byte record per member (u'_x, u'_y, u'_z, fc E), b^delta =
+// ex2(delta lg2 b) on the MUFU pipe (ex2.approx / lg2.approx, ~2 ulp each), FFMA ladders, FP32 partial sums
+// per lane (summed over the lanes in FP64)
+template <int NL, int NC>
+__device__ __forceinline__ void lean_pair_eval(float (&acc)[NL * NC * FNET_LADDER], const double *__restrict__,
+                                               const float4 *__restrict__ recf, int a, int b,
+                                               int m0, const double (&lam)[NL], const double *__restrict__,
+                                               const LeanTables &lt) {
+  const float4 A = recf[a], B = recf[b];
+  const float base = A.w * B.w;
+  float c = A.x * B.x;
+  c = fmaf(A.y, B.y, c);
+  c = fmaf(A.z, B.z, c);
+  const float delta = (float)lt.powC[0];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const float bb = fmaxf(fmaf((float)lam[l], c, 1.0f), 1e-30f);
+    const float q = exp2f(delta * __log2f(bb));
+    float pw = bb * base;
+    const float q2 = q * q, q4 = q2 * q2;
+    if (m0 > 0) {
+      float qm = 1.0f, qb = q4 * q4;
+      for (int t = m0 >> 3; t; t >>= 1) { if (t & 1) qm *= qb; qb *= qb; }
+      pw *= qm;
+    }
+#pragma unroll
+    for (int ch = 0; ch < NC; ch++) {
+      float *ac = &acc[(l * NC + ch) * FNET_LADDER];
+      const float q3 = q2 * q, q5 = q4 * q, q6 = q4 * q2, q7 = q4 * q3;
+      ac[0] += pw;
+      ac[1] = fmaf(pw, q, ac[1]); ac[2] = fmaf(pw, q2, ac[2]); ac[3] = fmaf(pw, q3, ac[3]);
+      ac[4] = fmaf(pw, q4, ac[4]); ac[5] = fmaf(pw, q5, ac[5]); ac[6] = fmaf(pw, q6, ac[6]);
+      ac[7] = fmaf(pw, q7, ac[7]);
+      if (ch + 1 < NC) pw = (pw * q4) * q4;
+    }
   }
-  a = SORTED ? list_at(l1, j) : j; b = SORTED ? list_at(l2, k) : k;
 }
 
-// pairs per lane and loop iteration for the 16-accumulator shapes: two independent pairs hide the latency of the
-// dependent table-lookup / DFMA chains at 16 resident warps per SM (measured on C2 / C3: 0.91 -> 0.83 ms,
-// 18.4 -> 16.7 ms with 128 registers and 4 CTAs per SM; 5 CTAs at 96 registers spill and lose)
+// pair index -> list positions.  KIND 0: identical lists, strict triangle p = k (k-1)/2 + j through the pair table;
+// 1: identical lists longer than the table; 2: two lists (p = j n2 + k).  KIND 1 / 2 decode the first index of a lane
+// once and then ADVANCE (j, k) by the loop stride -- no division, no square root in the loop.
+__device__ __forceinline__ void lean_rect_decode(int p, int n2, int &j, int &k) {
+  const float invW = n2 > 0 ? 1.0f / (float)n2 : 0.0f;
+  j = (int)(((float)p + 0.5f) * invW);
+  if (j * n2 > p) j--;
+  else if ((j + 1) * n2 <= p) j++;
+  k = p - j * n2;
+}
+
 #ifndef FNET_LEAN_UNROLL
 #define FNET_LEAN_UNROLL 2
 #endif
-// One angular pass over the pairs of (l1, l2); index p = nP maps to (0, n1) resp. (n1, 0): the dummy neighbour
-template <int NL, int NC, int LPA, bool SORTED, int KIND>
-__device__ __forceinline__ void lean_pair_loop(double (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
+// One angular pass over the pairs of (l1, l2); indices beyond the last pair map to (0, n1) resp. (n1, 0): the dummy
+// neighbour.  Two pairs per lane and iteration for the 16-accumulator shapes: two independent pairs hide the latency of
+// the dependent table-lookup / DFMA chains at 16 resident warps per SM (measured on C2 / C3: 0.91 -> 0.83 ms,
+// 18.4 -> 16.7 ms with 128 registers and 4 CTAs per SM; 5 CTAs at 96 registers spill and lose)
+template <int NL, int NC, int LPA, bool SORTED, int KIND, typename AT>
+__device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
+                                               const float4 *__restrict__ recf,
                                                const NbList &l1, const NbList &l2, int n1, int n2, int m0,
                                                const double (&lam)[NL], const double *__restrict__ pt,
                                                const unsigned short *__restrict__ ptab, const LeanTables &lt, int sl) {
-  const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
-  const float invW = (KIND == 2 && n2 > 0) ? 1.0f / (float)n2 : 0.0f;
   constexpr int U = NL * NC <= 2 ? FNET_LEAN_UNROLL : 1;
-  for (int p0 = 0; p0 < nP; p0 += U * LPA) {
+  constexpr int S = U * LPA;
+  const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
+  int jj[U], kk[U];
+  if (KIND != 0) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (KIND == 1) lean_tri_decode(u * LPA + sl, jj[u], kk[u]);
+      else lean_rect_decode(u * LPA + sl, n2, jj[u], kk[u]);
+    }
+  }
+  for (int p0 = 0; p0 < nP; p0 += S) {
     int a[U], b[U];
 #pragma unroll
-    for (int u = 0; u < U; u++)
-      lean_pair_index<SORTED, KIND>(min(p0 + u * LPA + sl, nP), ptab, l1, l2, n2, invW, a[u], b[u]);
+    for (int u = 0; u < U; u++) {
+      int j, k;
+      if (KIND == 0) { const unsigned jk = ptab[min(p0 + u * LPA + sl, nP)]; j = jk & 255; k = jk >> 8; }
+      else if (KIND == 1) {
+        j = jj[u]; k = kk[u];
+        if (k >= n1) { j = 0; k = n1; }
+        jj[u] += S;
+        while (jj[u] >= kk[u]) { jj[u] -= kk[u]; kk[u]++; }
+      } else {
+        j = jj[u]; k = kk[u];
+        if (j >= n1) { j = n1; k = 0; }
+        kk[u] += S;
+        while (kk[u] >= n2) { kk[u] -= n2; jj[u]++; }
+      }
+      a[u] = SORTED ? list_at(l1, j) : j; b[u] = SORTED ? list_at(l2, k) : k;
+    }
 #pragma unroll
-    for (int u = 0; u < U; u++) lean_pair_eval<NL, NC>(acc, rec, a[u], b[u], m0, lam, pt, lt);
+    for (int u = 0; u < U; u++) lean_pair_eval<NL, NC>(acc, rec, recf, a[u], b[u], m0, lam, pt, lt);
   }
 }
 
 #ifndef FNET_LEAN_MINB
 #define FNET_LEAN_MINB 4
 #endif
-template <int NL, int NC, int PATH, bool SORTED, int G>
+template <int NL, int NC, int PATH, bool SORTED, int G, bool F32A>
 __global__ void __launch_bounds__(128, (NL * NC <= 2 ? FNET_LEAN_MINB : 3))
 k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, LeanTables lt, int cap,
             int capC, void *__restrict__ featv, int f32, int nFeat, const double *__restrict__ zprec, int nExtSel,
@@ -261,6 +318,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   const unsigned ltmask = (1u << sl) - 1u;
   CtaGeom cg;
   unsigned char *wbase;
+  typedef typename std::conditional<F32A, float, double>::type AT;   // arithmetic type of the pair sums
   if (!acsf_cta_prologue<PATH, true>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;   // exp table only
   const int F = tab.F, Fp = (F + 1) & ~1;
   double *pt = (double *)wbase;                     // power tables
@@ -294,13 +352,14 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   __syncthreads();
   wbase += lean_cta_tables_bytes(F, cap, lt.stageBytes);
   const int a0 = cg.a0, a1 = cg.a1;
-  const size_t gbytes = lean_group_bytes(cap, F, SORTED);
-  unsigned char *wb = wbase + (size_t)wib * lean_warp_smem_bytes(cap, F, lt.redRows, SORTED, G);
+  const size_t gbytes = lean_group_bytes(cap, F, SORTED, F32A);
+  unsigned char *wb = wbase + (size_t)wib * lean_warp_smem_bytes(cap, F, lt.redRows, SORTED, G, F32A);
   unsigned char *gb = wb + (size_t)grp * gbytes;
   double *rec = (double *)gb;                                        // [cap][6]: u'_x, u'_y | u'_z, fc E | r, fc
-  double *gx = rec + 6 * cap, *gy = gx + cap, *gz = gy + cap;        // SORTED: unsorted displacements
+  float4 *recf = (float4 *)(rec + 6 * cap);                          // F32A: [cap] (u'_x, u'_y, u'_z, fc E)
+  double *gx = rec + 6 * cap + (F32A ? 2 * cap : 0), *gy = gx + cap, *gz = gy + cap;   // SORTED: unsorted displacements
   int *gc = (int *)(gz + cap);                                       //         and species codes
-  int *seg = SORTED ? gc + cap : (int *)(rec + 6 * cap);
+  int *seg = SORTED ? gc + cap : (int *)gx;
   double *outv = (double *)(seg + ((FNET_MAX_CODES + 4 + 3) & ~3));
   double *red = (double *)(wb + (size_t)G * gbytes);
   const double *ftab = cg.ftab;
@@ -312,8 +371,25 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     const int i = me.idx;
     // ---------------- neighbours of each group's central atom: candidates -> compacted displacements ----------------
     int n = 0;
-    {
-      const double rc2 = tab.rcMax * tab.rcMax;
+    const double rc2 = tab.rcMax * tab.rcMax;
+    auto take = [&](bool ok, double dx, double dy, double dz, int j, int zs) {
+      const unsigned mg = (__ballot_sync(0xffffffffu, ok) >> gshift) & lowmask;
+      const int pos = n + __popc(mg & ltmask);
+      if (ok && pos < cap - 1) {
+        if (SORTED) {
+          gx[pos] = dx; gy[pos] = dy; gz[pos] = dz;
+          gc[pos] = (j == i) ? tab.nCodes + 1 : (int)zcode[(zs & ~FNET_SHIFT_FLAG) & 127];
+        } else {
+          rec[6 * pos] = dx; rec[6 * pos + 1] = dy; rec[6 * pos + 2] = dz;
+        }
+      }
+      n += __popc(mg);
+    };
+    if (PATH == FNET_PATH_DIRECT) {            // candidates straight from the cell list (bins too crowded to stage): G = 1
+      for_each_candidate_direct(*cg.S, cg.bp, cg.cellStart, cg.crec, me, [&](bool valid, double dx, double dy, double dz, int j, int zs) {
+        take(is_neighbor(valid && act, dx * dx + dy * dy + dz * dz, rc2, j, zs, i), dx, dy, dz, j, zs);
+      });
+    } else {
       const bool per = PATH == FNET_PATH_STRUCT && cg.sg->periodic != 0;
       const bool diag = PATH == FNET_PATH_STRUCT && cg.sg->diag != 0;
       const StructGeom *__restrict__ sg = cg.sg;
@@ -340,18 +416,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
             dz -= n0 * sg->lat[2] + n1 * sg->lat[5] + n2 * sg->lat[8];
           }
         }
-        const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, i);
-        const unsigned mg = (__ballot_sync(0xffffffffu, ok) >> gshift) & lowmask;
-        const int pos = n + __popc(mg & ltmask);
-        if (ok && pos < cap - 1) {
-          if (SORTED) {
-            gx[pos] = dx; gy[pos] = dy; gz[pos] = dz;
-            gc[pos] = (r.idx == i) ? tab.nCodes + 1 : (int)zcode[(r.zs & ~FNET_SHIFT_FLAG) & 127];
-          } else {
-            rec[6 * pos] = dx; rec[6 * pos + 1] = dy; rec[6 * pos + 2] = dz;
-          }
-        }
-        n += __popc(mg);
+        take(is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, i), dx, dy, dz, r.idx, r.zs);
       }
     }
     if (n > cap - 1) {                                       // one slot is the dummy neighbour
@@ -410,6 +475,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
       *(double2 *)(rec + 6 * t) = make_double2(ux, uy);
       *(double2 *)(rec + 6 * t + 2) = make_double2(uz, fe);
       *(double2 *)(rec + 6 * t + 4) = make_double2(rr, fc);
+      if (F32A) recf[t] = make_float4((float)ux, (float)uy, (float)uz, (float)fe);
     }
     __syncwarp();
     // ---------------- radial ladder groups (acsf.F90:1287-1373): lanes = neighbours, 8 functions per sweep ----------------
@@ -470,23 +536,28 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
       __syncwarp();
       if (P->recomp) {
         const double rc = P->rc, invrc = P->invrc, eta = P->eta;
-        for (int t = sl; t < n; t += LPA) { double fc; rec[6 * t + 3] = lean_fce(rec[6 * t + 4], rc, invrc, eta, ftab, fc); }
+        for (int t = sl; t < n; t += LPA) {
+          double fc;
+          const double fe = lean_fce(rec[6 * t + 4], rc, invrc, eta, ftab, fc);
+          rec[6 * t + 3] = fe;
+          if (F32A) recf[t].w = (float)fe;
+        }
         __syncwarp();
       }
       double lam[NL];
 #pragma unroll
       for (int l = 0; l < NL; l++) lam[l] = P->lam[l];
-      double acc[M];
+      AT acc[M];
 #pragma unroll
-      for (int f = 0; f < M; f++) acc[f] = 0.0;
+      for (int f = 0; f < M; f++) acc[f] = (AT)0;
       if (same) {
         int nmaxG = n1;                              // the table covers lists of <= FNET_PAIR_TAB_MAXN neighbours: warp-uniform choice
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nmaxG = max(nmaxG, __shfl_xor_sync(0xffffffffu, nmaxG, o));
-        if (nmaxG <= FNET_PAIR_TAB_MAXN) lean_pair_loop<NL, NC, LPA, SORTED, 0>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
-        else lean_pair_loop<NL, NC, LPA, SORTED, 1>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
+        if (nmaxG <= FNET_PAIR_TAB_MAXN) lean_pair_loop<NL, NC, LPA, SORTED, 0, AT>(acc, rec, recf, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
+        else lean_pair_loop<NL, NC, LPA, SORTED, 1, AT>(acc, rec, recf, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
       } else {
-        lean_pair_loop<NL, NC, LPA, SORTED, 2>(acc, rec, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
+        lean_pair_loop<NL, NC, LPA, SORTED, 2, AT>(acc, rec, recf, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
       }
       // diagonal of identical lists: S0 = sum fcE^2, S1 = sum fcE^2 eps, eps = 1e-13 / r^2 (a 1e-14 correction: FP32 reciprocal)
       double S0 = 0.0, S1 = 0.0;
@@ -505,7 +576,14 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         }
       }
       double v[RA];
-      lean_group_reduce<M, LPA>(acc, lane, red, v);
+      if constexpr (F32A) {
+        double accd[M];
+#pragma unroll
+        for (int f = 0; f < M; f++) accd[f] = (double)acc[f];
+        lean_group_reduce<M, LPA>(accd, lane, red, v);
+      } else {
+        lean_group_reduce<M, LPA>(acc, lane, red, v);
+      }
 #pragma unroll
       for (int q = 0; q < RA; q++) {
         const int e = M >= LPA ? sl + q * LPA : (sl & (M - 1));

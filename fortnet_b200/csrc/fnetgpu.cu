@@ -829,11 +829,13 @@ static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
     int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
     if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
     const size_t extra = lean_cta_extra_bytes(T.F, cap, ctx->lean.stageBytes);
+    const bool f32a = ctx->precision == 32;   // FP32 pair arithmetic (acsf_lean.cuh)
     for (; G >= 1; G >>= 1) {
       AcsfLaunch Q;
-      const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows, ctx->leanSorted, G);
+      const size_t wb = lean_warp_smem_bytes(cap, T.F, ctx->lean.redRows, ctx->leanSorted, G, f32a);
       const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
-      if (rc == 0 && Q.path != FNET_PATH_DIRECT && Q.wpb == 4) { L = Q; L.lean = true; L.G = G; return 0; }
+      // bins too crowded to stage their candidates (PATH_DIRECT): the lean kernel walks the cell list with a full warp per atom
+      if (rc == 0 && Q.wpb == 4 && (Q.path != FNET_PATH_DIRECT || G == 1)) { L = Q; L.lean = true; L.G = G; return 0; }
       ctx->err.clear();
     }
   }
@@ -900,6 +902,14 @@ extern "C" int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx) {
 extern "C" int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot) {
   if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used) return -1;
   return ctx->slots[slot].lastPath;
+}
+
+// what the last ACSF value launch of the slot used: info[0] = 1 k_acsf_lean / 0 k_acsf, [1] = central atoms per
+// warp, [2] = neighbour capacity, [3] = staged candidates capacity, [4] = path, [5] = dynamic shared memory (bytes)
+extern "C" int fnetgpu_acsf_launch_info(const fnetgpu_ctx *ctx, int slot, int *info) {
+  if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used || !info) return 1;
+  for (int k = 0; k < 6; k++) info[k] = ctx->slots[slot].lastLaunch[k];
+  return 0;
 }
 
 extern "C" int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh) {
@@ -989,16 +999,20 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   } while (0)
 #define FNET_ACSF_LAUNCH_NS(PATH)                                                                              \
   do { if (ns == 1) FNET_ACSF_LAUNCH(1, PATH); else if (ns == 2) FNET_ACSF_LAUNCH(2, PATH); else FNET_ACSF_LAUNCH(4, PATH); } while (0)
+  s.lastLaunch[0] = L.lean ? 1 : 0; s.lastLaunch[1] = L.lean ? L.G : 1; s.lastLaunch[2] = L.cap; s.lastLaunch[3] = L.capC;
+  s.lastLaunch[4] = L.path; s.lastLaunch[5] = (int)L.smem;
   if (L.lean) {
     const LeanTables &LT = ctx->lean;
     const int f32 = std::is_same<real, float>::value ? 1 : 0;
-#define FNET_LEAN_LAUNCH(NL, NC, PATH, SORTED, G)                                                              \
+#define FNET_LEAN_LAUNCH2(NL, NC, PATH, SORTED, G, F32A)                                                        \
   do {                                                                                                         \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<NL, NC, PATH, SORTED, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
-    LAUNCH(ctx, K_ACSF, (k_acsf_lean<NL, NC, PATH, SORTED, G><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(     \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<NL, NC, PATH, SORTED, G, F32A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    LAUNCH(ctx, K_ACSF, (k_acsf_lean<NL, NC, PATH, SORTED, G, F32A><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>( \
                             L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, (void *)feat, f32, nFeat, zp, \
                             nExtSel, ctx->d_extIdx, ctx->d_flags)));                                           \
   } while (0)
+#define FNET_LEAN_LAUNCH(NL, NC, PATH, SORTED, G)                                                              \
+  do { if (f32) FNET_LEAN_LAUNCH2(NL, NC, PATH, SORTED, G, true); else FNET_LEAN_LAUNCH2(NL, NC, PATH, SORTED, G, false); } while (0)
 #define FNET_LEAN_LAUNCH_S(NL, NC, PATH)                                                                       \
   do {                                                                                                         \
     if (ctx->leanSorted) { if (L.G == 2) FNET_LEAN_LAUNCH(NL, NC, PATH, true, 2); else FNET_LEAN_LAUNCH(NL, NC, PATH, true, 1); } \
@@ -1007,13 +1021,19 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
     else FNET_LEAN_LAUNCH(NL, NC, PATH, false, 1);                                                             \
   } while (0)
 #define FNET_LEAN_LAUNCH_P(NL, NC)                                                                             \
-  do { if (L.path == FNET_PATH_STRUCT) FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STRUCT); else FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STAGED); } while (0)
+  do {                                                                                                         \
+    if (L.path == FNET_PATH_STRUCT) FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STRUCT);                              \
+    else if (L.path == FNET_PATH_STAGED) FNET_LEAN_LAUNCH_S(NL, NC, FNET_PATH_STAGED);                         \
+    else if (ctx->leanSorted) FNET_LEAN_LAUNCH(NL, NC, FNET_PATH_DIRECT, true, 1);                             \
+    else FNET_LEAN_LAUNCH(NL, NC, FNET_PATH_DIRECT, false, 1);                                                 \
+  } while (0)
     if (ctx->leanNC == 1) FNET_LEAN_LAUNCH_P(2, 1);
     else if (ctx->leanNC == 2) FNET_LEAN_LAUNCH_P(2, 2);
     else FNET_LEAN_LAUNCH_P(1, 4);
 #undef FNET_LEAN_LAUNCH_P
 #undef FNET_LEAN_LAUNCH_S
 #undef FNET_LEAN_LAUNCH
+#undef FNET_LEAN_LAUNCH2
     return 0;
   }
   const int ns = ctx->maxSlots <= 1 ? 1 : (ctx->maxSlots <= 2 ? 2 : 4);

@@ -163,6 +163,7 @@ struct Slot {
   double *d_lat = nullptr;          // [nStruct][9] lattice vectors (whole-structure ACSF path)
   int maxAtoms = 0;                 // largest structure
   int lastPath = -1;                // path of the last ACSF launch (fnetgpu_acsf_path_get)
+  int lastLaunch[6] = {0, 0, 0, 0, -1, 0};   // fnetgpu_acsf_launch_info
   int structPath = 1;               // whole-structure path allowed for the current lattices (reset by coords_update)
   double *d_fpos = nullptr;         // [N][3] folded positions (atom order)
   CRec *d_crec = nullptr;    // [N] 32-byte records in cell order (position, atom index, atomic number)

@@ -162,6 +162,10 @@ int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot);
 int fnetgpu_acsf_kernel_set(fnetgpu_ctx *ctx, int mode);
 /* 1: the configured functions run through k_acsf_lean, 0: k_acsf, -1: no configuration */
 int fnetgpu_acsf_kernel_get(const fnetgpu_ctx *ctx);
+/* what the last value launch of the slot actually used: info[0] = 1 k_acsf_lean / 0 k_acsf (the lean kernel needs the
+ * candidates staged in shared memory; bins with too many candidates fall back), [1] central atoms per warp,
+ * [2] neighbour capacity, [3] staged-candidate capacity, [4] path (as fnetgpu_acsf_path_get), [5] shared memory bytes */
+int fnetgpu_acsf_launch_info(const fnetgpu_ctx *ctx, int slot, int *info /* [6] */);
 /* Subnetwork kernels in precision 64.  mode 0 (default): FP64 tensor-core (DMMA) kernels when the
  * network fits their limits (sum of layer widths <= 128, <= 72 8x8 weight-gradient tiles, shared
  * memory), else the register-tiled DFMA kernels -- and, for single-species datasets with <= 64
