@@ -245,6 +245,18 @@ class Bpnn:
 
     set_params = serial_weights_and_biases_fillup
 
+    def set_regularization(self, strength=0.0, alpha=0.0, n_datapoints=0.0):
+        """``TBpnn_update``'s gradient post-processing on the device (bpnn.F90:750-767): elastic-net term
+        (nestedtypes.F90:336-370) and division by sum(weights); (0, *, 0) switches both off."""
+        self.ctx._check(self.ctx._lib.fnetgpu_regularization_set(self.ctx._h, C.c_double(strength), C.c_double(alpha),
+                                                                 C.c_double(n_datapoints)))
+
+    def regularization_loss(self):
+        """``reguLoss`` of every species for the current parameters (loss.F90:119-196)"""
+        out = np.zeros(self.n_species)
+        self.ctx._check(self.ctx._lib.fnetgpu_regularization_loss(self.ctx._h, _p(out)))
+        return out
+
     def update_gradients(self, slot, loss="mse", shuffle=None, want_global=False, fetch=True):
         """``updateGradients`` + ``loss`` (bpnn.F90:277-283, 394-481).
         Returns (ddSerial (nSpecies,nTot), loss[, globalPredictions (nStruct,nG)])."""

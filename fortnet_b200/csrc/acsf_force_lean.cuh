@@ -49,7 +49,7 @@ template <int NL, int NC, int PATH, bool SORTED, int G, bool LOCAL>
 __global__ void __launch_bounds__(128, (NL * NC <= 2 ? 4 : 3))
 k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int cap, int capC, int localAtoms,
                   const double *__restrict__ dEdG, int nOut, const double *__restrict__ zprec,
-                  double *__restrict__ forces, int *__restrict__ flags) {
+                  double *__restrict__ forces, double *__restrict__ fpart, int *__restrict__ flags) {
   constexpr int MH = NC * FNET_LADDER;              // coefficients per lambda-group
   constexpr int M = NL * MH;
   constexpr int LPA = 32 / G;
@@ -435,13 +435,29 @@ k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int c
     }
     __syncwarp();
   }
-  if (LOCAL) {   // the CTA owns its structure: fixed-order sum of the warps' copies, plain stores
-    __syncthreads();
+  if (LOCAL) {   // fixed-order sum of the warps' copies, plain stores: to the forces when this CTA owns the whole structure,
+    __syncthreads();   // else to this CTA's partial (k_force_reduce sums the CTAs of a structure in a fixed order)
     const int nAt = cg.nCand;                       // atoms of the structure (PATH_STRUCT)
+    double *part = fpart + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * nOut + kt) * (size_t)(3 * localAtoms);
     for (int e = threadIdx.x; e < 3 * nAt; e += blockDim.x) {
       double s = 0.0;
       for (int w2 = 0; w2 < nw; w2++) s += *(const double *)(wbase + (size_t)w2 * wbytes + (size_t)G * gbytes + (size_t)e * sizeof(double));
-      forces[(size_t)stride * (cg.first + e / 3) + 3 * kt + e % 3] = s;
+      if (gridDim.y == 1) forces[(size_t)stride * (cg.first + e / 3) + 3 * kt + e % 3] = s;
+      else part[e] = s;
     }
   }
+}
+
+// forces of structures that were split over several CTAs (few, large structures: an MD step of one cell):
+// out = sum over the nSplit partials in a fixed order
+__global__ void k_force_reduce(int nStruct, int nSplit, int nOut, int localAtoms, const int *__restrict__ offsets,
+                               const double *__restrict__ fpart, double *__restrict__ forces) {
+  const int st = blockIdx.y;
+  const int beg = offsets[st], nAt = offsets[st + 1] - beg;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // (k, 3 atom + c)
+  if (e >= nOut * 3 * nAt) return;
+  const int k = e / (3 * nAt), r = e % (3 * nAt);
+  double s = 0.0;
+  for (int y = 0; y < nSplit; y++) s += fpart[(((size_t)st * nSplit + y) * nOut + k) * (size_t)(3 * localAtoms) + r];
+  forces[(size_t)(3 * nOut) * (beg + r / 3) + 3 * k + r % 3] = s;
 }

@@ -73,6 +73,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   }
   { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0;
     ctx->mlpNoFuse = (pm && strcmp(pm, "nofuse") == 0) ? 1 : 0; }
+  { const char *pm = getenv("FNETGPU_GRAPHS"); ctx->useGraphs = !(pm && strcmp(pm, "0") == 0); }
   { const char *pm = getenv("FNETGPU_ACSF_KERNEL"); ctx->acsfGeneric = (pm && strcmp(pm, "generic") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
@@ -80,6 +81,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
 }
 
 static void free_slot(Slot &s) {
+  if (s.sockGraph) { cudaGraphExecDestroy(s.sockGraph); s.sockGraph = nullptr; }
   cudaFree(s.d_offsets); cudaFree(s.d_structOf); cudaFree(s.d_atnum); cudaFree(s.d_sp); cudaFree(s.d_periodic);
   cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
@@ -97,8 +99,9 @@ extern "C" int fnetgpu_finalize(fnetgpu_ctx *ctx) {
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) free_slot(ctx->slots[i]);
   cudaFree(ctx->d_rgroups); cudaFree(ctx->d_rfeat); cudaFree(ctx->d_rp1); cudaFree(ctx->d_rp2);
   cudaFree(ctx->d_apasses); cudaFree(ctx->d_lrad); cudaFree(ctx->d_lpass); cudaFree(ctx->d_powtab); cudaFree(ctx->d_pairtab); cudaFree(ctx->d_extIdx); cudaFree(ctx->d_zprec); cudaFree(ctx->d_wb);
-  cudaFree(ctx->d_wb64); cudaFree(ctx->d_conv); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_wb64); cudaFree(ctx->d_fpart); cudaFree(ctx->d_conv); cudaFree(ctx->d_partials); cudaFree(ctx->d_dd); cudaFree(ctx->d_flags);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_pinIn) cudaFreeHost(ctx->h_pinIn);
   if (ctx->comm && ctx->nccl) {
     typedef int (*destroy_t)(void *);
     destroy_t d = (destroy_t)dlsym(ctx->nccl, "ncclCommDestroy");
@@ -176,6 +179,7 @@ extern "C" int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kid, double *ms, long l
 static int ensure_pinned(fnetgpu_ctx *ctx, size_t n) {
   if (ctx->pinnedN >= n) return 0;
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_pinIn) cudaFreeHost(ctx->h_pinIn);
   ctx->h_pinned = nullptr; ctx->pinnedN = 0;
   CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinned, n * sizeof(double)));
   ctx->pinnedN = n;
@@ -604,7 +608,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
   T.apasses = ctx->d_apasses;
   if (dev_alloc(ctx, &ctx->d_zprec, (size_t)2 * std::max(F, 1))) return 1;
   ctx->haveZ = false;
-  ctx->acsfSet = true;
+  ctx->acsfSet = true; ctx->acsfEpoch++;
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].featValid = false; ctx->slots[i].maxNeigh = -1; ctx->slots[i].maxCand = -1; ctx->slots[i].okEpoch = 0; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -771,7 +775,7 @@ static GeomArgs geom_args(const Slot &s) {
   return g;
 }
 static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes, AcsfLaunch &L, int cap = -1, size_t extraCta = 0,
-                              bool wholeStructure = false) {
+                              bool wholeStructure = false, int atomsPerIter = 1) {
   L.path = FNET_PATH_STRUCT; L.staged = false;
   L.cap = cap > 0 ? cap : struct_cap(s);
   L.capC = (s.maxAtoms + 31) & ~31;
@@ -787,7 +791,15 @@ static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes,
   const long long want = 8LL * ctx->nSM;
   if ((long long)s.nStruct * nSplit < want)
     nSplit = (int)std::min<long long>((s.maxAtoms + L.wpb - 1) / L.wpb, (want + s.nStruct - 1) / s.nStruct);
-  L.nSplit = wholeStructure ? 1 : std::max(1, std::min(nSplit, 65535));
+  if (wholeStructure) {
+    // deterministic force accumulation: one CTA per structure; only when there are too few structures to fill the
+    // GPU (an MD step of one cell) the atoms are split over CTAs, whose partial forces k_force_reduce sums in order
+    const long long wantF = 2LL * ctx->nSM;
+    nSplit = 1;
+    if ((long long)s.nStruct < wantF)
+      nSplit = (int)std::min<long long>((s.maxAtoms + L.wpb * atomsPerIter - 1) / (L.wpb * atomsPerIter), (wantF + s.nStruct - 1) / s.nStruct);
+  }
+  L.nSplit = std::max(1, std::min(nSplit, 65535));
   L.grid = dim3(s.nStruct, L.nSplit);
   return 0;
 }
@@ -861,7 +873,7 @@ static int plan_forces(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
     for (; G >= 1; G >>= 1) {
       AcsfLaunch Q;
       const size_t wb = force_lean_warp_bytes(cap, T.F, lean_M(ctx), ctx->leanSorted, G, localAtoms);
-      const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra, true) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
+      const int rc = structPath ? plan_struct_launch(ctx, s, wb, Q, cap, extra, true, G) : plan_acsf_launch(ctx, s, wb, Q, cap, extra);
       if (rc == 0 && Q.path != FNET_PATH_DIRECT && Q.wpb == 4) { L = Q; L.lean = true; L.G = G; L.local = structPath; return 0; }
       ctx->err.clear();
     }
@@ -1322,7 +1334,7 @@ extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, cons
   CUDA_TRY(ctx, cudaMalloc(&ctx->d_wb, bytes));
   if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
   if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
-  ctx->netSet = true; ctx->paramsSet = false;
+  ctx->netSet = true; ctx->paramsSet = false; ctx->netEpoch++;
   for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; }
   return 0;
 }
@@ -1517,6 +1529,54 @@ static int run_struct_loss(fnetgpu_ctx *ctx, Slot &s, int lossId) {
   return 0;
 }
 
+// TWeightDerivs_elasticNetRegularization (lib_common/nestedtypes.F90:336-370) + the division by the number of
+// datapoints of TBpnn_update (lib_nn/bpnn.F90:750-767) on the reduced gradient:
+//   dd(w) += lambda / nWeights * ((1 - alpha) w + alpha sign(w))  for the nW weight entries of every species, then dd *= inv
+template <typename real>
+__global__ void k_regularize(int nSpecies, int nTot, int nW, const real *__restrict__ wb, double *__restrict__ dd, double c,
+                             double alpha, double inv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nSpecies * nTot) return;
+  double g = dd[e];
+  if (e % nTot < nW) {
+    const double w = (double)wb[e];
+    const double sg = w > 0.0 ? 1.0 : (w < 0.0 ? -1.0 : 0.0);
+    g += c * ((1.0 - alpha) * w + alpha * sg);
+  }
+  dd[e] = g * inv;
+}
+
+// strength = 0 and nDatapoints <= 0 switch both off (the default: fnetgpu_grad returns the plain summed gradient)
+extern "C" int fnetgpu_regularization_set(fnetgpu_ctx *ctx, double strength, double alpha, double nDatapoints) {
+  CHECK_CTX(ctx);
+  if (strength < 0.0 || alpha < 0.0 || alpha > 1.0) FNET_FAIL(ctx, "regularization_set: need strength >= 0 and 0 <= alpha <= 1");
+  ctx->reguLambda = strength; ctx->reguAlpha = alpha; ctx->reguDiv = nDatapoints > 0.0 ? nDatapoints : 0.0;
+  return 0;
+}
+// reguLoss of every species (lib_common/loss.F90:119-196: lambda / nW ((1 - alpha) / 2 sum w^2 + alpha sum |w|)), from
+// the parameters on the device; out[nSpecies]
+extern "C" int fnetgpu_regularization_loss(fnetgpu_ctx *ctx, double *out) {
+  CHECK_CTX(ctx);
+  if (!ctx->netSet || !ctx->paramsSet) FNET_FAIL(ctx, "regularization_loss: network / parameters not set");
+  cudaSetDevice(ctx->device);
+  const NetTables &n = ctx->net;
+  const int nW = n.boff[0];
+  const size_t tot = (size_t)n.nTot * n.nSpecies;
+  std::vector<double> w(tot);
+  if (ctx->precision == 64) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(w.data(), ctx->d_wb, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    CUDA_TRY(ctx, cudaMemcpyAsync(w.data(), ctx->d_wb64, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int sp = 0; sp < n.nSpecies; sp++) {      // O(nW) numbers: summed on the host in the reference's order
+    double s2 = 0.0, s1 = 0.0;
+    for (int e = 0; e < nW; e++) { const double v = w[(size_t)n.nTot * sp + e]; s2 += v * v; s1 += fabs(v); }
+    out[sp] = ctx->reguLambda / (double)nW * ((1.0 - ctx->reguAlpha) / 2.0 * s2 + ctx->reguAlpha * s1);
+  }
+  return 0;
+}
+
 // the main stream must not touch d_dd before a pending all-reduce (side stream) is done with it
 static int wait_allreduce(fnetgpu_ctx *ctx) {
   if (!ctx->arPending) return 0;
@@ -1598,6 +1658,15 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
     if (allreduce_sum(ctx, ctx->d_dd, nDD + 2, ctx->arStream)) return 1;
     CUDA_TRY(ctx, cudaEventRecord(ctx->evAR, ctx->arStream));
     ctx->arPending = true;
+  }
+  if (ctx->reguLambda != 0.0 || ctx->reguDiv > 0.0) {   // regularised, normalised gradient (once, after the all-reduce)
+    if (wait_allreduce(ctx)) return 1;
+    const int nW = n.boff[0];
+    const double c = ctx->reguLambda / (double)nW, inv = ctx->reguDiv > 0.0 ? 1.0 / ctx->reguDiv : 1.0;
+    if (ctx->precision == 64)
+      LAUNCH(ctx, K_MISC, (k_regularize<double><<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(n.nSpecies, n.nTot, nW, (const double *)ctx->d_wb, ctx->d_dd, c, ctx->reguAlpha, inv)));
+    else
+      LAUNCH(ctx, K_MISC, (k_regularize<double><<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(n.nSpecies, n.nTot, nW, ctx->d_wb64, ctx->d_dd, c, ctx->reguAlpha, inv)));
   }
   if (ddSerial || loss) {
     if (wait_allreduce(ctx)) return 1;
@@ -1691,11 +1760,18 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   if (L.lean) {
     const LeanTables &LT = ctx->lean;
     const int localAtoms = L.local ? ((s.maxAtoms + 1) & ~1) : 0;
+    double *fpart = nullptr;
+    if (L.local && L.nSplit > 1) {       // partial forces of the CTAs of a structure
+      const size_t need = (size_t)s.nStruct * L.nSplit * n.nOut * 3 * localAtoms;
+      if (dev_reserve(ctx, &ctx->d_fpart, &ctx->fpartN, need)) return 1;
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_fpart, 0, need * sizeof(double), ctx->stream));   // CTAs without atoms write nothing
+      fpart = ctx->d_fpart;
+    }
 #define FNET_FLEAN(NL, NC, PATH, SORTED, G, LOCAL)                                                               \
   do {                                                                                                          \
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
     LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL><<<g, L.wpb * 32, L.smem, ctx->stream>>>( \
-                                  L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, s.d_forces, ctx->d_flags))); \
+                                  L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, s.d_forces, fpart, ctx->d_flags))); \
   } while (0)
 #define FNET_FLEAN_S(NL, NC, PATH, LOCAL)                                                                        \
   do {                                                                                                          \
@@ -1712,6 +1788,10 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 #undef FNET_FLEAN_P
 #undef FNET_FLEAN_S
 #undef FNET_FLEAN
+    if (fpart) {
+      const dim3 rg((n.nOut * 3 * s.maxAtoms + 127) / 128, s.nStruct);
+      LAUNCH(ctx, K_ACSF_FORCE, (k_force_reduce<<<rg, 128, 0, ctx->stream>>>(s.nStruct, L.nSplit, n.nOut, localAtoms, s.d_offsets, fpart, s.d_forces)));
+    }
     return 0;
   }
 #define FNET_FORCE_LAUNCH(PATH)                                                                                 \
@@ -1817,36 +1897,95 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
   bool done = false;
   if (ctx->precision == 64) {
     for (int attempt = 0; attempt < 3 && !done && use_struct_path(ctx, s); attempt++) {
-      CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      if (latvecs) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, latvecs, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
-      }
+      if (latvecs) s.h_lat.assign(latvecs, latvecs + (size_t)9 * s.nStruct);
       s.cellRc = -1.0; s.neighStale = true; s.geomEpoch++;
       const double *zp = s.zscored ? ctx->d_zprec : nullptr;
       AcsfLaunch Lv, Lf;
       if (plan_values(ctx, s, true, Lv)) return 1;
       if (plan_forces(ctx, s, true, Lf)) return 1;
-      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
-      if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;
-      s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
-      if (check_ready<double>(ctx, s, false)) return 1;
-      if (run_forward<double>(ctx, s)) return 1;
-      if (ensure_force_buffers(ctx, s, sizeof(double))) return 1;
-      if (run_ingrad<double>(ctx, s)) return 1;
-      CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));
-      if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
       if (ensure_pinned(ctx, nRaw + nFrc + 16)) return 1;
-      double *hp = ctx->h_pinned;
-      CUDA_TRY(ctx, cudaMemcpyAsync(hp, s.d_raw, nRaw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw + nFrc, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      const size_t nIn = (size_t)3 * s.N + (size_t)9 * s.nStruct;
+      if (ctx->pinInN < nIn) {
+        if (ctx->h_pinIn) cudaFreeHost(ctx->h_pinIn);
+        ctx->h_pinIn = nullptr; ctx->pinInN = 0;
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinIn, nIn * sizeof(double)));
+        ctx->pinInN = nIn;
+      }
+      double *hp = ctx->h_pinned, *hin = ctx->h_pinIn;
+      // the step's device work: geometry in, ACSF, subnetworks, input gradients, forces, results + flags out
+      auto enqueue = [&](const double *srcCoords, const double *srcLat) -> int {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, srcCoords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (srcLat) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, srcLat, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+        if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;
+        s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
+        if (check_ready<double>(ctx, s, false)) return 1;
+        if (run_forward<double>(ctx, s)) return 1;
+        if (ensure_force_buffers(ctx, s, sizeof(double))) return 1;
+        if (run_ingrad<double>(ctx, s)) return 1;
+        if (!Lf.local) CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));   // atomics path accumulates
+        if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(hp, s.d_raw, nRaw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw + nFrc, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+      };
+      // the sequence depends on the launch plans and the buffers only: captured once as a CUDA graph, replayed per
+      // MD step (one graph launch instead of 4-6 kernel launches, 3 memsets and 5 copies); the first step with a new
+      // plan runs eagerly (it may allocate), profiling runs eagerly (per-kernel events)
+      std::vector<long long> key = {
+          (long long)s.N, s.nStruct, T.F, n.nOut, Lv.cap, Lv.capC, Lv.G, (long long)Lv.lean, (long long)Lv.smem, Lv.nSplit,
+          Lf.cap, Lf.capC, Lf.G, (long long)Lf.lean, (long long)Lf.smem, Lf.nSplit, (long long)Lf.local, (long long)s.zscored,
+          (long long)(size_t)s.d_coords, (long long)(size_t)s.d_lat, (long long)(size_t)s.d_feat, (long long)(size_t)s.d_raw,
+          (long long)(size_t)s.d_dEdG, (long long)(size_t)s.d_forces, (long long)(size_t)hp, (long long)(size_t)hin,
+          (long long)(size_t)ctx->d_wb, (long long)(size_t)ctx->stream, ctx->mlpLegacy, ctx->mlpNoFuse, ctx->acsfGeneric,
+          (long long)(size_t)ctx->d_fpart, (long long)ctx->netEpoch, (long long)ctx->acsfEpoch};
+      const bool graphOk = !ctx->profiling && ctx->useGraphs;
+      if (graphOk && s.sockGraph && key == s.sockKey) {
+        memcpy(hin, coords, (size_t)3 * s.N * sizeof(double));
+        memcpy(hin + (size_t)3 * s.N, s.h_lat.data(), (size_t)9 * s.nStruct * sizeof(double));
+        CUDA_TRY(ctx, cudaGraphLaunch(s.sockGraph, ctx->stream));
+        ctx->launches += s.sockGraphLaunches;
+        s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
+      } else if (graphOk && s.sockKeyWanted == key) {
+        // second step with this plan: capture (everything is allocated by now), then replay
+        if (s.sockGraph) { cudaGraphExecDestroy(s.sockGraph); s.sockGraph = nullptr; }
+        memcpy(hin, coords, (size_t)3 * s.N * sizeof(double));
+        memcpy(hin + (size_t)3 * s.N, s.h_lat.data(), (size_t)9 * s.nStruct * sizeof(double));
+        const long long l0 = ctx->launches;
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int erc = enqueue(hin, hin + (size_t)3 * s.N);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (erc != 0 || ce != cudaSuccess || !g) {
+          if (g) cudaGraphDestroy(g);
+          cudaGetLastError();
+          ctx->useGraphs = false;                       // no graphs on this context any more: eager steps
+          s.sockKeyWanted.clear();
+          if (enqueue(coords, latvecs ? latvecs : nullptr)) return 1;
+        } else {
+          s.sockGraphLaunches = ctx->launches - l0;
+          ctx->launches = l0;
+          const cudaError_t ie = cudaGraphInstantiate(&s.sockGraph, g, 0);
+          cudaGraphDestroy(g);
+          if (ie != cudaSuccess) { s.sockGraph = nullptr; ctx->useGraphs = false; if (enqueue(coords, latvecs)) return 1; }
+          else {
+            s.sockKey = key;
+            CUDA_TRY(ctx, cudaGraphLaunch(s.sockGraph, ctx->stream));
+            ctx->launches += s.sockGraphLaunches;
+          }
+        }
+      } else {
+        if (enqueue(coords, latvecs)) return 1;
+        s.sockKeyWanted = key;
+      }
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       int h[8];
       memcpy(h, hp + nRaw + nFrc, sizeof(h));
       if (h[4] != 0) { s.structPath = 0; s.maxNeigh = -1; s.featValid = false; break; }   // lattice too small: general path below
       if (h[7] != 0) { s.featValid = false; break; }
       if (h[1] != 0) { s.maxNeigh = h[1]; s.featValid = false; continue; }               // neighbour buffers too small: retry
+      if (Lv.lean && h[0] > 0 && h[0] != s.maxNeigh) s.maxNeigh = std::max(s.maxNeigh, h[0]);   // capacity hint only grows here: a stable plan keeps the graph
       if (atomicPred) memcpy(atomicPred, hp, nRaw * sizeof(double));
       if (forces) memcpy(forces, hp + nRaw, nFrc * sizeof(double));
       if (globalPred)

@@ -164,6 +164,10 @@ struct Slot {
   int maxAtoms = 0;                 // largest structure
   int lastPath = -1;                // path of the last ACSF launch (fnetgpu_acsf_path_get)
   int lastLaunch[6] = {0, 0, 0, 0, -1, 0};   // fnetgpu_acsf_launch_info
+  // fnetgpu_socket_step as a CUDA graph: instantiated for one (launch plans, buffers) key
+  cudaGraphExec_t sockGraph = nullptr;
+  std::vector<long long> sockKey, sockKeyWanted;
+  long long sockGraphLaunches = 0;
   int structPath = 1;               // whole-structure path allowed for the current lattices (reset by coords_update)
   double *d_fpos = nullptr;         // [N][3] folded positions (atom order)
   CRec *d_crec = nullptr;    // [N] 32-byte records in cell order (position, atom index, atomic number)
@@ -251,12 +255,17 @@ struct fnetgpu_ctx {
   NetTables net;
   void *d_wb = nullptr;             // [nSpecies][nTot] real
   double *d_wb64 = nullptr;
+  double *d_fpart = nullptr; size_t fpartN = 0;   // partial forces of structures split over several CTAs (k_force_reduce)
   double *d_conv = nullptr; size_t convN = 0;   // FP32 mode: device-side float -> double staging of downloads
   bool paramsSet = false;
+  double reguLambda = 0.0, reguAlpha = 0.0, reguDiv = 0.0;   // fnetgpu_regularization_set
   // gradient work
   double *d_partials = nullptr; size_t partialsN = 0;
   double *d_dd = nullptr;           // [nSpecies*nTot + 2] reduced gradient + loss numerator/denominator
   double *h_pinned = nullptr; size_t pinnedN = 0;
+  double *h_pinIn = nullptr; size_t pinInN = 0;   // socket step: geometry staged for the graph's host-to-device copies
+  bool useGraphs = true;            // FNETGPU_GRAPHS=0: eager socket steps
+  long long acsfEpoch = 0, netEpoch = 0;
   int *d_flags = nullptr;           // [8] statistics / overflow flags (cells.cuh, acsf.cuh)
   int mlpNoFuse = 0;                // FNETGPU_MLP=nofuse / mlp_path_set(2): DMMA kernels without the fused per-structure sums (tests, A/B)
   int mlpLegacy = 0;                // FNETGPU_MLP=legacy: register-tiled DFMA kernels of mlp.cuh also in precision 64 (tests, A/B)

@@ -105,6 +105,14 @@ int fnetgpu_grad(fnetgpu_ctx *ctx, int slot, int lossId, const int *shuffle,
                  double *ddSerial /* [nTot*nSpecies] */, double *loss, double *globalPred /* [nG*nStruct] or NULL */);
 
 /* ---- prediction: TBpnn_predictBatch (bpnn.F90:1001-1058) and validation loss ---- */
+/* TBpnn_update's host work on the gradient moved to the device (lib_nn/bpnn.F90:750-767): with strength > 0 the
+ * elastic-net term of TWeightDerivs_elasticNetRegularization (lib_common/nestedtypes.F90:336-370; alpha = 0 ridge,
+ * 1 lasso) is added to the weight entries of ddSerial, and with nDatapoints > 0 (sum(trainDataset%weights),
+ * bpnn.F90:298-299) the gradient is divided by it -- both once, after the all-reduce.  strength = 0, nDatapoints <= 0
+ * (the default) leave fnetgpu_grad's plain summed gradient.  fnetgpu_regularization_loss returns reguLoss of every
+ * species (lib_common/loss.F90:119-196) for the current parameters, out[nSpecies]. */
+int fnetgpu_regularization_set(fnetgpu_ctx *ctx, double strength, double alpha, double nDatapoints);
+int fnetgpu_regularization_loss(fnetgpu_ctx *ctx, double *out);
 int fnetgpu_predict(fnetgpu_ctx *ctx, int slot, double *raw /* [nOut*N] = predicts(t,i), dataset atom order */);
 int fnetgpu_loss(fnetgpu_ctx *ctx, int slot, int lossId, double *loss);
 

@@ -67,18 +67,29 @@ class Case:
         return str(self.training.get("loss", "mse")).strip("'\"").lower()
 
     # --- TBpnn_update restated for SD (bpnn.F90:708-778) -----------------------------
-    def sd_update(self, wb, dd):
+    def regularization(self):
+        """(strength, alpha) of the case's Regularization block, (0, 0) without one"""
+        regu = self.training.get("regularization")
+        if not regu:
+            return 0.0, 0.0
+        kind = regu.get("_type")
+        return float(regu.get("strength", 0.0)), {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
+
+    def sd_update(self, wb, dd, pre_regularized=False):
+        """pre_regularized: dd already carries the elastic-net term and the division by sum(weights)
+        (fnetgpu_regularization_set: done on the device)"""
         tr = self.training
         nW = self.n_weights()
         dd = dd.copy()
         regu = tr.get("regularization")
-        if regu:
+        if regu and not pre_regularized:
             kind = regu.get("_type")
             lam = float(regu.get("strength", 0.0))
             alpha = {"ridge": 0.0, "lasso": 1.0}.get(kind, float(regu.get("alpha", 0.0)))
             w = wb[:, :nW]
             dd[:, :nW] += lam / nW * ((1.0 - alpha) * w + alpha * np.sign(w))
-        dd /= float(np.sum(self.dataset.weights))
+        if not pre_regularized:
+            dd /= float(np.sum(self.dataset.weights))
         lr = float(tr["learningrate"])
         maxd = float(tr["maxdisplacement"])
         thr = float(tr.get("threshold", 0.0))

@@ -149,3 +149,43 @@ def test_fresh_sd_training_step(fb, entry):
     keep[nW - int(case.dims[-1]):nW] = False           # the unused ww(d_L, 1) is not in the netstat file
     assert gio.allclose(wb1[:, keep], ref[:, keep]), gio.maxdiff(wb1[:, keep], ref[:, keep])
     ctx.close()
+
+
+_REGU = [e for e in _FRESH if "lossregu" in e["case"]]
+
+
+@pytest.mark.parametrize("entry", _REGU, ids=[e["case"] for e in _REGU])
+def test_fresh_training_step_regularized_on_device(fb, entry):
+    """input/lossregu/{ridge,lasso,elasticnet} with TBpnn_update's gradient post-processing on the GPU
+    (fnetgpu_regularization_set): elastic-net term + division by sum(weights) applied to the reduced gradient on the
+    device, optimiser step on the host -> golden theta_1; reguLoss against loss.F90:119-196 evaluated in numpy"""
+    import ranlux
+    from test_oracle_fresh_training import FreshCase
+    case = FreshCase(entry)
+    ds = case.dataset
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, fb.GFunctions(case.funcs), standardize=case.zmeans is not None, ext_indices=case.ext_indices)
+    acsf.calculate(0)
+    nsp = len(case.atomic_numbers)
+    net = fb.Bpnn(ctx, case.dims, nsp, case.activation)
+    wb0 = ranlux.initial_parameters(case.seed, case.dims, nsp)
+    net.set_params(wb0)
+    lam, alpha = case.regularization()
+    assert lam > 0.0 and entry["training"] == "sd"
+    net.set_regularization(lam, alpha, float(np.sum(ds.weights)))
+    dd, _loss = net.update_gradients(0, loss=case.loss_name())
+    wb1 = case.sd_update(wb0, dd, pre_regularized=True)[0]
+    ref = case.wb("ref_")
+    nW = case.n_weights()
+    keep = np.ones(wb1.shape[1], bool)
+    keep[nW - int(case.dims[-1]):nW] = False
+    assert gio.allclose(wb1[:, keep], ref[:, keep]), gio.maxdiff(wb1[:, keep], ref[:, keep])
+    w = wb0[:, :nW]
+    want = lam / nW * ((1.0 - alpha) / 2.0 * (w ** 2).sum(1) + alpha * np.abs(w).sum(1))
+    assert np.allclose(net.regularization_loss(), want, rtol=1e-12, atol=0.0)
+    net.set_regularization(0.0, 0.0, 0.0)                  # back to the plain summed gradient
+    dd_plain, _ = net.update_gradients(0, loss=case.loss_name())
+    wb1b = case.sd_update(wb0, dd_plain)[0]
+    assert gio.allclose(wb1b[:, keep], ref[:, keep])
+    ctx.close()
