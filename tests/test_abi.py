@@ -39,3 +39,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), "%s references the oracle" % f
+
+
+def test_fortran_shim_is_consistent_with_the_header():
+    """no Fortran compiler in this image: a structural check of fortnet_b200/host/fnet_gpu.F90 instead -- every bound C name
+    is declared in include/fnetgpu.h, every public name is defined in the module, blocks are balanced"""
+    src = open(os.path.join(ROOT, "fortnet_b200", "host", "fnet_gpu.F90")).read()
+    code = "\n".join(l.split("!")[0] if not l.strip().startswith("!") else "" for l in src.splitlines())
+    bound = set(re.findall(r"bind\(C,\s*name='(fnetgpu_[a-z_0-9]+)'\)", code))
+    decl = set(_declared_symbols())
+    assert bound and bound <= decl, sorted(bound - decl)
+    for must in ("fnetgpu_socket_step", "fnetgpu_loss", "fnetgpu_features_config", "fnetgpu_coords_update",
+                 "fnetgpu_comm_unique_id", "fnetgpu_comm_init", "fnetgpu_mg_init", "fnetgpu_mg_grad", "fnetgpu_regularization_set"):
+        assert must in bound, must
+    public = set()
+    for m in re.finditer(r"^\s*public\s*::\s*(.*)$", code, flags=re.M):
+        public |= {x.strip() for x in m.group(1).split(",") if x.strip()}
+    defined = set(re.findall(r"^\s*(?:subroutine|type\s*::)\s*(\w+)", code, flags=re.M | re.I))
+    assert public and public <= defined, sorted(public - defined)
+    assert "gpuSocketStep" in public and "gpuUnserialize" in public
+    low = code.lower()
+    assert len(re.findall(r"^\s*subroutine\s", low, flags=re.M)) == len(re.findall(r"^\s*end subroutine", low, flags=re.M))
+    assert len(re.findall(r"^\s*(?:integer\(c_int\)|type\(c_ptr\))\s+function\s", low, flags=re.M)) == \
+        len(re.findall(r"^\s*end function", low, flags=re.M))
