@@ -1094,9 +1094,13 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
     for (int attempt = 0; attempt < 4; attempt++) {
       AcsfLaunch L;
       const bool sp = use_struct_path(ctx, s);
-      if (sp) {
-        if (plan_values(ctx, s, true, L)) return 1;
-      } else {
+      if (sp && plan_values(ctx, s, true, L)) {
+        // the whole-structure buffers do not fit (very many neighbours per atom): the cell list takes the slot
+        ctx->err.clear();
+        s.structPath = 0; s.maxNeigh = -1;
+        continue;
+      }
+      if (!sp) {
         if (h_coords) {                         // the cell list is built from the device copy: plain upload first
           CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, h_coords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
           h_coords = nullptr;
