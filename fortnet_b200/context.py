@@ -160,6 +160,12 @@ class Context:
             raise FnetGpuError("acsf_launch_info: empty slot")
         return dict(zip(["lean", "atoms_per_warp", "cap", "cap_candidates", "path", "smem_bytes"], [int(v) for v in info]))
 
+    def measure_peaks(self):
+        """live FP64 FMA / FP64 tensor (DMMA) / FP32 FMA issue rates of this device in T FMA/s"""
+        out = (C.c_double * 3)()
+        self._check(self._lib.fnetgpu_measure_peaks(self._h, out))
+        return dict(dfma_tfma_s=out[0], dmma_tfma_s=out[1], ffma_tfma_s=out[2])
+
     def max_neighbors(self, slot):
         m, mean = C.c_int(), C.c_double()
         self._check(self._lib.fnetgpu_max_neighbors(self._h, C.c_int(slot), C.byref(m), C.byref(mean)))

@@ -105,50 +105,11 @@ k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int c
     const CRec me = central_atom<PATH>(cg, act ? slot : a0);
     const int i = me.idx;
     // ---------------- neighbours (as in k_acsf_lean, plus the atom index of every neighbour) ----------------
-    int n = 0;
-    {
-      const double rc2 = tab.rcMax * tab.rcMax;
-      const bool per = PATH == FNET_PATH_STRUCT && cg.sg->periodic != 0;
-      const bool diag = PATH == FNET_PATH_STRUCT && cg.sg->diag != 0;
-      const StructGeom *__restrict__ sg = cg.sg;
-      for (int base = 0; base < cg.nCand; base += LPA) {
-        const int t = base + sl;
-        const bool valid = act && t < cg.nCand;
-        CRec r;
-        r.x = me.x; r.y = me.y; r.z = me.z; r.idx = -1; r.zs = 0;
-        if (valid) r = cg.cand[t];
-        double dx = r.x - me.x, dy = r.y - me.y, dz = r.z - me.z;
-        if (PATH == FNET_PATH_STRUCT) {
-          const double magic = 6755399441055744.0;
-          if (diag) {
-            const double n0 = (sg->inv[0] * dx + magic) - magic;
-            const double n1 = (sg->inv[4] * dy + magic) - magic;
-            const double n2 = (sg->inv[8] * dz + magic) - magic;
-            dx -= n0 * sg->lat[0]; dy -= n1 * sg->lat[4]; dz -= n2 * sg->lat[8];
-          } else if (per) {
-            const double n0 = (sg->inv[0] * dx + sg->inv[1] * dy + sg->inv[2] * dz + magic) - magic;
-            const double n1 = (sg->inv[3] * dx + sg->inv[4] * dy + sg->inv[5] * dz + magic) - magic;
-            const double n2 = (sg->inv[6] * dx + sg->inv[7] * dy + sg->inv[8] * dz + magic) - magic;
-            dx -= n0 * sg->lat[0] + n1 * sg->lat[3] + n2 * sg->lat[6];
-            dy -= n0 * sg->lat[1] + n1 * sg->lat[4] + n2 * sg->lat[7];
-            dz -= n0 * sg->lat[2] + n1 * sg->lat[5] + n2 * sg->lat[8];
-          }
-        }
-        const bool ok = is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, i);
-        const unsigned mg = (__ballot_sync(0xffffffffu, ok) >> gshift) & lowmask;
-        const int pos = n + __popc(mg & ltmask);
-        if (ok && pos < cap - 1) {
-          if (SORTED) {
-            gx[pos] = dx; gy[pos] = dy; gz[pos] = dz; gi[pos] = r.idx;
-            gc[pos] = (r.idx == i) ? tab.nCodes + 1 : (int)zcode[(r.zs & ~FNET_SHIFT_FLAG) & 127];
-          } else {
-            double *q = rec + (size_t)FNET_FREC * pos;
-            q[0] = dx; q[1] = dy; q[2] = dz; ((int *)(q + 9))[0] = r.idx;
-          }
-        }
-        n += __popc(mg);
-      }
-    }
+    const int n0 = lean_gather_linear<PATH, SORTED, G, FNET_FREC, true>(cg, tab, me, act, cap, (double *)wb, (double *)wb + (gx - rec),
+                                                                        (double *)wb + (gy - rec), (double *)wb + (gz - rec),
+                                                                        (int *)wb + (gc - (int *)rec), (int *)wb + (gi - (int *)rec),
+                                                                        gbytes, zcode, lane);
+    int n = n0;
     if (n > cap - 1) {
       if (sl == 0) atomicMax(&flags[1], n + 1);
       act = false; n = 0;

@@ -298,6 +298,85 @@ __device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER],
   }
 }
 
+// Neighbour gather over a LINEAR candidate array (whole structure: minimum image; staged bin candidates) for the G
+// central atoms of a warp at once: every lane loads ONE candidate per sweep and tests it against all G central atoms
+// (their coordinates live in registers), so a sweep costs 2 shared-memory loads + G distance tests for 32 candidates --
+// G times fewer sweeps than one candidate array walk per group.  Accepted candidates are compacted (ballot) in candidate
+// order into group q's arrays: displacements to rec[RS * pos + 0..2] (or the unsorted scratch when SORTED, with the
+// species code), atom indices when WITHIDX.  Returns this lane's group's neighbour count.
+template <int PATH, bool SORTED, int G, int RS, bool WITHIDX>
+__device__ __forceinline__ int lean_gather_linear(const CtaGeom &cg, const AcsfTables &tab, const CRec &me, bool act, int cap,
+                                                  double *rec0, double *gx0, double *gy0, double *gz0, int *gc0, int *gi0,
+                                                  size_t gbytes, const unsigned char *__restrict__ zcode, int lane) {
+  constexpr int LPA = 32 / G;
+  const int grp = lane / LPA;
+  const unsigned ltm = (1u << lane) - 1u;
+  const double rc2 = tab.rcMax * tab.rcMax;
+  double mx[G], my[G], mz[G];
+  int mi[G], nq[G];
+  bool aq[G];
+#pragma unroll
+  for (int q = 0; q < G; q++) {
+    mx[q] = __shfl_sync(0xffffffffu, me.x, q * LPA); my[q] = __shfl_sync(0xffffffffu, me.y, q * LPA);
+    mz[q] = __shfl_sync(0xffffffffu, me.z, q * LPA); mi[q] = __shfl_sync(0xffffffffu, me.idx, q * LPA);
+    aq[q] = __shfl_sync(0xffffffffu, act ? 1 : 0, q * LPA) != 0;
+    nq[q] = 0;
+  }
+  const bool per = PATH == FNET_PATH_STRUCT && cg.sg->periodic != 0;
+  const bool diag = PATH == FNET_PATH_STRUCT && cg.sg->diag != 0;
+  const StructGeom *__restrict__ sg = cg.sg;
+  for (int base = 0; base < cg.nCand; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < cg.nCand;
+    CRec r;
+    r.x = 0.0; r.y = 0.0; r.z = 0.0; r.idx = -1; r.zs = 0;
+    if (valid) r = cg.cand[t];
+    int code = 0;
+    if (SORTED) code = (int)zcode[(r.zs & ~FNET_SHIFT_FLAG) & 127];
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+      double dx = r.x - mx[q], dy = r.y - my[q], dz = r.z - mz[q];
+      if (PATH == FNET_PATH_STRUCT) {                      // minimum image (cells.cuh for_each_candidate_struct)
+        const double magic = 6755399441055744.0;
+        if (diag) {
+          const double n0 = (sg->inv[0] * dx + magic) - magic;
+          const double n1 = (sg->inv[4] * dy + magic) - magic;
+          const double n2 = (sg->inv[8] * dz + magic) - magic;
+          dx -= n0 * sg->lat[0]; dy -= n1 * sg->lat[4]; dz -= n2 * sg->lat[8];
+        } else if (per) {
+          const double n0 = (sg->inv[0] * dx + sg->inv[1] * dy + sg->inv[2] * dz + magic) - magic;
+          const double n1 = (sg->inv[3] * dx + sg->inv[4] * dy + sg->inv[5] * dz + magic) - magic;
+          const double n2 = (sg->inv[6] * dx + sg->inv[7] * dy + sg->inv[8] * dz + magic) - magic;
+          dx -= n0 * sg->lat[0] + n1 * sg->lat[3] + n2 * sg->lat[6];
+          dy -= n0 * sg->lat[1] + n1 * sg->lat[4] + n2 * sg->lat[7];
+          dz -= n0 * sg->lat[2] + n1 * sg->lat[5] + n2 * sg->lat[8];
+        }
+      }
+      const bool ok = is_neighbor(valid && aq[q], dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, mi[q]);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      const int pos = nq[q] + __popc(m & ltm);
+      if (ok && pos < cap - 1) {
+        const size_t go = (size_t)q * gbytes;
+        if (SORTED) {
+          ((double *)((unsigned char *)gx0 + go))[pos] = dx; ((double *)((unsigned char *)gy0 + go))[pos] = dy;
+          ((double *)((unsigned char *)gz0 + go))[pos] = dz;
+          ((int *)((unsigned char *)gc0 + go))[pos] = (r.idx == mi[q]) ? tab.nCodes + 1 : code;
+          if (WITHIDX) ((int *)((unsigned char *)gi0 + go))[pos] = r.idx;
+        } else {
+          double *qq = (double *)((unsigned char *)rec0 + go) + (size_t)RS * pos;
+          qq[0] = dx; qq[1] = dy; qq[2] = dz;
+          if (WITHIDX) ((int *)(qq + RS - 1))[0] = r.idx;
+        }
+      }
+      nq[q] += __popc(m);
+    }
+  }
+  int n = nq[0];
+#pragma unroll
+  for (int q = 1; q < G; q++) n = (grp == q) ? nq[q] : n;
+  return n;
+}
+
 #ifndef FNET_LEAN_MINB
 #define FNET_LEAN_MINB 4
 #endif
@@ -390,34 +469,9 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         take(is_neighbor(valid && act, dx * dx + dy * dy + dz * dz, rc2, j, zs, i), dx, dy, dz, j, zs);
       });
     } else {
-      const bool per = PATH == FNET_PATH_STRUCT && cg.sg->periodic != 0;
-      const bool diag = PATH == FNET_PATH_STRUCT && cg.sg->diag != 0;
-      const StructGeom *__restrict__ sg = cg.sg;
-      for (int base = 0; base < cg.nCand; base += LPA) {
-        const int t = base + sl;
-        const bool valid = act && t < cg.nCand;
-        CRec r;
-        r.x = me.x; r.y = me.y; r.z = me.z; r.idx = -1; r.zs = 0;
-        if (valid) r = cg.cand[t];
-        double dx = r.x - me.x, dy = r.y - me.y, dz = r.z - me.z;
-        if (PATH == FNET_PATH_STRUCT) {                      // minimum image (cells.cuh for_each_candidate_struct)
-          const double magic = 6755399441055744.0;
-          if (diag) {
-            const double n0 = (sg->inv[0] * dx + magic) - magic;
-            const double n1 = (sg->inv[4] * dy + magic) - magic;
-            const double n2 = (sg->inv[8] * dz + magic) - magic;
-            dx -= n0 * sg->lat[0]; dy -= n1 * sg->lat[4]; dz -= n2 * sg->lat[8];
-          } else if (per) {
-            const double n0 = (sg->inv[0] * dx + sg->inv[1] * dy + sg->inv[2] * dz + magic) - magic;
-            const double n1 = (sg->inv[3] * dx + sg->inv[4] * dy + sg->inv[5] * dz + magic) - magic;
-            const double n2 = (sg->inv[6] * dx + sg->inv[7] * dy + sg->inv[8] * dz + magic) - magic;
-            dx -= n0 * sg->lat[0] + n1 * sg->lat[3] + n2 * sg->lat[6];
-            dy -= n0 * sg->lat[1] + n1 * sg->lat[4] + n2 * sg->lat[7];
-            dz -= n0 * sg->lat[2] + n1 * sg->lat[5] + n2 * sg->lat[8];
-          }
-        }
-        take(is_neighbor(valid, dx * dx + dy * dy + dz * dz, rc2, r.idx, r.zs, i), dx, dy, dz, r.idx, r.zs);
-      }
+      unsigned char *g0 = wb;                              // group 0's arrays; group q's are gbytes * q further
+      n = lean_gather_linear<PATH, SORTED, G, 6, false>(cg, tab, me, act, cap, (double *)g0, (double *)g0 + (gx - rec), (double *)g0 + (gy - rec),
+                                                        (double *)g0 + (gz - rec), (int *)g0 + (gc - (int *)rec), nullptr, gbytes, zcode, lane);
     }
     if (n > cap - 1) {                                       // one slot is the dummy neighbour
       if (sl == 0) atomicMax(&flags[1], n + 1);

@@ -26,6 +26,17 @@ extern "C" const char *fnetgpu_kernel_name(int kernelId) {
 
 static thread_local std::string g_err;  // errors before a context exists
 
+// dynamic shared memory opt-in of a kernel + the MAXIMUM shared-memory carve-out of the unified L1: without the explicit
+// preference the driver picks the split per launch from recent history, and a context that alternates kernels with
+// different footprints can settle on a smaller carve-out -- measured on this pool as one CTA per SM less for the ACSF
+// kernels (C3: 21.6 instead of 16.7 ms at identical clocks).  Occupancy must not depend on launch history.
+template <typename K>
+static cudaError_t fnet_smem_attr(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 #define CHECK_CTX(ctx) do { if (!(ctx)) { g_err = "null context"; return 1; } (ctx)->err.clear(); } while (0)
 #define CHECK_SLOT(ctx, slot)                                                        \
   do { if ((slot) < 0 || (slot) >= FNETGPU_MAX_SLOTS) FNET_FAIL(ctx, "slot out of range"); } while (0)
@@ -1004,7 +1015,7 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   geo.stBase = L.stBase;
 #define FNET_ACSF_LAUNCH(NS, PATH)                                                                             \
   do {                                                                                                         \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf<real, NS, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    CUDA_TRY(ctx, fnet_smem_attr(k_acsf<real, NS, PATH>, L.smem)); \
     LAUNCH(ctx, K_ACSF, (k_acsf<real, NS, PATH><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>(                   \
                             L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, feat, nFeat, zp, nExtSel,        \
                             ctx->d_extIdx, ctx->d_flags)));                                                    \
@@ -1018,7 +1029,7 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
     const int f32 = std::is_same<real, float>::value ? 1 : 0;
 #define FNET_LEAN_LAUNCH2(NL, NC, PATH, SORTED, G, F32A)                                                        \
   do {                                                                                                         \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_lean<NL, NC, PATH, SORTED, G, F32A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    CUDA_TRY(ctx, fnet_smem_attr(k_acsf_lean<NL, NC, PATH, SORTED, G, F32A>, L.smem)); \
     LAUNCH(ctx, K_ACSF, (k_acsf_lean<NL, NC, PATH, SORTED, G, F32A><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>( \
                             L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, (void *)feat, f32, nFeat, zp, \
                             nExtSel, ctx->d_extIdx, ctx->d_flags)));                                           \
@@ -1124,15 +1135,20 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
           CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
           for (int c = 0; c < 8; c++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evChunk[c], cudaEventDisableTiming));
         }
-        const int nChunk = std::max(1, std::min(8, s.nStruct / 512));
+        // chunks of doubling size (1 : 2 : 4 : 8): the first kernel starts after 1/15 of the copy, the copy of chunk
+        // c + 1 (twice the bytes, ~2.5x the kernel's rate per byte) hides behind the kernel of chunk c, and only four
+        // launches pay a partially filled last wave (eight equal chunks cost ~16 % of the kernel time in tails)
+        const int nChunk = s.nStruct >= 4096 ? 4 : (s.nStruct >= 1024 ? 2 : 1);
+        int bound[9];
+        for (int c = 0; c <= nChunk; c++) bound[c] = (int)((long long)s.nStruct * ((1 << c) - 1) / ((1 << nChunk) - 1));
         for (int c = 0; c < nChunk; c++) {
-          const int st0 = (int)((long long)s.nStruct * c / nChunk), st1 = (int)((long long)s.nStruct * (c + 1) / nChunk);
+          const int st0 = bound[c], st1 = bound[c + 1];
           const size_t a0 = s.h_offsets[st0], a1 = s.h_offsets[st1];
           CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords + 3 * a0, h_coords + 3 * a0, 3 * (a1 - a0) * sizeof(double), cudaMemcpyHostToDevice, ctx->copyStream));
           CUDA_TRY(ctx, cudaEventRecord(ctx->evChunk[c], ctx->copyStream));
         }
         for (int c = 0; c < nChunk; c++) {
-          const int st0 = (int)((long long)s.nStruct * c / nChunk), st1 = (int)((long long)s.nStruct * (c + 1) / nChunk);
+          const int st0 = bound[c], st1 = bound[c + 1];
           CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evChunk[c], 0));
           AcsfLaunch Lc = L;
           Lc.stBase = st0; Lc.grid = dim3(st1 - st0, L.nSplit);
@@ -1471,7 +1487,7 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
       const MmaLaunch M = plan_mma(ctx, s, 2);
 #define FNET_MMA_FWD(FCH)                                                                                         \
       do {                                                                                                        \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<2, 1, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<2, 1, FCH>, M.smem)); \
         const int fgrid = mma_grid(ctx, s, k_bpnn_mma<2, 1, FCH>, M.smem, M.grid);                                \
         LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(       \
                                    s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,          \
@@ -1484,7 +1500,7 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
     }
   }
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 2);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  CUDA_TRY(ctx, fnet_smem_attr(k_bpnn<real, 2>, B.smem));
   LAUNCH(ctx, K_MLP_FWD, (k_bpnn<real, 2><<<B.grid, B.threads, B.smem, ctx->stream>>>(
                              s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
                              s.tileT, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0, nullptr,
@@ -1501,7 +1517,7 @@ static int run_ingrad(fnetgpu_ctx *ctx, Slot &s) {
       const MmaLaunch M = plan_mma(ctx, s, 1);
 #define FNET_MMA_ING(FCH)                                                                                         \
       do {                                                                                                        \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<1, 1, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<1, 1, FCH>, M.smem)); \
         const int fgrid = mma_grid(ctx, s, k_bpnn_mma<1, 1, FCH>, M.smem, M.grid);                                \
         LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn_mma<1, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(    \
                                       s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,       \
@@ -1514,7 +1530,7 @@ static int run_ingrad(fnetgpu_ctx *ctx, Slot &s) {
     }
   }
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 1);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  CUDA_TRY(ctx, fnet_smem_attr(k_bpnn<real, 1>, B.smem));
   LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn<real, 1><<<B.grid, B.threads, B.smem, ctx->stream>>>(
                                 s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
                                 s.tileT, 0, s.d_structOf, s.d_offsets, nullptr, nullptr, nullptr, nullptr, s.nG, s.nA, 0,
@@ -1620,7 +1636,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
 #define FNET_MMA_GRAD2(NSLOT, FCH)                                                                                \
       do {                                                                                                        \
         if (fused) {                                                                                              \
-          CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT, FCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+          CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<0, NSLOT, FCH, true>, M.smem)); \
           LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH, true><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>( \
                                       s.nTilesS, s.d_tilesS, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                       (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, s.d_at,   \
@@ -1628,7 +1644,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                       s.d_gt, s.d_Es, s.d_lossPart)));                                            \
           break;                                                                                                  \
         }                                                                                                         \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn_mma<0, NSLOT, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<0, NSLOT, FCH>, M.smem)); \
         LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(   \
                                     s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                     (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
@@ -1641,7 +1657,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
     }
   }
   if (!launched) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_bpnn<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    CUDA_TRY(ctx, fnet_smem_attr(k_bpnn<real, 0>, B.smem));
     LAUNCH(ctx, K_MLP_GRAD, (k_bpnn<real, 0><<<grid, B.threads, B.smem, ctx->stream>>>(
                                 s.nTiles, s.d_tiles, s.d_perm, (const real *)s.d_feat, s.nFeat, (const real *)ctx->d_wb, n,
                                 s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
@@ -1773,7 +1789,7 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
     }
 #define FNET_FLEAN(NL, NC, PATH, SORTED, G, LOCAL)                                                               \
   do {                                                                                                          \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    CUDA_TRY(ctx, fnet_smem_attr(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, L.smem)); \
     LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL><<<g, L.wpb * 32, L.smem, ctx->stream>>>( \
                                   L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, s.d_forces, fpart, ctx->d_flags))); \
   } while (0)
@@ -1800,7 +1816,7 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
   }
 #define FNET_FORCE_LAUNCH(PATH)                                                                                 \
   do {                                                                                                          \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_acsf_force<PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem)); \
+    CUDA_TRY(ctx, fnet_smem_attr(k_acsf_force<PATH>, L.smem)); \
     LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<PATH><<<g, L.wpb * 32, L.smem, ctx->stream>>>(                      \
                                   L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp,         \
                                   s.d_forces, ctx->d_flags)));                                                  \
@@ -2019,6 +2035,64 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
         for (int i = s.h_offsets[st]; i < s.h_offsets[st + 1]; i++) e += raw[(size_t)n.nOut * i + k];
         globalPred[(size_t)n.nOut * st + k] = e;
       }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// live roofline denominators of THIS device (the pool's B200 boxes differ by up to 30 % in FP64-bound kernel time at the
+// same reported clocks): FP64 FMA, FP64 tensor (DMMA m8n8k4) and FP32 FMA issue rates in T FMA/s.  ~30 ms.
+// ------------------------------------------------------------------------------------------
+template <typename T, int CH>
+__global__ void k_peak_fma(int iters, T *out, T a, T b) {
+  T acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) acc[c] = (T)(threadIdx.x + c);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < CH; c++) acc[c] = acc[c] * a + b;
+  }
+  T sres = 0;
+#pragma unroll
+  for (int c = 0; c < CH; c++) sres += acc[c];
+  if (sres == (T)123456789) out[0] = sres;
+}
+template <int CH>
+__global__ void k_peak_dmma(int iters, double *out, double a, double b) {
+  double c0[CH], c1[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) { c0[c] = threadIdx.x; c1[c] = c; }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[c]), "+d"(c1[c]) : "d"(a), "d"(b));
+  }
+  double sres = 0;
+#pragma unroll
+  for (int c = 0; c < CH; c++) sres += c0[c] + c1[c];
+  if (sres == 123456789.0) out[0] = sres;
+}
+extern "C" int fnetgpu_measure_peaks(fnetgpu_ctx *ctx, double *out /* [3]: DFMA, DMMA, FFMA in T FMA/s */) {
+  CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  const int iters = 2048, threads = 256, ctas = ctx->nSM * 8;
+  double *scratch = (double *)ctx->d_flags;    // never written (the guard value cannot occur)
+  auto timeit = [&](auto launch, double fmaPerLaunch, double &res) -> int {
+    launch();
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < 3; r++) launch();
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res = fmaPerLaunch * 3.0 / (ms * 1e-3) / 1e12;
+    return 0;
+  };
+  const double lanes = (double)ctas * threads;
+  if (timeit([&] { k_peak_fma<double, 8><<<ctas, threads, 0, ctx->stream>>>(iters, scratch, 1.0000001, 1e-9); }, lanes * iters * 8.0, out[0])) return 1;
+  if (timeit([&] { k_peak_dmma<8><<<ctas, threads, 0, ctx->stream>>>(iters, scratch, 1.0000001, 1e-9); }, (double)ctas * (threads / 32) * iters * 8.0 * 256.0, out[1])) return 1;
+  if (timeit([&] { k_peak_fma<float, 8><<<ctas, threads, 0, ctx->stream>>>(iters, (float *)scratch, 1.0000001f, 1e-9f); }, lanes * iters * 8.0, out[2])) return 1;
   return 0;
 }
 

@@ -153,6 +153,8 @@ int fnetgpu_profile(fnetgpu_ctx *ctx, int enable);
 int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kernelId, double *ms_total, long long *launches);
 const char *fnetgpu_kernel_name(int kernelId);                /* NULL past the last id */
 int fnetgpu_max_neighbors(fnetgpu_ctx *ctx, int slot, int *maxNeigh, double *meanNeigh);
+/* live roofline denominators of this device: FP64 FMA, FP64 tensor (DMMA) and FP32 FMA issue rates, T FMA/s (~30 ms) */
+int fnetgpu_measure_peaks(fnetgpu_ctx *ctx, double *out /* [3] */);
 /* Neighbour search of the ACSF kernels.  mode 0 (default): automatic -- datasets whose structures
  * all have <= 256 atoms and lattice-plane spacings >= 2 rc (or are clusters) take the
  * whole-structure / minimum-image path, everything else the cell list (what replaces
