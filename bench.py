@@ -408,6 +408,11 @@ def main():
         mean_neigh = ctx.max_neighbors(0)[1]          # builds the cell list once: outside every timed region
     except Exception:
         pass
+    grad_launch = None
+    try:
+        grad_launch = ctx.grad_launch_info(0)         # 0 two passes / 1 fused sums / 2 cluster-fused sums, cluster size, grid
+    except Exception:
+        pass
     live_peaks = None
     try:
         live_peaks = ctx.measure_peaks()              # this box, now (outside every timed region)
@@ -501,6 +506,7 @@ def main():
             "roofline_fp64": roof64,
             "box_peaks_now": live_peaks,
             "kernel_ms_per_step": kshare,
+            "grad_launch": grad_launch,
             "loss": loss,
         }
         if c4 is not None:

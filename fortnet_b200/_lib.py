@@ -18,7 +18,7 @@ SYMBOLS = [
     "fnetgpu_launch_count", "fnetgpu_profile", "fnetgpu_profile_get", "fnetgpu_kernel_name",
     "fnetgpu_max_neighbors", "fnetgpu_acsf_path_set", "fnetgpu_acsf_path_get",
     "fnetgpu_mlp_path_set", "fnetgpu_mlp_path_get", "fnetgpu_socket_step", "fnetgpu_acsf_update_calculate",
-    "fnetgpu_acsf_kernel_set", "fnetgpu_acsf_kernel_get", "fnetgpu_acsf_launch_info",
+    "fnetgpu_acsf_kernel_set", "fnetgpu_acsf_kernel_get", "fnetgpu_acsf_launch_info", "fnetgpu_grad_launch_info",
     "fnetgpu_regularization_set", "fnetgpu_regularization_loss", "fnetgpu_measure_peaks",
     "fnetgpu_mg_init", "fnetgpu_mg_finalize", "fnetgpu_mg_last_error", "fnetgpu_mg_device_count", "fnetgpu_mg_context",
     "fnetgpu_mg_shard", "fnetgpu_mg_dataset_upload", "fnetgpu_mg_coords_update", "fnetgpu_mg_acsf_set",

@@ -160,6 +160,13 @@ class Context:
             raise FnetGpuError("acsf_launch_info: empty slot")
         return dict(zip(["lean", "atoms_per_warp", "cap", "cap_candidates", "path", "smem_bytes"], [int(v) for v in info]))
 
+    def grad_launch_info(self, slot):
+        """what the last update_gradients of the slot launched (fnetgpu_grad_launch_info)"""
+        info = (C.c_int * 4)()
+        if self._lib.fnetgpu_grad_launch_info(self._h, C.c_int(slot), info) != 0:
+            raise FnetGpuError("grad_launch_info: empty slot")
+        return dict(zip(["fusion", "cluster_size", "grid", "rounds"], [int(v) for v in info]))
+
     def measure_peaks(self):
         """live FP64 FMA / FP64 tensor (DMMA) / FP32 FMA issue rates of this device in T FMA/s"""
         out = (C.c_double * 3)()

@@ -97,7 +97,7 @@ static void free_slot(Slot &s) {
   cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
   cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
-  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_tilesS); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
+  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_tilesS); cudaFree(s.d_tilesC); cudaFree(s.d_permC); cudaFree(s.d_segBE); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
   cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
   s = Slot();
 }
@@ -922,6 +922,11 @@ extern "C" int fnetgpu_mlp_path_get(const fnetgpu_ctx *ctx) {
   if (!ctx || !ctx->netSet) return -1;
   return (ctx->precision == 64 && !ctx->mlpLegacy && bpnn_mma_fits(ctx->net)) ? 1 : 0;
 }
+extern "C" int fnetgpu_grad_launch_info(const fnetgpu_ctx *ctx, int slot, int *info) {
+  if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used || !info) return 1;
+  for (int k = 0; k < 4; k++) info[k] = ctx->slots[slot].lastGrad[k];
+  return 0;
+}
 extern "C" int fnetgpu_acsf_path_get(const fnetgpu_ctx *ctx, int slot) {
   if (!ctx || slot < 0 || slot >= FNETGPU_MAX_SLOTS || !ctx->slots[slot].used) return -1;
   return ctx->slots[slot].lastPath;
@@ -1355,7 +1360,7 @@ extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, cons
   if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
   if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
   ctx->netSet = true; ctx->paramsSet = false; ctx->netEpoch++;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; }
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; ctx->slots[i].nTilesC = -1; }
   return 0;
 }
 
@@ -1605,6 +1610,142 @@ static int wait_allreduce(fnetgpu_ctx *ctx) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Cluster-fused per-structure sums (k_bpnn_mma<0, .., 2>, mlp_mma.cuh): multi-species data and structures of more than
+// 64 atoms get E_s / the loss gradient inside the gradient kernel too.  Consecutive structures are packed into groups
+// whose species-homogeneous rounds (<= 64 atoms) number <= CS; the CS CTAs of a thread-block cluster take one round
+// each and exchange their partial sums through distributed shared memory.  CS is chosen per dataset from the
+// co-resident clusters the device reports (cudaOccupancyMaxActiveClusters: GPC sizes strand SMs for some CS) and
+// the padding of the groups; when the two-pass path (forward kernel + k_struct_loss + gradient kernel) is estimated
+// cheaper -- or a structure needs more than 8 rounds -- it stays.
+// ------------------------------------------------------------------------------------------
+typedef void (*MmaKernelT)(int, const int *, const int *, const double *, int, const double *, NetTables, const int *,
+                           const int *, const double *, const double *, const double *, const double *, int, int, int,
+                           double *, double *, const double *, double *, double *, const int *);
+static MmaKernelT mma_cluster_kernel(const NetTables &n) {
+  const MmaLayout ml = mma_layout(n);
+  const int perWarp = (ml.nGradTiles + FNET_MMA_WARPS - 1) / FNET_MMA_WARPS;
+  const bool f1 = n.dims[0] <= 32;
+  if (perWarp <= 4) return f1 ? (MmaKernelT)k_bpnn_mma<0, 4, 1, 2> : (MmaKernelT)k_bpnn_mma<0, 4, 2, 2>;
+  return f1 ? (MmaKernelT)k_bpnn_mma<0, FNET_MMA_MAXSLOTS, 1, 2> : (MmaKernelT)k_bpnn_mma<0, FNET_MMA_MAXSLOTS, 2, 2>;
+}
+struct ClusterPlan { int CS = 0, nSuper = 0; double cost = 0.0; std::vector<int> tiles, perm, seg; };
+// spCount: [nStruct][nSp] atoms per structure and species; false: some structure needs more than CS rounds
+static bool build_cluster_plan(const Slot &s, const std::vector<int> &spCount, int CS, bool fill, ClusterPlan &P) {
+  const int R = FNET_MMA_TA * FNET_MMA_WARPS;
+  const int nSp = (int)s.spBeg.size() - 1;
+  P.CS = CS; P.nSuper = 0; P.cost = 0.0; P.tiles.clear();
+  if (fill) { P.perm.assign(s.N, 0); P.seg.assign(s.N, 0); }
+  std::vector<int> cnt(nSp), lastSp(CS, 0), run, runSt;
+  int st = 0, pos = 0;
+  while (st < s.nStruct) {
+    std::fill(cnt.begin(), cnt.end(), 0);
+    int e = st;
+    while (e < s.nStruct && e - st < FNET_MMA_CSLOTS) {
+      int rounds = 0;
+      for (int sp = 0; sp < nSp; sp++) rounds += (cnt[sp] + spCount[(size_t)e * nSp + sp] + R - 1) / R;
+      if (rounds > CS) break;
+      for (int sp = 0; sp < nSp; sp++) cnt[sp] += spCount[(size_t)e * nSp + sp];
+      e++;
+    }
+    if (e == st) return false;
+    int rank = 0, maxTiles = 0;
+    for (int sp = 0; sp < nSp; sp++) {
+      if (cnt[sp] == 0) continue;
+      const int nr = (cnt[sp] + R - 1) / R;
+      const int per = std::min(R, (((cnt[sp] + nr - 1) / nr) + 7) & ~7);
+      if (fill) {
+        run.clear(); runSt.clear();
+        for (int t = st; t < e; t++)
+          for (int i = s.h_offsets[t]; i < s.h_offsets[t + 1]; i++)
+            if (s.h_globalsp[i] == sp) { run.push_back(i); runSt.push_back(t); }
+      }
+      for (int q = 0; q < nr; q++) {
+        const int b = q * per, c = std::min(per, cnt[sp] - b);
+        maxTiles = std::max(maxTiles, (c + FNET_MMA_TW - 1) / FNET_MMA_TW);
+        P.tiles.push_back(pos); P.tiles.push_back(c); P.tiles.push_back(sp); P.tiles.push_back(st);
+        if (fill) {
+          for (int t = 0; t < c;) {           // segments: the atoms of one structure in this round
+            int segE = t + 1;
+            while (segE < c && runSt[b + segE] == runSt[b + t]) segE++;
+            for (int u = t; u < segE; u++) { P.perm[pos + u] = run[b + u]; P.seg[pos + u] = t | (segE << 16); }
+            t = segE;
+          }
+        }
+        pos += c;
+        lastSp[rank] = sp;
+        rank++;
+      }
+    }
+    for (; rank < CS; rank++) { P.tiles.push_back(0); P.tiles.push_back(0); P.tiles.push_back(lastSp[rank]); P.tiles.push_back(st); }
+    P.cost += (double)maxTiles + 1.0;
+    P.nSuper++;
+    st = e;
+  }
+  return true;
+}
+static int ensure_cluster_plan(fnetgpu_ctx *ctx, Slot &s) {
+  if (s.nTilesC >= 0) return 0;
+  s.nTilesC = 0;
+  const NetTables &n = ctx->net;
+  const int nSp = (int)s.spBeg.size() - 1;
+  if (s.nA != 0 || s.nG < 1 || nSp < 1) return 0;
+  const size_t smem = bpnn_mma_smem_bytes(n, 0, s.nG);
+  if (smem > 227 * 1024) return 0;
+  const char *env = getenv("FNETGPU_MLP_CLUSTER");          // 0: never; 2..8: pin the cluster size (tests, A/B)
+  const int pin = env ? atoi(env) : -1;
+  if (pin == 0) return 0;
+  MmaKernelT kc = mma_cluster_kernel(n);
+  if (fnet_smem_attr(kc, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const int R = FNET_MMA_TA * FNET_MMA_WARPS;
+  std::vector<int> spCount((size_t)s.nStruct * nSp, 0);
+  int minCS = 1;
+  for (int st = 0; st < s.nStruct; st++) {
+    for (int i = s.h_offsets[st]; i < s.h_offsets[st + 1]; i++) spCount[(size_t)st * nSp + s.h_globalsp[i]]++;
+    int rounds = 0;
+    for (int sp = 0; sp < nSp; sp++) rounds += (spCount[(size_t)st * nSp + sp] + R - 1) / R;
+    minCS = std::max(minCS, rounds);
+  }
+  if (minCS > 8) return 0;
+  // two-pass estimate in the same unit (16-atom tiles of the slowest warp pair + 1 per round, per resident CTA):
+  // the forward kernel costs about a third of the gradient kernel
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, FNET_MMA_WARPS * 32, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); return 0; }
+  double cost2 = 0.0;
+  int rounds2 = 0;
+  for (int sp = 0; sp < nSp; sp++) {
+    const int c = s.spBeg[sp + 1] - s.spBeg[sp];
+    cost2 += (double)(c / R) * (R / FNET_MMA_TW + 1) + ((c % R) ? (double)((c % R + FNET_MMA_TW - 1) / FNET_MMA_TW + 1) : 0.0);
+    rounds2 += (c + R - 1) / R;
+  }
+  double best = pin > 0 ? 1e300 : 1.35 * cost2 / (double)std::max(1, std::min(ctx->nSM * occ, rounds2));
+  ClusterPlan P, bestP;
+  int bestClusters = 0;
+  for (int CS = std::max(minCS, pin > 0 ? pin : 1); CS <= (pin > 0 ? pin : 8); CS++) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * ctx->nSM * occ); cfg.blockDim = dim3(FNET_MMA_WARPS * 32); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kc, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); continue; }
+    if (!build_cluster_plan(s, spCount, CS, false, P)) continue;
+    const double est = P.cost / (double)std::min(nc, P.nSuper);
+    if (est < best) { best = est; bestP.CS = CS; bestClusters = nc; }
+  }
+  if (bestP.CS == 0) return 0;
+  if (!build_cluster_plan(s, spCount, bestP.CS, true, bestP)) return 0;
+  if (dev_upload(ctx, &s.d_tilesC, bestP.tiles.data(), bestP.tiles.size())) return 1;
+  if (dev_upload(ctx, &s.d_permC, bestP.perm.data(), bestP.perm.size())) return 1;
+  if (dev_upload(ctx, &s.d_segBE, bestP.seg.data(), bestP.seg.size())) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the vectors go out of scope
+  s.clusterCS = bestP.CS;
+  s.clusterGrid = bestP.CS * std::max(1, std::min(bestClusters, bestP.nSuper));
+  s.nTilesC = bestP.nSuper;
+  return 0;
+}
+
 template <typename real>
 static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, double *loss, double *globalPred) {
   if (check_ready<real>(ctx, s, true)) return 1;
@@ -1614,15 +1755,24 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
   const bool mma = use_mma<real>(ctx);
   // every structure inside one round of the DMMA kernel: E_s, loss gradient and loss terms are formed
   // in the gradient kernel itself -- no separate forward pass, no k_struct_loss
-  const bool fused = mma && s.nTilesS > 0 && s.nA == 0 && s.nG >= 1 && !ctx->mlpNoFuse;
-  if (!fused) {
+  bool fused = mma && s.nTilesS > 0 && s.nA == 0 && s.nG >= 1 && !ctx->mlpNoFuse;
+  // ... or inside one super-round of a thread-block cluster
+  bool cfused = false;
+  if (mma && !fused && !ctx->mlpNoFuse) {
+    if (ensure_cluster_plan(ctx, s)) return 1;
+    cfused = s.nTilesC > 0;
+  }
+  if (!fused && !cfused) {
     if (run_forward<real>(ctx, s)) return 1;
     if (run_struct_loss<real>(ctx, s, lossId)) return 1;
   }
   const BpnnLaunch B = plan_bpnn<real>(ctx, s, 0);
   MmaLaunch M = plan_mma(ctx, s, 0);
   if (fused) M.grid = std::max(1, std::min(M.grid, s.nTilesS));
+  if (cfused) { M.grid = s.clusterGrid; M.smem = bpnn_mma_smem_bytes(n, 0, s.nG); }
   const int grid = mma ? M.grid : B.grid;
+  s.lastGrad[0] = cfused ? 2 : (fused ? 1 : 0); s.lastGrad[1] = cfused ? s.clusterCS : 1; s.lastGrad[2] = grid;
+  s.lastGrad[3] = cfused ? s.nTilesC : (fused ? s.nTilesS : (mma ? s.nTiles16 : s.nTiles));
   size_t need = (size_t)grid * nDD;
   if (ctx->partialsN < need) { if (dev_alloc(ctx, &ctx->d_partials, need)) return 1; ctx->partialsN = need; }
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_partials, 0, need * sizeof(double), ctx->stream));
@@ -1636,8 +1786,8 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
 #define FNET_MMA_GRAD2(NSLOT, FCH)                                                                                \
       do {                                                                                                        \
         if (fused) {                                                                                              \
-          CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<0, NSLOT, FCH, true>, M.smem)); \
-          LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH, true><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>( \
+          CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<0, NSLOT, FCH, 1>, M.smem)); \
+          LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH, 1><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>( \
                                       s.nTilesS, s.d_tilesS, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                       (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, s.d_at,   \
                                       s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr,    \
@@ -1650,7 +1800,22 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                     (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
                                     s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr)));   \
       } while (0)
-      if (perWarp <= 4) FNET_MMA_GRAD(4); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
+      if (cfused) {
+        MmaKernelT kc = mma_cluster_kernel(n);
+        CUDA_TRY(ctx, fnet_smem_attr(kc, M.smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FNET_MMA_WARPS * 32); cfg.dynamicSmemBytes = M.smem; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = s.clusterCS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LAUNCH(ctx, K_MLP_GRAD, (cudaLaunchKernelEx(&cfg, kc, s.nTilesC, (const int *)s.d_tilesC, (const int *)s.d_permC,
+                                                    (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, n,
+                                                    (const int *)s.d_structOf, (const int *)s.d_offsets, (const double *)nullptr,
+                                                    (const double *)s.d_at, (const double *)s.d_aw, (const double *)s.d_dsw, s.nG, s.nA,
+                                                    lossId, ctx->d_partials, (double *)nullptr, (const double *)s.d_gt, s.d_Es,
+                                                    s.d_lossPart, (const int *)s.d_segBE)));
+      } else if (perWarp <= 4) FNET_MMA_GRAD(4); else FNET_MMA_GRAD(FNET_MMA_MAXSLOTS);
 #undef FNET_MMA_GRAD
 #undef FNET_MMA_GRAD2
       launched = true;
@@ -1664,7 +1829,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                 lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
   }
   LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
-  if (fused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
+  if (fused || cfused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
   if (ctx->nRanks > 1 && ctx->comm) {
     // gradient | loss numerator | denominator: ONE all-reduce, on its own stream -- when the caller does not fetch the
     // result now, it overlaps whatever comes next on the main stream (the next step's ACSF kernel)

@@ -199,6 +199,11 @@ struct Slot {
   int *d_tiles = nullptr; int nTiles = 0, tileT = 0; // (start, count, species) triples
   int *d_tilesS = nullptr; int nTilesS = 0;          // structure-aligned rounds (fused per-structure sums), 0 = not applicable
   int *d_tiles16 = nullptr; int nTiles16 = 0;        // rounds (64 atoms of one species) of the FP64 tensor-core path (mlp_mma.cuh)
+  // cluster-fused per-structure sums (k_bpnn_mma<0,..,2>): super-rounds of clusterCS rounds holding whole structures
+  int *d_tilesC = nullptr, *d_permC = nullptr, *d_segBE = nullptr;
+  int nTilesC = -1;                 // super-rounds; -1 = not planned yet, 0 = not applicable
+  int clusterCS = 0, clusterGrid = 0;
+  int lastGrad[4] = {0, 0, 0, 0};   // fnetgpu_grad_launch_info
   // work buffers
   void *d_raw = nullptr;            // [N][nOut] real
   double *d_gS = nullptr;           // [nStruct][nG] loss gradients of the global targets

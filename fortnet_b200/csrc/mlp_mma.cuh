@@ -25,6 +25,7 @@
 // gain is issue slots and latency, not peak.  Precision 32, the input-gradient sweep of the
 // forces (MODE 1) and networks that do not fit the limits below stay on mlp.cuh.
 #pragma once
+#include <cooperative_groups.h>
 #include "mlp.cuh"
 
 #define FNET_MMA_TA 8              // atoms per warp (one m8 tile)
@@ -33,6 +34,7 @@
 #define FNET_MMA_WARPS 8
 #define FNET_MMA_TILES (FNET_MMA_WARPS / 2)
 #define FNET_MMA_MAXSLOTS 9        // weight-gradient output tiles a warp can own
+#define FNET_MMA_CSLOTS 32         // cluster-fused sums: structures per super-round (slots of the exchange buffer)
 
 __host__ __device__ inline int fnet_ru4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int fnet_ru8(int x) { return (x + 7) & ~7; }
@@ -82,9 +84,11 @@ __host__ __device__ inline MmaLayout mma_layout(const NetTables &net) {
   return m;
 }
 
-__host__ inline size_t bpnn_mma_smem_bytes(const NetTables &net, int mode) {
+// nGc >= 0: plus the double-buffered exchange area of the cluster-fused per-structure sums (nGc global targets)
+__host__ inline size_t bpnn_mma_smem_bytes(const NetTables &net, int mode, int nGc = -1) {
   const MmaLayout m = mma_layout(net);
-  return ((size_t)m.wTotal + FNET_EXP_TAB_N + (size_t)FNET_MMA_TILES * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS) * sizeof(double);
+  const size_t ex = nGc >= 0 ? (size_t)2 * FNET_MMA_CSLOTS * (nGc + 2) : 0;
+  return ((size_t)m.wTotal + FNET_EXP_TAB_N + (size_t)FNET_MMA_TILES * (mode == 2 ? m.rowsA : m.rows) * FNET_MMA_TS + ex) * sizeof(double);
 }
 // limits of this path (else mlp.cuh): bias accumulators are one per thread, gradient tiles
 // <= MAXSLOTS per warp, everything in 220 KB of shared memory
@@ -292,14 +296,21 @@ struct MmaWgradDispatch<0, NSLOT> {
 // (TBpnn_sysTrain, bpnn.F90:677-684; loss.F90:370-721) are formed inside the round, between the
 // forward and the backward sweep, so the separate forward kernel and k_struct_loss disappear and
 // every atom is propagated forward exactly once per iteration.
-template <int MODE, int NSLOT, int FCH, bool FUSED = false>
+// FUSED == 2 (cluster-fused): the same for multi-species data and structures of up to 64 x (cluster size) atoms.  The
+// kernel is launched as thread-block CLUSTERS; `tiles` holds SUPER-ROUNDS of CS entries (start, count, species, first
+// structure), one per CTA of the cluster: together the CS species-homogeneous rounds of a super-round hold all atoms of
+// a group of <= FNET_MMA_CSLOTS whole structures (`perm` is ordered group / species / structure / atom, `segBE` the
+// round-local range of every atom's structure).  After its forward sweep each CTA leaves the partial sums of its
+// structures in shared memory, the cluster synchronises (barrier.cluster) and every CTA reads the other CTAs' partial
+// sums through distributed shared memory in rank order: E_s, loss gradient and loss terms without a second forward pass.
+template <int MODE, int NSLOT, int FCH, int FUSED = 0>
 __global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 4 ? 2 : 1))
 k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
            int nFeat, const double *__restrict__ wb, NetTables net, const int *__restrict__ structOf,
            const int *__restrict__ offsets, const double *__restrict__ gS, const double *__restrict__ at,
            const double *__restrict__ aw, const double *__restrict__ dsw, int nG, int nA, int lossId,
            double *__restrict__ partials, double *__restrict__ raw, const double *__restrict__ gt = nullptr,
-           double *__restrict__ Es = nullptr, double *__restrict__ lossPart = nullptr) {
+           double *__restrict__ Es = nullptr, double *__restrict__ lossPart = nullptr, const int *__restrict__ segBE = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int TS = FNET_MMA_TS, TA = FNET_MMA_TA, TW = FNET_MMA_TW, NW = FNET_MMA_WARPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -314,6 +325,14 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   double *T = tiles0 + (size_t)(warp >> 1) * rows * TS + TA * (warp & 1);   // this warp's 8 columns of its tile
   for (int e = threadIdx.x; e < FNET_MMA_TILES * rows * TS; e += blockDim.x) tiles0[e] = 0.0;   // padding rows stay zero from here on
   __syncthreads();
+  // cluster-fused sums: CS CTAs walk the super-rounds of their cluster in lock step
+  int CS = 1, crank = 0;
+  double *exch = tiles0 + (size_t)FNET_MMA_TILES * rows * TS;   // [2][FNET_MMA_CSLOTS][nG + 2]: E partials | sum of aw | atoms present
+  if (FUSED == 2) {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    CS = (int)cl.num_blocks(); crank = (int)cl.block_rank();
+  }
+  const int ES = FUSED == 2 ? 4 : 3;              // ints per entry
 
   // ---- weight-gradient tiles owned by this warp: q = warp*per + s <-> (layer, i-tile, o-tile) ----
   int aRow[NSLOT], dRow[NSLOT], gInfo[NSLOT];
@@ -380,17 +399,22 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   //   entries two rounds ahead, atom indices two rounds ahead, feature rows of round r+2 pulled
   //   into L2, feature rows of round r+1 loaded into registers (pf) while round r's weight
   //   gradients are accumulated (MODE 0) / its hidden layers are evaluated (MODE 2).
-  const int round0 = (int)(((long long)nTiles * blockIdx.x) / gridDim.x);
-  const int round1 = (int)(((long long)nTiles * (blockIdx.x + 1)) / gridDim.x);
+  const int nWalk = gridDim.x / CS, walker = blockIdx.x / CS;   // CTAs (clusters) that share the rounds (super-rounds)
+  const int round0 = (int)(((long long)nTiles * walker) / nWalk);
+  const int round1 = (int)(((long long)nTiles * (walker + 1)) / nWalk);
   int curSp = -1;
-  int e0[3] = {0, 0, 0}, e1[3] = {0, 0, 0};           // entries of round r and r + 1
+  int e0[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0};     // entries of round r and r + 1
   int atom0 = -1, atom1 = -1;                         // lane < 16: atom of this warp's tile in round r / r + 1
   double pf[FCH][TA];                                 // features of round r (lane <-> feature 32 ch + lane)
-  auto load_entry = [&](int r, int (&e)[3]) {
-    e[0] = e[1] = e[2] = 0;
-    if (r < round1) { e[0] = tiles[3 * r]; e[1] = tiles[3 * r + 1]; e[2] = tiles[3 * r + 2]; }
+  auto load_entry = [&](int r, int (&e)[4]) {
+    e[0] = e[1] = e[2] = e[3] = 0;
+    if (r < round1) {
+      const int *t = tiles + (size_t)ES * ((size_t)r * CS + crank);
+      e[0] = t[0]; e[1] = t[1]; e[2] = t[2];
+      if (FUSED == 2) e[3] = t[3];
+    }
   };
-  auto load_atom = [&](const int (&e)[3]) -> int {
+  auto load_atom = [&](const int (&e)[4]) -> int {
     const int cnt = min(max(e[1] - TA * warp, 0), TA);
     return (lane < cnt) ? perm[e[0] + TA * warp + lane] : -1;
   };
@@ -417,9 +441,13 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
                                                     // is swept with zero features so that no stale delta reaches the gradient sweep)
     const int count = min(max(e0[1] - TA * warp, 0), TA);
     const int myAtom = atom0;
-    int e2[3];
+    int e2[4];
     load_entry(r + 2, e2);
-    if (sp != curSp) {
+    if (FUSED == 2) {      // this round's half of the exchange area: its last readers passed the previous cluster barrier
+      double *ex = exch + (size_t)(r & 1) * FNET_MMA_CSLOTS * (nG + 2);
+      for (int e = threadIdx.x; e < FNET_MMA_CSLOTS * (nG + 2); e += blockDim.x) ex[e] = 0.0;
+    }
+    if (sp != curSp && (FUSED != 2 || e0[1] > 0)) {
       __syncthreads();
       if (MODE == 0 && curSp >= 0) flush(curSp);
       mma_load_weights(net, m, wb + (size_t)net.nTot * sp, wsm);
@@ -428,10 +456,11 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
     }
     // per-atom loss-gradient scale (MODE 0): issued now, consumed after the forward sweep
     double lgScale = 0.0, lgG0 = 0.0, lgG1 = 0.0, lgAw = 0.0, lgW = 0.0;
-    int lgStruct = 0, lgB = 0, lgE = 0;
+    int lgStruct = 0, lgB = 0, lgE = 0, lgSeg = 0;
     if (warp < nIn) {
       if (MODE == 0 && myAtom >= 0) {
         lgStruct = structOf[myAtom];
+        if (FUSED == 2) lgSeg = segBE[e0[0] + TA * warp + lane];
         lgB = offsets[lgStruct]; lgE = offsets[lgStruct + 1];
         lgAw = aw[myAtom]; lgW = dsw[lgStruct];
         lgScale = lgW * lgAw / (double)(lgE - lgB);   // bpnn.F90:446,698
@@ -487,7 +516,106 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         __syncwarp();
       }
     }
-    if (MODE == 0 && FUSED) {
+    if (MODE == 0 && FUSED == 2) {
+      // ---- cluster-fused: partial sums of this CTA's round -> exchange area; cluster barrier; totals in rank order ----
+      if (warp < nIn && lane < TA) T[m.sOff * TS + lane] = lgAw;       // atomic weights of the tile (0 for padding)
+      __syncthreads();
+      const int NF = nG + 2;                                           // fields per slot: E_k partials | sum of aw | atoms present
+      double *ex = exch + (size_t)(r & 1) * FNET_MMA_CSLOTS * NF;
+      const bool mine = warp < nIn && lane < TA && myAtom >= 0;
+      const int slot = lgStruct - e0[3];
+      bool lead = false, uni = false;
+      if (warp < nIn) {
+        int b = lgSeg & 0xffff, e = lgSeg >> 16;                       // this structure's atoms in this round, round-local
+        const int bU = __shfl_sync(0xffffffffu, b, 0), eU = __shfl_sync(0xffffffffu, e, 0);
+        uni = count > 0 && __all_sync(0xffffffffu, !mine || (b == bU && e == eU));
+        if (uni) { b = bU; e = eU; }
+        lead = mine && (TA * warp + lane == b);
+        for (int k = 0; k <= nG; k++) {                                // k == nG: the atomic weights (scratch row)
+          const size_t rowk = (size_t)(k < nG ? m.aOff[L - 1] + k : m.sOff) * TS;
+          double ek = 0.0;
+          if (uni) {
+            for (int i = b + lane; i < e; i += 32) ek += tiles0[(size_t)(i >> 4) * rows * TS + rowk + (i & 15)];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ek += __shfl_xor_sync(0xffffffffu, ek, o);
+          } else if (mine) {
+            for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {
+              const double *rp = tiles0 + (size_t)w2 * rows * TS + rowk;
+              const int t1 = min(e - TW * w2, TW);
+              for (int t = max(b - TW * w2, 0); t < t1; t++) ek += rp[t];
+            }
+          }
+          if (lead) ex[slot * NF + k] = ek;
+        }
+        if (lead) ex[slot * NF + nG + 1] = 1.0;
+      }
+      cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+      cl.sync();
+      if (warp < nIn) {
+        double *dL = T + m.dOff[L - 1] * TS;
+        double sw = 0.0, before = 0.0, E0 = 0.0, E1 = 0.0;
+        const bool fast = uni && NF <= 4;                              // warp-uniform
+        if (fast) {
+          // one structure for the whole warp: lane = (field, rank) -- every remote value is ONE load in flight per lane,
+          // summed over the ranks in rank order by shuffles
+          const int slotU = __shfl_sync(0xffffffffu, slot, 0);
+          const int f = lane >> 3, j = lane & 7;
+          double v = 0.0;
+          if (f < NF && j < CS) v = cl.map_shared_rank(ex, j)[slotU * NF + f];
+          double tot = 0.0, bef = 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const double x = __shfl_sync(0xffffffffu, v, (lane & ~7) + q);
+            tot += x;
+            if (q < crank) bef += x;
+          }
+          sw = __shfl_sync(0xffffffffu, tot, 8 * nG);
+          before = __shfl_sync(0xffffffffu, bef, 8 * (nG + 1));
+          E0 = __shfl_sync(0xffffffffu, tot, 0);
+          E1 = __shfl_sync(0xffffffffu, tot, nG > 1 ? 8 : 0);
+        } else if (mine) {
+          for (int j = 0; j < CS; j++) {
+            const double *rx = cl.map_shared_rank(ex, j) + slot * NF;
+            sw += rx[nG];
+            if (j < crank) before += rx[nG + 1];
+          }
+        }
+        if (mine) {
+          double ss = 0.0;
+          const bool writer = lead && before == 0.0;                  // first round (in rank order) that holds atoms of the structure
+          for (int k = 0; k < nG; k++) {
+            double ek = (k == 0) ? E0 : E1;
+            if (!fast) {
+              ek = 0.0;
+              for (int j = 0; j < CS; j++) ek += cl.map_shared_rank(ex, j)[slot * NF + k];
+            }
+            const double tv = (k == 0) ? lgG0 : (k == 1) ? lgG1 : gt[(size_t)nG * lgStruct + k];
+            dL[k * TS + lane] = loss_grad_fn(lossId, ek, tv) * lgScale;
+            if (writer) {
+              Es[(size_t)nG * lgStruct + k] = ek;
+              switch (lossId) {
+                case FNETGPU_LOSS_MAE: ss += fabs(tv - ek); break;
+                case FNETGPU_LOSS_MAPE: ss += fabs((tv - ek) / tv); break;
+                default: ss += (tv - ek) * (tv - ek);
+              }
+            }
+          }
+          if (writer) {
+            double lg;
+            switch (lossId) {
+              case FNETGPU_LOSS_RMS: lg = sqrt(ss / nG); break;
+              case FNETGPU_LOSS_MAPE: lg = 100.0 * ss / nG; break;
+              default: lg = ss / nG;
+            }
+            lossPart[2 * (size_t)lgStruct] = lgW * sw * lg;
+            lossPart[2 * (size_t)lgStruct + 1] = lgW * sw;
+          }
+        } else if (lane < TA) {
+          for (int k = 0; k < net.nOut; k++) dL[k * TS + lane] = 0.0;  // padding atoms
+        }
+      }
+    }
+    if (MODE == 0 && FUSED == 1) {
       // ---- per-structure sums across the warps of the round (fixed order), loss gradient, loss terms ----
       if (warp < nIn && lane < TA) T[m.sOff * TS + lane] = lgAw;       // atomic weights of the tile (0 for padding)
       __syncthreads();
@@ -527,13 +655,19 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
             }
           }
         }
-        if (lead) {
-          double sw = 0.0;
+        double sw = 0.0;                                             // sum of the structure's atomic weights
+        if (uni) {
+          for (int i = b + lane; i < e; i += 32) sw += tiles0[(size_t)(i >> 4) * rows * TS + (size_t)m.sOff * TS + (i & 15)];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        } else if (lead) {
           for (int w2 = b >> 4; w2 <= (e - 1) >> 4; w2++) {
             const double *rp = tiles0 + (size_t)w2 * rows * TS + m.sOff * TS;
             const int t1 = min(e - TW * w2, TW);
             for (int t = max(b - TW * w2, 0); t < t1; t++) sw += rp[t];
           }
+        }
+        if (lead) {
           double lg;
           switch (lossId) {
             case FNETGPU_LOSS_RMS: lg = sqrt(ss / nG); break;
@@ -626,9 +760,10 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
           asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
       }
     }
-    e0[0] = e1[0]; e0[1] = e1[1]; e0[2] = e1[2];
-    e1[0] = e2[0]; e1[1] = e2[1]; e1[2] = e2[2];
+    e0[0] = e1[0]; e0[1] = e1[1]; e0[2] = e1[2]; e0[3] = e1[3];
+    e1[0] = e2[0]; e1[1] = e2[1]; e1[2] = e2[2]; e1[3] = e2[3];
     atom0 = atom1; atom1 = atom2;
   }
   if (MODE == 0 && curSp >= 0) flush(curSp);
+  if (FUSED == 2) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still read its exchange area
 }

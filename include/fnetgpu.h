@@ -176,6 +176,12 @@ int fnetgpu_acsf_kernel_get(const fnetgpu_ctx *ctx);
  * candidates staged in shared memory; bins with too many candidates fall back), [1] central atoms per warp,
  * [2] neighbour capacity, [3] staged-candidate capacity, [4] path (as fnetgpu_acsf_path_get), [5] shared memory bytes */
 int fnetgpu_acsf_launch_info(const fnetgpu_ctx *ctx, int slot, int *info /* [6] */);
+/* what the last fnetgpu_grad of the slot launched: info[0] = 0 two passes (forward kernel, per-structure sums, gradient
+ * kernel), 1 per-structure sums fused into the gradient kernel (every structure inside one 64-atom round), 2 the same
+ * across a thread-block cluster (multi-species data / structures of up to 8 x 64 atoms: partial sums exchanged through
+ * distributed shared memory); [1] = cluster size, [2] = grid (CTAs), [3] = rounds (super-rounds for 2).
+ * FNETGPU_MLP_CLUSTER=0 disables mode 2, =2..8 pins its cluster size (tests, A/B). */
+int fnetgpu_grad_launch_info(const fnetgpu_ctx *ctx, int slot, int *info /* [4] */);
 /* Subnetwork kernels in precision 64.  mode 0 (default): FP64 tensor-core (DMMA) kernels when the
  * network fits their limits (sum of layer widths <= 128, <= 72 8x8 weight-gradient tiles, shared
  * memory), else the register-tiled DFMA kernels -- and, for single-species datasets with <= 64

@@ -42,7 +42,7 @@ STRUCT, CELLS = (2,), (0, 1)   # values of Context.acsf_path()
 
 
 def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, seed=3, acsf_path="auto",
-                expect_path=None, mlp="auto", expect_mlp=None, acsf_kernel="auto", expect_lean=None):
+                expect_path=None, mlp="auto", expect_mlp=None, acsf_kernel="auto", expect_lean=None, expect_fusion=None):
     """features (raw + z-scored), statistics, predictions, loss, gradient and forces vs the oracle"""
     fd = funcs.asdicts()
     nt = _nthreads()
@@ -83,6 +83,9 @@ def _full_check(fb, orc, ds, funcs, dims, act="tanh", loss="mse", forces=True, s
     raw_o = orc.predict(zref, ds.globalsp, dims, act, wb, nthreads=nt)
     assert np.allclose(raw, raw_o, rtol=RTOL, atol=ATOL), _md(raw, raw_o)
     dd, lossv, gpred = net.update_gradients(0, loss, want_global=True)
+    if expect_fusion is not None:     # 0 two passes, 1 sums fused into the gradient kernel, 2 fused across a thread-block cluster
+        gi = ctx.grad_launch_info(0)
+        assert gi["fusion"] == (expect_fusion if mlp == "auto" else 0), gi
     dd_o, raw_o2 = orc.grad(ds.offsets, zref, ds.globalsp, dims, act, wb, loss, ds.weights, ds.atomic_weights,
                             ds.gtargets, ds.atargets, nthreads=nt)
     assert np.allclose(dd, dd_o, rtol=RTOL, atol=ATOL * max(1.0, np.abs(dd_o).max())), _md(dd, dd_o)
@@ -118,7 +121,7 @@ def test_c2_si_bulk(fb, orc, path, mlp):
     ds = synthetic.si_bulk(n_struct=12, seed=20260001)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 16, 16)
     _full_check(fb, orc, ds, funcs, [32, 20, 20, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1,
-                expect_lean=1)
+                expect_lean=1, expect_fusion=1)
 
 
 KERNELS = ["auto", "generic"]   # ACSF value kernel: k_acsf_lean for automatic-scheme configurations, or always k_acsf
@@ -168,7 +171,87 @@ def test_c3_tio2(fb, orc, path, mlp):
     ds = synthetic.tio2(n_struct=3, seed=20260002)
     funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 8, 16).resolve_species([22, 8])
     assert len(funcs) == 64
-    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1)
+    _full_check(fb, orc, ds, funcs, [64, 32, 32, 32, 1], acsf_path=path, expect_path=STRUCT, mlp=mlp, expect_mlp=1,
+                expect_fusion=2)
+
+
+def _ragged_two_species(fb, seed, natoms, n_targets):
+    rng = np.random.default_rng(seed)
+    rc = 3.5 * fb.BOHR_PER_AA
+    coords = np.concatenate([rng.uniform(0.0, 2.0 * rc + 0.4 * rc * n ** (1 / 3), size=(n, 3)) for n in natoms])
+    N = sum(natoms)
+    atnum = rng.choice([22, 8, 8], size=N).astype(np.int32)
+    atnum[0], atnum[1] = 22, 8
+    ds = fb.Dataset.build(natoms, coords, np.zeros(len(natoms), np.int32), np.zeros((len(natoms), 3, 3)), atnum,
+                          gtargets=rng.uniform(1.0, 2.0, size=(len(natoms), n_targets)),
+                          weights=rng.integers(1, 4, size=len(natoms)), atomic_weights=rng.uniform(0.5, 1.5, size=N),
+                          atomic_numbers=[22, 8])
+    return ds, rc
+
+
+@pytest.mark.parametrize("loss", ["mse", "rms", "mae", "mape"])
+@pytest.mark.parametrize("mlp", ["auto", "nofuse"])
+def test_cluster_fused_structure_sums_ragged_two_species(fb, orc, mlp, loss, monkeypatch):
+    """two-species structures of 1..150 atoms (several small ones per super-round, structures whose species spans
+    two rounds, single atoms of one species only), two global targets, dataset and atomic weights: the per-structure
+    sums exchanged between the CTAs of a thread-block cluster (k_bpnn_mma<0,..,2>) against the oracle and against the
+    two-pass kernels"""
+    natoms = [1, 7, 64, 3, 150, 30, 5, 97, 63, 2, 17, 40, 24, 1, 1, 9, 130, 12]
+    ds, rc = _ragged_two_species(fb, 52, natoms, 2)
+    monkeypatch.setenv("FNETGPU_MLP_CLUSTER", "4")      # tiny batch: do not leave the choice to the cost estimate
+    funcs = _mixed_functions(fb, rc)
+    _full_check(fb, orc, ds, funcs, [len(funcs), 6, 5, 2], loss=loss, forces=False, mlp=mlp, expect_mlp=1, expect_fusion=2)
+
+
+@pytest.mark.parametrize("cs", [2, 3, 4, 5, 8])
+def test_cluster_fused_every_cluster_size(fb, cs, monkeypatch):
+    """the cluster-fused gradient with the cluster size pinned to 2..8 (FNETGPU_MLP_CLUSTER) is the two-pass gradient:
+    same loss, same per-structure energies, gradient to summation-order accuracy; repeat launches are bit-identical"""
+    natoms = [40, 3, 64, 17, 64, 1, 60, 25, 25, 25, 9] if cs == 2 else [40, 3, 96, 17, 64, 1, 80, 25, 25, 25, 128, 9]
+    ds, rc = _ragged_two_species(fb, 53, natoms, 1)
+    funcs = fb.GFunctions.from_auto_scheme(rc, 5, 4).resolve_species([22, 8])
+    dims = [len(funcs), 24, 16, 1]
+    wb = np.random.default_rng(9).uniform(-0.5, 0.5, size=(2, _ntot(dims)))
+    res = {}
+    for mode in ("nofuse", "auto"):
+        if mode == "auto":
+            monkeypatch.setenv("FNETGPU_MLP_CLUSTER", str(cs))
+        ctx = fb.Context(mlp=mode)
+        ctx.upload(0, ds)
+        fb.Acsf(ctx, funcs, standardize=True).calculate(0)
+        net = fb.Bpnn(ctx, dims, 2, "tanh")
+        net.set_params(wb)
+        out = net.update_gradients(0, "mse", want_global=True)
+        gi = ctx.grad_launch_info(0)
+        if mode == "auto":
+            assert gi["fusion"] == 2 and gi["cluster_size"] == cs and gi["grid"] % cs == 0, gi
+            again = net.update_gradients(0, "mse", want_global=True)
+            assert np.array_equal(out[0], again[0]) and out[1] == again[1] and np.array_equal(out[2], again[2])
+        else:
+            assert gi["fusion"] == 0, gi
+        res[mode] = out
+        ctx.close()
+    (dd0, l0, g0), (dd1, l1, g1) = res["nofuse"], res["auto"]
+    assert np.allclose(dd1, dd0, rtol=1e-11, atol=1e-12 * np.abs(dd0).max()), _md(dd1, dd0)
+    assert abs(l1 - l0) <= 1e-12 * abs(l0)
+    assert np.allclose(g1, g0, rtol=1e-12, atol=1e-13)
+
+
+def test_cluster_fused_falls_back_for_atomic_targets_and_huge_structures(fb):
+    """atomic targets, or a structure that needs more than 8 rounds of 64 atoms, keep the two-pass path"""
+    from fortnet_b200 import synthetic
+    big = synthetic.dense_liquid(n_atoms=600, density_aa3=0.05, seed=5, n_struct=1)
+    ds = fb.Dataset.build([600], big.coords, np.ones(1, np.int32), big.latvecs, np.full(600, 14, np.int32),
+                          gtargets=np.array([[1.0]]), atomic_numbers=[14])
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 4, 4)
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    fb.Acsf(ctx, funcs, standardize=True).calculate(0)
+    net = fb.Bpnn(ctx, [8, 6, 1], 1, "tanh")
+    net.set_params(np.random.default_rng(1).uniform(-0.5, 0.5, size=(1, _ntot([8, 6, 1]))))
+    net.update_gradients(0, "mse")
+    assert ctx.grad_launch_info(0)["fusion"] == 0
+    ctx.close()
 
 
 @pytest.mark.parametrize("loss", ["mse", "rms", "mae", "mape"])
