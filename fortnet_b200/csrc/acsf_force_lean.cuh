@@ -411,14 +411,19 @@ k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int c
 
 // forces of structures that were split over several CTAs (few, large structures: an MD step of one cell):
 // out = sum over the nSplit partials in a fixed order
+// (and the partials are cleared behind the sum: the next launch finds the zeros its empty CTAs rely on)
 __global__ void k_force_reduce(int nStruct, int nSplit, int nOut, int localAtoms, const int *__restrict__ offsets,
-                               const double *__restrict__ fpart, double *__restrict__ forces) {
+                               double *__restrict__ fpart, double *__restrict__ forces) {
   const int st = blockIdx.y;
   const int beg = offsets[st], nAt = offsets[st + 1] - beg;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;      // (k, 3 atom + c)
   if (e >= nOut * 3 * nAt) return;
   const int k = e / (3 * nAt), r = e % (3 * nAt);
   double s = 0.0;
-  for (int y = 0; y < nSplit; y++) s += fpart[(((size_t)st * nSplit + y) * nOut + k) * (size_t)(3 * localAtoms) + r];
+  for (int y = 0; y < nSplit; y++) {
+    double *q = fpart + (((size_t)st * nSplit + y) * nOut + k) * (size_t)(3 * localAtoms) + r;
+    s += *q;
+    *q = 0.0;
+  }
   forces[(size_t)(3 * nOut) * (beg + r / 3) + 3 * k + r % 3] = s;
 }

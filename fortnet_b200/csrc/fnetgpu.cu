@@ -9,6 +9,7 @@
 #include "acsf_force_lean.cuh"
 #include "mlp.cuh"
 #include "mlp_mma.cuh"
+#include "mlp_warp.cuh"
 
 #include <dlfcn.h>
 #include <map>
@@ -18,7 +19,7 @@
 static const char *kKernelNames[K_NUM_KERNELS] = {
     "bin_count", "bin_scan", "bin_fill", "bin_sort", "neigh_count", "acsf", "zstat", "zstat_final",
     "zapply", "ext_concat", "mlp_fwd", "struct_loss", "loss_final", "mlp_grad", "grad_reduce",
-    "mlp_ingrad", "acsf_force", "misc"};
+    "mlp_ingrad", "acsf_force", "misc", "mlp_warp"};
 
 extern "C" const char *fnetgpu_kernel_name(int kernelId) {
   return (kernelId >= 0 && kernelId < K_NUM_KERNELS) ? kKernelNames[kernelId] : nullptr;
@@ -97,7 +98,7 @@ static void free_slot(Slot &s) {
   cudaFree(s.d_coords); cudaFree(s.d_lat); cudaFree(s.d_fpos); cudaFree(s.d_crec); cudaFree(s.d_binStruct); cudaFree(s.d_sinfo); cudaFree(s.d_atomCell);
   cudaFree(s.d_cellStart); cudaFree(s.d_cellCount); cudaFree(s.d_cellAtoms); cudaFree(s.d_dsw); cudaFree(s.d_aw);
   cudaFree(s.d_gt); cudaFree(s.d_at); cudaFree(s.d_ext); cudaFree(s.d_feat);
-  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_tilesS); cudaFree(s.d_tilesC); cudaFree(s.d_permC); cudaFree(s.d_segBE); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
+  cudaFree(s.d_perm); cudaFree(s.d_tiles); cudaFree(s.d_tiles16); cudaFree(s.d_tilesS); cudaFree(s.d_tilesW); cudaFree(s.d_tilesC); cudaFree(s.d_permC); cudaFree(s.d_segBE); cudaFree(s.d_raw); cudaFree(s.d_gS); cudaFree(s.d_Es);
   cudaFree(s.d_lossPart); cudaFree(s.d_dEdG); cudaFree(s.d_forces);
   s = Slot();
 }
@@ -850,6 +851,7 @@ static int plan_values(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
     const int cap = std::max(8, (hint + 1 + 7) & ~7);
     static const int gEnv = [] { const char *e = getenv("FNETGPU_LEAN_G"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
     int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
+    if (s.N <= 2 * ctx->nSM) G = 1;          // a handful of atoms (an MD step of one cell): latency, not lane occupancy -- a warp per atom
     if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
     const size_t extra = lean_cta_extra_bytes(T.F, cap, ctx->lean.stageBytes);
     const bool f32a = ctx->precision == 32;   // FP32 pair arithmetic (acsf_lean.cuh)
@@ -878,6 +880,7 @@ static int plan_forces(fnetgpu_ctx *ctx, const Slot &s, bool structPath, AcsfLau
     const int cap = std::max(8, (hint + 1 + 7) & ~7);
     static const int gEnv = [] { const char *e = getenv("FNETGPU_LEAN_G"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
     int G = ctx->leanSorted ? (hint <= 48 ? 2 : 1) : (hint <= 20 ? 4 : (hint <= 64 ? 2 : 1));
+    if (s.N <= 2 * ctx->nSM) G = 1;          // a handful of atoms (an MD step of one cell): latency, not lane occupancy -- a warp per atom
     if (gEnv) G = (ctx->leanSorted && gEnv == 4) ? 2 : gEnv;
     const size_t extra = force_lean_cta_extra_bytes(ctx->lean.stageBytes);
     const int localAtoms = structPath ? ((s.maxAtoms + 1) & ~1) : 0;
@@ -1360,7 +1363,7 @@ extern "C" int fnetgpu_net_set(fnetgpu_ctx *ctx, int nSpecies, int nLayers, cons
   if (dev_alloc(ctx, &ctx->d_wb64, (size_t)n.nTot * nSpecies)) return 1;
   if (dev_alloc(ctx, &ctx->d_dd, (size_t)n.nTot * nSpecies + 8)) return 1;
   ctx->netSet = true; ctx->paramsSet = false; ctx->netEpoch++;
-  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; ctx->slots[i].nTilesC = -1; }
+  for (int i = 0; i < FNETGPU_MAX_SLOTS; i++) { ctx->slots[i].nTiles = 0; ctx->slots[i].nTiles16 = 0; ctx->slots[i].nTilesS = 0; ctx->slots[i].nTilesC = -1; ctx->slots[i].nTilesW = 0; }
   return 0;
 }
 
@@ -1937,26 +1940,34 @@ static int ensure_force_buffers(fnetgpu_ctx *ctx, Slot &s, size_t realBytes) {
   return 0;
 }
 // one launch of the fused force kernel for the planned geometry path (no flag read-back)
-static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, const double *dEdG64, const double *zp) {
+// forcesOut: where the forces go (default: s.d_forces).  The deterministic whole-structure path only STORES them, so the
+// socket step passes mapped pinned host memory and needs no device-to-host copy.
+static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, const double *dEdG64, const double *zp,
+                              double *forcesOut = nullptr) {
   const AcsfTables &T = ctx->acsf;
   const NetTables &n = ctx->net;
   const dim3 g(L.grid.x, L.grid.y, n.nOut);
   const GeomArgs geo = geom_args(s);
+  double *fout = forcesOut ? forcesOut : s.d_forces;
   if (L.lean) {
     const LeanTables &LT = ctx->lean;
     const int localAtoms = L.local ? ((s.maxAtoms + 1) & ~1) : 0;
     double *fpart = nullptr;
     if (L.local && L.nSplit > 1) {       // partial forces of the CTAs of a structure
       const size_t need = (size_t)s.nStruct * L.nSplit * n.nOut * 3 * localAtoms;
+      if (!ctx->d_fpart || ctx->fpartN < need) ctx->fpartZeroN = 0;
       if (dev_reserve(ctx, &ctx->d_fpart, &ctx->fpartN, need)) return 1;
-      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_fpart, 0, need * sizeof(double), ctx->stream));   // CTAs without atoms write nothing
+      // CTAs without atoms write nothing: the partials start from zero.  k_force_reduce clears what it has summed, so
+      // only the first use of the buffer (or a larger one) needs the memset
+      if (ctx->fpartZeroN < need) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_fpart, 0, ctx->fpartN * sizeof(double), ctx->stream));
+      ctx->fpartZeroN = 0;                  // until the reduction below has been enqueued
       fpart = ctx->d_fpart;
     }
 #define FNET_FLEAN(NL, NC, PATH, SORTED, G, LOCAL)                                                               \
   do {                                                                                                          \
     CUDA_TRY(ctx, fnet_smem_attr(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, L.smem)); \
     LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL><<<g, L.wpb * 32, L.smem, ctx->stream>>>( \
-                                  L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, s.d_forces, fpart, ctx->d_flags))); \
+                                  L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, fout, fpart, ctx->d_flags))); \
   } while (0)
 #define FNET_FLEAN_S(NL, NC, PATH, LOCAL)                                                                        \
   do {                                                                                                          \
@@ -1975,7 +1986,8 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 #undef FNET_FLEAN
     if (fpart) {
       const dim3 rg((n.nOut * 3 * s.maxAtoms + 127) / 128, s.nStruct);
-      LAUNCH(ctx, K_ACSF_FORCE, (k_force_reduce<<<rg, 128, 0, ctx->stream>>>(s.nStruct, L.nSplit, n.nOut, localAtoms, s.d_offsets, fpart, s.d_forces)));
+      LAUNCH(ctx, K_ACSF_FORCE, (k_force_reduce<<<rg, 128, 0, ctx->stream>>>(s.nStruct, L.nSplit, n.nOut, localAtoms, s.d_offsets, fpart, fout)));
+      ctx->fpartZeroN = ctx->fpartN;
     }
     return 0;
   }
@@ -1984,7 +1996,7 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
     CUDA_TRY(ctx, fnet_smem_attr(k_acsf_force<PATH>, L.smem)); \
     LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force<PATH><<<g, L.wpb * 32, L.smem, ctx->stream>>>(                      \
                                   L.nSplit, geo, s.nExt, s.d_ext, T, L.cap, L.capC, dEdG64, n.nOut, zp,         \
-                                  s.d_forces, ctx->d_flags)));                                                  \
+                                  fout, ctx->d_flags)));                                                        \
   } while (0)
   if (L.path == FNET_PATH_STRUCT) FNET_FORCE_LAUNCH(FNET_PATH_STRUCT);
   else if (L.path == FNET_PATH_STAGED) FNET_FORCE_LAUNCH(FNET_PATH_STAGED);
@@ -2063,6 +2075,51 @@ extern "C" int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces) {
 // stream with the capacities of the previous step and the host synchronises ONCE; overflow /
 // lattice flags are inspected afterwards and send the step through the general entry points.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// socket / MD step helpers: geometry in and flags out without copy nodes.  The step's device work is a chain of small
+// dependent kernels; every cudaMemcpy / cudaMemset node in that chain costs as much as a kernel.  Inputs are staged in
+// pinned host memory, which the device reads directly (k_sock_prologue also clears the flags); the subnetwork outputs
+// and the forces are STORED straight into mapped pinned memory by the kernels that produce them; k_sock_epilogue
+// publishes the flags.
+// ------------------------------------------------------------------------------------------
+__global__ void k_sock_prologue(int n3, const double *__restrict__ hCoords, double *__restrict__ coords, int n9,
+                                const double *__restrict__ hLat, double *__restrict__ lat, int *__restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (t < 8) flags[t] = 0;
+  for (int e = t; e < n3; e += nt) coords[e] = hCoords[e];
+  for (int e = t; e < n9; e += nt) lat[e] = hLat[e];
+}
+__global__ void k_sock_epilogue(const int *__restrict__ flags, int *__restrict__ hFlags) {
+  if (threadIdx.x < 8) hFlags[threadIdx.x] = flags[threadIdx.x];
+}
+// (start, count <= FNET_WARP_WPB, species) entries of the species-sorted order for k_bpnn_warp
+static int ensure_tiles_warp(fnetgpu_ctx *ctx, Slot &s) {
+  if (s.nTilesW > 0) return 0;
+  std::vector<int> t;
+  for (int sp = 0; sp + 1 < (int)s.spBeg.size(); sp++)
+    for (int b = s.spBeg[sp]; b < s.spBeg[sp + 1]; b += FNET_WARP_WPB) {
+      t.push_back(b); t.push_back(std::min(FNET_WARP_WPB, s.spBeg[sp + 1] - b)); t.push_back(sp);
+    }
+  if (dev_upload(ctx, &s.d_tilesW, t.data(), t.size())) return 1;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  s.nTilesW = (int)t.size() / 3;
+  return 0;
+}
+// the latency kernel serves small batches in precision 64 (FNETGPU_SOCK_MLP=mma keeps the throughput kernels: A/B)
+static bool use_warp_mlp(const fnetgpu_ctx *ctx, const Slot &s) {
+  static const bool off = [] { const char *e = getenv("FNETGPU_SOCK_MLP"); return e && !strcmp(e, "mma"); }();
+  return !off && ctx->precision == 64 && s.N <= 16 * ctx->nSM && bpnn_warp_smem_bytes(ctx->net) <= 200 * 1024;
+}
+static int run_warp_mlp(fnetgpu_ctx *ctx, Slot &s, double *rawOut, double *dEdG) {
+  if ((int)s.spBeg.size() - 1 > ctx->net.nSpecies) FNET_FAIL(ctx, "dataset references more species than the network has sub-networks");
+  if (ensure_tiles_warp(ctx, s)) return 1;
+  const size_t smem = bpnn_warp_smem_bytes(ctx->net);
+  CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_warp, smem));
+  LAUNCH(ctx, K_MLP_WARP, (k_bpnn_warp<<<s.nTilesW, FNET_WARP_WPB * 32, smem, ctx->stream>>>(
+                              s.d_tilesW, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, ctx->net, rawOut, dEdG)));
+  return 0;
+}
+
 extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coords, const double *latvecs,
                                    double *globalPred, double *atomicPred, double *forces) {
   CHECK_CTX(ctx); CHECK_SLOT(ctx, slot);
@@ -2097,22 +2154,30 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
         ctx->pinInN = nIn;
       }
       double *hp = ctx->h_pinned, *hin = ctx->h_pinIn;
-      // the step's device work: geometry in, ACSF, subnetworks, input gradients, forces, results + flags out
+      const bool warpMlp = use_warp_mlp(ctx, s);
+      // the step's device work: geometry in (read from pinned host memory), ACSF, subnetworks + input gradients,
+      // forces, flags out; outputs and forces are stored straight into pinned host memory where the kernels allow it
       auto enqueue = [&](const double *srcCoords, const double *srcLat) -> int {
-        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_coords, srcCoords, (size_t)3 * s.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (srcLat) CUDA_TRY(ctx, cudaMemcpyAsync(s.d_lat, srcLat, (size_t)9 * s.nStruct * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), ctx->stream));
+        LAUNCH(ctx, K_MISC, (k_sock_prologue<<<1, 256, 0, ctx->stream>>>(3 * s.N, srcCoords, s.d_coords, 9 * s.nStruct, srcLat, s.d_lat, ctx->d_flags)));
         if (launch_acsf_values<double>(ctx, s, Lv, zp)) return 1;
         s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
         if (check_ready<double>(ctx, s, false)) return 1;
-        if (run_forward<double>(ctx, s)) return 1;
         if (ensure_force_buffers(ctx, s, sizeof(double))) return 1;
-        if (run_ingrad<double>(ctx, s)) return 1;
-        if (!Lf.local) CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));   // atomics path accumulates
-        if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
-        CUDA_TRY(ctx, cudaMemcpyAsync(hp, s.d_raw, nRaw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw + nFrc, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (warpMlp) {
+          if (run_warp_mlp(ctx, s, hp, (double *)s.d_dEdG)) return 1;
+        } else {
+          if (run_forward<double>(ctx, s)) return 1;
+          if (run_ingrad<double>(ctx, s)) return 1;
+          CUDA_TRY(ctx, cudaMemcpyAsync(hp, s.d_raw, nRaw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (Lf.local) {
+          if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp, hp + nRaw)) return 1;
+        } else {                                            // atomics path accumulates on the device
+          CUDA_TRY(ctx, cudaMemsetAsync(s.d_forces, 0, nFrc * sizeof(double), ctx->stream));
+          if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
+          CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        LAUNCH(ctx, K_MISC, (k_sock_epilogue<<<1, 32, 0, ctx->stream>>>(ctx->d_flags, (int *)(hp + nRaw + nFrc))));
         return 0;
       };
       // the sequence depends on the launch plans and the buffers only: captured once as a CUDA graph, replayed per
@@ -2124,19 +2189,18 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
           (long long)(size_t)s.d_coords, (long long)(size_t)s.d_lat, (long long)(size_t)s.d_feat, (long long)(size_t)s.d_raw,
           (long long)(size_t)s.d_dEdG, (long long)(size_t)s.d_forces, (long long)(size_t)hp, (long long)(size_t)hin,
           (long long)(size_t)ctx->d_wb, (long long)(size_t)ctx->stream, ctx->mlpLegacy, ctx->mlpNoFuse, ctx->acsfGeneric,
-          (long long)(size_t)ctx->d_fpart, (long long)ctx->netEpoch, (long long)ctx->acsfEpoch};
+          (long long)(size_t)ctx->d_fpart, (long long)ctx->netEpoch, (long long)ctx->acsfEpoch, (long long)warpMlp,
+          (long long)(size_t)s.d_tilesW, (long long)(ctx->fpartZeroN >= ctx->fpartN)};
       const bool graphOk = !ctx->profiling && ctx->useGraphs;
+      memcpy(hin, coords, (size_t)3 * s.N * sizeof(double));
+      memcpy(hin + (size_t)3 * s.N, s.h_lat.data(), (size_t)9 * s.nStruct * sizeof(double));
       if (graphOk && s.sockGraph && key == s.sockKey) {
-        memcpy(hin, coords, (size_t)3 * s.N * sizeof(double));
-        memcpy(hin + (size_t)3 * s.N, s.h_lat.data(), (size_t)9 * s.nStruct * sizeof(double));
         CUDA_TRY(ctx, cudaGraphLaunch(s.sockGraph, ctx->stream));
         ctx->launches += s.sockGraphLaunches;
         s.featValid = true; s.lastPath = FNET_PATH_STRUCT;
       } else if (graphOk && s.sockKeyWanted == key) {
         // second step with this plan: capture (everything is allocated by now), then replay
         if (s.sockGraph) { cudaGraphExecDestroy(s.sockGraph); s.sockGraph = nullptr; }
-        memcpy(hin, coords, (size_t)3 * s.N * sizeof(double));
-        memcpy(hin + (size_t)3 * s.N, s.h_lat.data(), (size_t)9 * s.nStruct * sizeof(double));
         const long long l0 = ctx->launches;
         cudaGraph_t g = nullptr;
         CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -2147,13 +2211,13 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
           cudaGetLastError();
           ctx->useGraphs = false;                       // no graphs on this context any more: eager steps
           s.sockKeyWanted.clear();
-          if (enqueue(coords, latvecs ? latvecs : nullptr)) return 1;
+          if (enqueue(hin, hin + (size_t)3 * s.N)) return 1;
         } else {
           s.sockGraphLaunches = ctx->launches - l0;
           ctx->launches = l0;
           const cudaError_t ie = cudaGraphInstantiate(&s.sockGraph, g, 0);
           cudaGraphDestroy(g);
-          if (ie != cudaSuccess) { s.sockGraph = nullptr; ctx->useGraphs = false; if (enqueue(coords, latvecs)) return 1; }
+          if (ie != cudaSuccess) { s.sockGraph = nullptr; ctx->useGraphs = false; if (enqueue(hin, hin + (size_t)3 * s.N)) return 1; }
           else {
             s.sockKey = key;
             CUDA_TRY(ctx, cudaGraphLaunch(s.sockGraph, ctx->stream));
@@ -2161,7 +2225,7 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
           }
         }
       } else {
-        if (enqueue(coords, latvecs)) return 1;
+        if (enqueue(hin, hin + (size_t)3 * s.N)) return 1;
         s.sockKeyWanted = key;
       }
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

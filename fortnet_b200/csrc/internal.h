@@ -26,7 +26,7 @@ struct CRec;
 enum KernelId {
   K_BIN_COUNT = 0, K_BIN_SCAN, K_BIN_FILL, K_BIN_SORT, K_NEIGH_COUNT, K_ACSF, K_ZSTAT, K_ZSTAT_FINAL,
   K_ZAPPLY, K_EXT_CONCAT, K_MLP_FWD, K_STRUCT_LOSS, K_LOSS_FINAL, K_MLP_GRAD, K_GRAD_REDUCE,
-  K_MLP_INGRAD, K_ACSF_FORCE, K_MISC, K_NUM_KERNELS
+  K_MLP_INGRAD, K_ACSF_FORCE, K_MISC, K_MLP_WARP, K_NUM_KERNELS
 };
 
 struct StructInfo {
@@ -204,6 +204,7 @@ struct Slot {
   int nTilesC = -1;                 // super-rounds; -1 = not planned yet, 0 = not applicable
   int clusterCS = 0, clusterGrid = 0;
   int lastGrad[4] = {0, 0, 0, 0};   // fnetgpu_grad_launch_info
+  int *d_tilesW = nullptr; int nTilesW = 0;          // <= 4 atoms of one species per entry: the one-warp-per-atom latency kernel (mlp_warp.cuh)
   // work buffers
   void *d_raw = nullptr;            // [N][nOut] real
   double *d_gS = nullptr;           // [nStruct][nG] loss gradients of the global targets
@@ -261,6 +262,7 @@ struct fnetgpu_ctx {
   void *d_wb = nullptr;             // [nSpecies][nTot] real
   double *d_wb64 = nullptr;
   double *d_fpart = nullptr; size_t fpartN = 0;   // partial forces of structures split over several CTAs (k_force_reduce)
+  size_t fpartZeroN = 0;            // leading elements of d_fpart known to be zero (k_force_reduce clears what it has summed)
   double *d_conv = nullptr; size_t convN = 0;   // FP32 mode: device-side float -> double staging of downloads
   bool paramsSet = false;
   double reguLambda = 0.0, reguAlpha = 0.0, reguDiv = 0.0;   // fnetgpu_regularization_set
