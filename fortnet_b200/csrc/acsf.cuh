@@ -87,6 +87,8 @@ __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit,
     c.ftab = ft;
     smem_raw += EXPONLY ? FNET_EXP_TAB_N * sizeof(double) : FNET_FTAB_BYTES;
   }
+  FNET_PDL_TRIGGER();     // socket step (internal.h): the next kernel of the chain may be scheduled now ...
+  FNET_PDL_WAIT();        // ... and this one reads geometry / upstream results only after its predecessor has completed
   c.S = nullptr; c.cellStart = G.cellStart; c.crec = G.crec; c.cand = (const CRec *)smem_raw; c.nCand = 0; c.sg = nullptr;
   c.first = 0;
   wbase = smem_raw;

@@ -414,16 +414,25 @@ k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int c
 // (and the partials are cleared behind the sum: the next launch finds the zeros its empty CTAs rely on)
 __global__ void k_force_reduce(int nStruct, int nSplit, int nOut, int localAtoms, const int *__restrict__ offsets,
                                double *__restrict__ fpart, double *__restrict__ forces) {
+  FNET_PDL_TRIGGER();
+  FNET_PDL_WAIT();
   const int st = blockIdx.y;
   const int beg = offsets[st], nAt = offsets[st + 1] - beg;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;      // (k, 3 atom + c)
   if (e >= nOut * 3 * nAt) return;
   const int k = e / (3 * nAt), r = e % (3 * nAt);
   double s = 0.0;
-  for (int y = 0; y < nSplit; y++) {
-    double *q = fpart + (((size_t)st * nSplit + y) * nOut + k) * (size_t)(3 * localAtoms) + r;
-    s += *q;
-    *q = 0.0;
+  double *q0 = fpart + ((size_t)st * nSplit * nOut + k) * (size_t)(3 * localAtoms) + r;
+  const size_t step = (size_t)nOut * (size_t)(3 * localAtoms);
+  int y = 0;
+  for (; y + 8 <= nSplit; y += 8) {          // eight loads in flight, summed in the fixed order
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = __ldcg(q0 + (size_t)(y + u) * step);
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += v[u];
   }
+  for (; y < nSplit; y++) s += __ldcg(q0 + (size_t)y * step);
+  for (y = 0; y < nSplit; y++) q0[(size_t)y * step] = 0.0;
   forces[(size_t)(3 * nOut) * (beg + r / 3) + 3 * k + r % 3] = s;
 }

@@ -86,6 +86,7 @@ extern "C" int fnetgpu_init(fnetgpu_ctx **out, int device, int precision, int de
   { const char *pm = getenv("FNETGPU_MLP"); ctx->mlpLegacy = (pm && strcmp(pm, "legacy") == 0) ? 1 : 0;
     ctx->mlpNoFuse = (pm && strcmp(pm, "nofuse") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_GRAPHS"); ctx->useGraphs = !(pm && strcmp(pm, "0") == 0); }
+  { const char *pm = getenv("FNETGPU_PDL"); ctx->usePdl = !(pm && strcmp(pm, "0") == 0); }
   { const char *pm = getenv("FNETGPU_ACSF_KERNEL"); ctx->acsfGeneric = (pm && strcmp(pm, "generic") == 0) ? 1 : 0; }
   { const char *pm = getenv("FNETGPU_ACSF_PATH"); ctx->acsfPathCells = (pm && strcmp(pm, "cells") == 0) ? 1 : 0; }
   *out = ctx;
@@ -1038,7 +1039,7 @@ static int launch_acsf_values(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 #define FNET_LEAN_LAUNCH2(NL, NC, PATH, SORTED, G, F32A)                                                        \
   do {                                                                                                         \
     CUDA_TRY(ctx, fnet_smem_attr(k_acsf_lean<NL, NC, PATH, SORTED, G, F32A>, L.smem)); \
-    LAUNCH(ctx, K_ACSF, (k_acsf_lean<NL, NC, PATH, SORTED, G, F32A><<<L.grid, L.wpb * 32, L.smem, ctx->stream>>>( \
+    LAUNCH(ctx, K_ACSF, (fnet_launch_k(ctx->pdl, k_acsf_lean<NL, NC, PATH, SORTED, G, F32A>, L.grid, dim3(L.wpb * 32), L.smem, ctx->stream, \
                             L.nSplit, geo, s.nExt, s.d_ext, T, LT, L.cap, L.capC, (void *)feat, f32, nFeat, zp, \
                             nExtSel, ctx->d_extIdx, ctx->d_flags)));                                           \
   } while (0)
@@ -1966,7 +1967,7 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 #define FNET_FLEAN(NL, NC, PATH, SORTED, G, LOCAL)                                                               \
   do {                                                                                                          \
     CUDA_TRY(ctx, fnet_smem_attr(k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, L.smem)); \
-    LAUNCH(ctx, K_ACSF_FORCE, (k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL><<<g, L.wpb * 32, L.smem, ctx->stream>>>( \
+    LAUNCH(ctx, K_ACSF_FORCE, (fnet_launch_k(ctx->pdl, k_acsf_force_lean<NL, NC, PATH, SORTED, G, LOCAL>, g, dim3(L.wpb * 32), L.smem, ctx->stream, \
                                   L.nSplit, geo, T, LT, L.cap, L.capC, localAtoms, dEdG64, n.nOut, zp, fout, fpart, ctx->d_flags))); \
   } while (0)
 #define FNET_FLEAN_S(NL, NC, PATH, LOCAL)                                                                        \
@@ -1986,7 +1987,7 @@ static int launch_acsf_forces(fnetgpu_ctx *ctx, Slot &s, const AcsfLaunch &L, co
 #undef FNET_FLEAN
     if (fpart) {
       const dim3 rg((n.nOut * 3 * s.maxAtoms + 127) / 128, s.nStruct);
-      LAUNCH(ctx, K_ACSF_FORCE, (k_force_reduce<<<rg, 128, 0, ctx->stream>>>(s.nStruct, L.nSplit, n.nOut, localAtoms, s.d_offsets, fpart, fout)));
+      LAUNCH(ctx, K_ACSF_FORCE, (fnet_launch_k(ctx->pdl, k_force_reduce, rg, dim3(128), 0, ctx->stream, s.nStruct, L.nSplit, n.nOut, localAtoms, (const int *)s.d_offsets, fpart, fout)));
       ctx->fpartZeroN = ctx->fpartN;
     }
     return 0;
@@ -2085,11 +2086,13 @@ extern "C" int fnetgpu_forces(fnetgpu_ctx *ctx, int slot, double *forces) {
 __global__ void k_sock_prologue(int n3, const double *__restrict__ hCoords, double *__restrict__ coords, int n9,
                                 const double *__restrict__ hLat, double *__restrict__ lat, int *__restrict__ flags) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  FNET_PDL_TRIGGER();
   if (t < 8) flags[t] = 0;
   for (int e = t; e < n3; e += nt) coords[e] = hCoords[e];
   for (int e = t; e < n9; e += nt) lat[e] = hLat[e];
 }
 __global__ void k_sock_epilogue(const int *__restrict__ flags, int *__restrict__ hFlags) {
+  FNET_PDL_WAIT();
   if (threadIdx.x < 8) hFlags[threadIdx.x] = flags[threadIdx.x];
 }
 // (start, count <= FNET_WARP_WPB, species) entries of the species-sorted order for k_bpnn_warp
@@ -2115,8 +2118,9 @@ static int run_warp_mlp(fnetgpu_ctx *ctx, Slot &s, double *rawOut, double *dEdG)
   if (ensure_tiles_warp(ctx, s)) return 1;
   const size_t smem = bpnn_warp_smem_bytes(ctx->net);
   CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_warp, smem));
-  LAUNCH(ctx, K_MLP_WARP, (k_bpnn_warp<<<s.nTilesW, FNET_WARP_WPB * 32, smem, ctx->stream>>>(
-                              s.d_tilesW, s.d_perm, (const double *)s.d_feat, s.nFeat, (const double *)ctx->d_wb, ctx->net, rawOut, dEdG)));
+  LAUNCH(ctx, K_MLP_WARP, (fnet_launch_k(ctx->pdl, k_bpnn_warp, dim3(s.nTilesW), dim3(FNET_WARP_WPB * 32), smem, ctx->stream,
+                                         (const int *)s.d_tilesW, (const int *)s.d_perm, (const double *)s.d_feat, s.nFeat,
+                                         (const double *)ctx->d_wb, ctx->net, rawOut, dEdG)));
   return 0;
 }
 
@@ -2177,9 +2181,10 @@ extern "C" int fnetgpu_socket_step(fnetgpu_ctx *ctx, int slot, const double *coo
           if (launch_acsf_forces(ctx, s, Lf, (const double *)s.d_dEdG, zp)) return 1;
           CUDA_TRY(ctx, cudaMemcpyAsync(hp + nRaw, s.d_forces, nFrc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
-        LAUNCH(ctx, K_MISC, (k_sock_epilogue<<<1, 32, 0, ctx->stream>>>(ctx->d_flags, (int *)(hp + nRaw + nFrc))));
+        LAUNCH(ctx, K_MISC, (fnet_launch_k(ctx->pdl, k_sock_epilogue, dim3(1), dim3(32), 0, ctx->stream, (const int *)ctx->d_flags, (int *)(hp + nRaw + nFrc))));
         return 0;
       };
+      struct PdlScope { fnetgpu_ctx *c; PdlScope(fnetgpu_ctx *c_, bool on) : c(c_) { c->pdl = on; } ~PdlScope() { c->pdl = false; } } pdlScope(ctx, ctx->usePdl && !ctx->profiling);
       // the sequence depends on the launch plans and the buffers only: captured once as a CUDA graph, replayed per
       // MD step (one graph launch instead of 4-6 kernel launches, 3 memsets and 5 copies); the first step with a new
       // plan runs eagerly (it may allocate), profiling runs eagerly (per-kernel events)

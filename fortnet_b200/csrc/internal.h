@@ -272,6 +272,9 @@ struct fnetgpu_ctx {
   double *h_pinned = nullptr; size_t pinnedN = 0;
   double *h_pinIn = nullptr; size_t pinInN = 0;   // socket step: geometry staged for the graph's host-to-device copies
   bool useGraphs = true;            // FNETGPU_GRAPHS=0: eager socket steps
+  bool pdl = false;                 // set while the socket step enqueues: kernels are launched with programmatic stream
+                                    // serialization (the next kernel's launch and table staging overlap the previous kernel)
+  bool usePdl = true;               // FNETGPU_PDL=0 switches it off (A/B)
   long long acsfEpoch = 0, netEpoch = 0;
   int *d_flags = nullptr;           // [8] statistics / overflow flags (cells.cuh, acsf.cuh)
   int mlpNoFuse = 0;                // FNETGPU_MLP=nofuse / mlp_path_set(2): DMMA kernels without the fused per-structure sums (tests, A/B)
@@ -320,6 +323,25 @@ struct ProfEvent { cudaEvent_t a, b; int kernel; };
       return 1;                                                                              \
     }                                                                                        \
   } while (0)
+
+// Programmatic dependent launch (griddepcontrol, sm_90+): a kernel launched with the attribute may start while its
+// predecessor in the stream is still running; it must not touch anything the predecessor produces before FNET_PDL_WAIT()
+// (which returns when the predecessor has completed and its writes are visible).  Every kernel of the socket step
+// triggers its dependents at once (FNET_PDL_TRIGGER) -- the step is a chain of small kernels on a mostly idle GPU, so
+// the next kernel's launch latency, CTA scheduling and constant-table staging disappear behind the current kernel.
+// Without the launch attribute both instructions are no-ops.
+#define FNET_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define FNET_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <typename... KA, typename... A>
+static inline void fnet_launch_k(bool pdl, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t st, A &&...a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k, std::forward<A>(a)...);
+}
 
 template <typename T>
 static inline int dev_alloc(fnetgpu_ctx *ctx, T **p, size_t n) {

@@ -54,13 +54,8 @@ k_bpnn_warp(const int *__restrict__ tiles, const int *__restrict__ perm, const d
   double *dA = fp + net.rowsA, *dB = dA + m.maxDim;             // deltas of the reverse sweep (ping-pong)
   const int start = tiles[3 * blockIdx.x], count = tiles[3 * blockIdx.x + 1], sp = tiles[3 * blockIdx.x + 2];
   const int atom = warp < count ? perm[start + warp] : -1;
-  // this atom's features: in flight while the CTA stages the weights
-  double f0 = 0.0, f1 = 0.0;
-  if (atom >= 0) {
-    if (lane < d0) f0 = feat[(size_t)nFeat * atom + lane];
-    if (lane + 32 < d0) f1 = feat[(size_t)nFeat * atom + lane + 32];
-  }
-  {
+  FNET_PDL_TRIGGER();
+  {   // weights, biases, exp table: constants of the step -- staged while the ACSF kernel in front may still be running
     const double *W = wb + (size_t)net.nTot * sp;
     for (int l = 0; l + 1 < L; l++) {
       const int din = net.dims[l], dout = net.dims[l + 1], ld = m.ld[l];
@@ -75,11 +70,9 @@ k_bpnn_warp(const int *__restrict__ tiles, const int *__restrict__ perm, const d
       for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = W[net.boff[l] + e];
     for (int e = threadIdx.x; e < FNET_EXP_TAB_N; e += blockDim.x) etab[e] = fnet_exp_tab_d[e];
   }
-  if (atom >= 0) {
-    if (lane < d0) a[lane] = f0;
-    if (lane + 32 < d0) a[lane + 32] = f1;
-    for (int f = lane + 64; f < d0; f += 32) a[f] = feat[(size_t)nFeat * atom + f];
-  }
+  FNET_PDL_WAIT();            // the features come from the kernel in front
+  if (atom >= 0)
+    for (int f = lane; f < d0; f += 32) a[f] = feat[(size_t)nFeat * atom + f];
   __syncthreads();
   if (atom < 0) return;
   // ---- forward: lane = output neuron ----
