@@ -108,7 +108,7 @@ k_acsf_force_lean(int nSplit, GeomArgs geo, AcsfTables tab, LeanTables lt, int c
     const int n0 = lean_gather_linear<PATH, SORTED, G, FNET_FREC, true>(cg, tab, me, act, cap, (double *)wb, (double *)wb + (gx - rec),
                                                                         (double *)wb + (gy - rec), (double *)wb + (gz - rec),
                                                                         (int *)wb + (gc - (int *)rec), (int *)wb + (gi - (int *)rec),
-                                                                        gbytes, zcode, lane);
+                                                                        gbytes, gbytes, zcode, lane);
     int n = n0;
     if (n > cap - 1) {
       if (sl == 0) atomicMax(&flags[1], n + 1);

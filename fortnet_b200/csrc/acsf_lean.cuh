@@ -43,13 +43,22 @@
 __host__ __device__ inline size_t lean_group_bytes(int cap, int F, bool sorted, bool f32a = false) {   // cap: multiple of 8
   size_t b = (size_t)cap * 6 * sizeof(double);                         // neighbour records
   if (f32a) b += (size_t)cap * 4 * sizeof(float);                      // FP32 pair arithmetic: (u'_x, u'_y, u'_z, fc E) as float4
-  if (sorted) b += (size_t)cap * (3 * sizeof(double) + sizeof(int));   // unsorted displacements + species codes
+  (void)sorted;                                                        // (the sort scratch lives in the reduction area, below)
   b += (size_t)((FNET_MAX_CODES + 4 + 3) & ~3) * sizeof(int);          // list segments
   b += (size_t)((F + 1) & ~1) * sizeof(double);                        // feature row
   return (b + 15) & ~(size_t)15;
 }
+// species-resolved configurations: unsorted displacements + species codes of a group, alive only between the neighbour
+// gather and the counting sort -- they share the warp's reduction scratch, which is first touched after the records
+// are final (C3: 63 -> 52 KB per CTA, 3 -> 4 CTAs per SM)
+__host__ __device__ inline size_t lean_scratch_bytes(int cap) {
+  return ((size_t)cap * (3 * sizeof(double) + sizeof(int)) + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t lean_warp_smem_bytes(int cap, int F, int redRows, bool sorted, int G, bool f32a = false) {
-  return (size_t)G * lean_group_bytes(cap, F, sorted, f32a) + (((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15);
+  size_t red = ((size_t)redRows * FNET_RED_STRIDE * sizeof(double) + 15) & ~(size_t)15;
+  const size_t sc = sorted ? (size_t)G * lean_scratch_bytes(cap) : 0;
+  if (sc > red) red = sc;
+  return (size_t)G * lean_group_bytes(cap, F, sorted, f32a) + red;
 }
 __host__ __device__ inline int lean_pair_entries(int cap) {        // staged part of the strict-triangle pair table
   const int need = cap * (cap - 1) / 2 + 1;
@@ -307,7 +316,7 @@ __device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER],
 template <int PATH, bool SORTED, int G, int RS, bool WITHIDX>
 __device__ __forceinline__ int lean_gather_linear(const CtaGeom &cg, const AcsfTables &tab, const CRec &me, bool act, int cap,
                                                   double *rec0, double *gx0, double *gy0, double *gz0, int *gc0, int *gi0,
-                                                  size_t gbytes, const unsigned char *__restrict__ zcode, int lane) {
+                                                  size_t gbytes, size_t sbytes, const unsigned char *__restrict__ zcode, int lane) {
   constexpr int LPA = 32 / G;
   const int grp = lane / LPA;
   const unsigned ltm = (1u << lane) - 1u;
@@ -356,12 +365,12 @@ __device__ __forceinline__ int lean_gather_linear(const CtaGeom &cg, const AcsfT
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       const int pos = nq[q] + __popc(m & ltm);
       if (ok && pos < cap - 1) {
-        const size_t go = (size_t)q * gbytes;
+        const size_t go = (size_t)q * gbytes, so = (size_t)q * sbytes;
         if (SORTED) {
-          ((double *)((unsigned char *)gx0 + go))[pos] = dx; ((double *)((unsigned char *)gy0 + go))[pos] = dy;
-          ((double *)((unsigned char *)gz0 + go))[pos] = dz;
-          ((int *)((unsigned char *)gc0 + go))[pos] = (r.idx == mi[q]) ? tab.nCodes + 1 : code;
-          if (WITHIDX) ((int *)((unsigned char *)gi0 + go))[pos] = r.idx;
+          ((double *)((unsigned char *)gx0 + so))[pos] = dx; ((double *)((unsigned char *)gy0 + so))[pos] = dy;
+          ((double *)((unsigned char *)gz0 + so))[pos] = dz;
+          ((int *)((unsigned char *)gc0 + so))[pos] = (r.idx == mi[q]) ? tab.nCodes + 1 : code;
+          if (WITHIDX) ((int *)((unsigned char *)gi0 + so))[pos] = r.idx;
         } else {
           double *qq = (double *)((unsigned char *)rec0 + go) + (size_t)RS * pos;
           qq[0] = dx; qq[1] = dy; qq[2] = dz;
@@ -436,11 +445,12 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   unsigned char *gb = wb + (size_t)grp * gbytes;
   double *rec = (double *)gb;                                        // [cap][6]: u'_x, u'_y | u'_z, fc E | r, fc
   float4 *recf = (float4 *)(rec + 6 * cap);                          // F32A: [cap] (u'_x, u'_y, u'_z, fc E)
-  double *gx = rec + 6 * cap + (F32A ? 2 * cap : 0), *gy = gx + cap, *gz = gy + cap;   // SORTED: unsorted displacements
-  int *gc = (int *)(gz + cap);                                       //         and species codes
-  int *seg = SORTED ? gc + cap : (int *)gx;
+  int *seg = (int *)(rec + 6 * cap + (F32A ? 2 * cap : 0));
   double *outv = (double *)(seg + ((FNET_MAX_CODES + 4 + 3) & ~3));
   double *red = (double *)(wb + (size_t)G * gbytes);
+  const size_t sbytes = lean_scratch_bytes(cap);                     // SORTED: unsorted displacements and species codes of the
+  double *gx = (double *)((unsigned char *)red + (size_t)grp * sbytes), *gy = gx + cap, *gz = gy + cap;   // group, inside the
+  int *gc = (int *)(gz + cap);                                       //         reduction scratch (dead until the records are final)
   const double *ftab = cg.ftab;
   int nmaxW = 0;
   for (int s0 = a0 + wib * G; s0 < a1; s0 += nw * G) {
@@ -469,9 +479,9 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         take(is_neighbor(valid && act, dx * dx + dy * dy + dz * dz, rc2, j, zs, i), dx, dy, dz, j, zs);
       });
     } else {
-      unsigned char *g0 = wb;                              // group 0's arrays; group q's are gbytes * q further
-      n = lean_gather_linear<PATH, SORTED, G, 6, false>(cg, tab, me, act, cap, (double *)g0, (double *)g0 + (gx - rec), (double *)g0 + (gy - rec),
-                                                        (double *)g0 + (gz - rec), (int *)g0 + (gc - (int *)rec), nullptr, gbytes, zcode, lane);
+      double *x0 = red;                                    // group 0's records at wb, its scratch at red; group q's are gbytes / sbytes * q further
+      n = lean_gather_linear<PATH, SORTED, G, 6, false>(cg, tab, me, act, cap, (double *)wb, x0, x0 + cap, x0 + 2 * cap, (int *)(x0 + 3 * cap),
+                                                        nullptr, gbytes, sbytes, zcode, lane);
     }
     if (n > cap - 1) {                                       // one slot is the dummy neighbour
       if (sl == 0) atomicMax(&flags[1], n + 1);
