@@ -122,11 +122,12 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
     for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = wb[net.boff[l] + e];
 }
 
-// transfer function as a separate element-wise pass over a warp tile (z -> f(z), optionally f'(z)):
-// ONE copy of the activation code in the kernel (the unrolled fragment epilogue would inline it 16
-// times per call site) and an even split of the dout*16 elements over the lanes
+// transfer function as a separate element-wise pass over a warp tile (z -> f(z), optionally f'(z)): an even split
+// of the dout*8 elements over the lanes.  Inlined into its two call sites (the layer loop of the forward sweep, with
+// and without derivative): as an out-of-line function its tile and table pointers were GENERIC (LD.E / ST.E instead of
+// LDS / STS) and the two-element arrays lived in local memory (ncu: 38 % of the kernel's instructions in this pass).
 template <bool DERIV>
-__device__ __noinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane,
+__device__ __forceinline__ void mma_activate(int actId, int dout, double *__restrict__ out, double *__restrict__ dact, int lane,
                                           const double *__restrict__ etab) {
   // two elements per lane and iteration: independent dependency chains (the FP64 exp / reciprocal
   // sequences are latency-bound); the warp's 8 atoms are columns 0..7 of `out`
@@ -148,7 +149,7 @@ __device__ __noinline__ void mma_activate(int actId, int dout, double *__restric
 #pragma unroll
       for (int q = 0; q < 2; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
     } else {
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < 2; q++) v[q] = act_f<double>(actId, x[q]);
     }
     double d[2];
@@ -157,7 +158,7 @@ __device__ __noinline__ void mma_activate(int actId, int dout, double *__restric
 #pragma unroll
         for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId == FNETGPU_ACT_TANH ? FNETGPU_ACT_TANH : FNETGPU_ACT_SIGMOID, x[q], v[q]);
       } else {
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId, x[q], v[q]);
       }
     }
