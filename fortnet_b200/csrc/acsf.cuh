@@ -82,6 +82,7 @@ __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit,
                                                   unsigned char *&wbase) {
   {   // tables first; the barriers of the staging below (or the explicit one of PATH 0) publish them
     double *ft = (double *)smem_raw;
+#pragma unroll 1
     for (int e = threadIdx.x; e < (EXPONLY ? FNET_EXP_TAB_N : FNET_TAB_DOUBLES); e += blockDim.x)
       ft[e] = e < FNET_EXP_TAB_N ? fnet_exp_tab_d[e] : fnet_log_tab_d[e - FNET_EXP_TAB_N];
     c.ftab = ft;

@@ -412,13 +412,18 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   double *pt = (double *)wbase;                     // power tables
   double *zmu = pt + FNET_POW_DOUBLES, *zis = zmu + Fp;
   unsigned char *zcode = (unsigned char *)(zis + Fp);   // atomic number -> species code (SORTED)
+  // staging loops stay rolled: once per CTA, and the kernel's executed code has to fit the 32 KB L1.5 instruction cache
+#pragma unroll 1
   for (int e = threadIdx.x; e < FNET_POW_DOUBLES; e += blockDim.x) pt[e] = lt.powtab[e];
+#pragma unroll 1
   for (int a = threadIdx.x; a < F; a += blockDim.x) {
     double mu = 0.0, is = 1.0;
     if (zprec) { const double sg = zprec[F + a]; if (!(sg < 1e-08)) { mu = zprec[a]; is = 1.0 / sg; } }   // acsf.F90:505-507
     zmu[a] = mu; zis[a] = is;
   }
-  if (SORTED) for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
+  if (SORTED)
+#pragma unroll 1
+    for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
   // pass / radial tables (when small) and the used part of the pair table: shared-memory latency instead of L1's
   unsigned char *stage = zcode + 128;
   const LeanPass *passes = lt.pass;
@@ -427,6 +432,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     const int nw8 = lt.stageBytes >> 3, np8 = (int)((lt.nPasses * sizeof(LeanPass)) >> 3);
     double *dst = (double *)stage;
     const double *srcP = (const double *)lt.pass, *srcR = (const double *)lt.rad;
+#pragma unroll 1
     for (int e = threadIdx.x; e < nw8; e += blockDim.x) dst[e] = e < np8 ? srcP[e] : srcR[e - np8];
     passes = (const LeanPass *)stage;
     rads = (const LeanRadial *)(stage + (size_t)np8 * 8);
@@ -435,6 +441,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   {
     const int ne2 = (lean_pair_entries(cap) + 1) >> 1;                 // 32-bit copies
     const unsigned *src = (const unsigned *)lt.pairtab;
+#pragma unroll 1
     for (int e = threadIdx.x; e < ne2; e += blockDim.x) ((unsigned *)ptab)[e] = src[e];
   }
   __syncthreads();
@@ -526,23 +533,38 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
       __syncwarp();
     }
     // ---------------- per-neighbour record; entry n is the dummy neighbour ----------------
+    // single list (!SORTED): the diagonal sums of the passes with the shared (rc, eta) -- S0 = sum (fc E)^2,
+    // S1 = sum (fc E)^2 eps -- are formed here, once per atom, instead of in a loop of their own per pass
+    double dS0 = 0.0, dS1 = 0.0;
     for (int t = sl; t <= n; t += LPA) {
       double ux = 0.0, uy = 0.0, uz = 0.0, fe = 0.0, rr = 2.0 * tab.rcMax, fc = 0.0;
       if (t < n) {
         const double dx = rec[6 * t], dy = rec[6 * t + 1], dz = rec[6 * t + 2];
         double ri;
         lean_rsqrt(dx * dx + dy * dy + dz * dz, ri, rr);   // dynneighlist.F90:311
-        const double sc = ri * fma(ri * ri, -0.5e-13, 1.0);  // u (1 - eps / 2), eps = 1e-13 / r^2
+        const double ri2 = ri * ri;
+        const double sc = ri * fma(ri2, -0.5e-13, 1.0);    // u (1 - eps / 2), eps = 1e-13 / r^2
         ux = dx * sc; uy = dy * sc; uz = dz * sc;          // acsf.F90:1565
         fe = lean_fce(rr, lt.rcShared, lt.invrcShared, lt.etaShared, ftab, fc);
+        if (!SORTED) { const double e2 = fe * fe; dS0 += e2; dS1 = fma(e2, ri2 * 1e-13, dS1); }
       }
       *(double2 *)(rec + 6 * t) = make_double2(ux, uy);
       *(double2 *)(rec + 6 * t + 2) = make_double2(uz, fe);
       *(double2 *)(rec + 6 * t + 4) = make_double2(rr, fc);
       if (F32A) recf[t] = make_float4((float)ux, (float)uy, (float)uz, (float)fe);
     }
+    if (!SORTED) {
+#pragma unroll
+      for (int o = LPA / 2; o > 0; o >>= 1) {
+        dS0 += __shfl_xor_sync(0xffffffffu, dS0, o);
+        dS1 += __shfl_xor_sync(0xffffffffu, dS1, o);
+      }
+    }
     __syncwarp();
-    // ---------------- radial ladder groups (acsf.F90:1287-1373): lanes = neighbours, 8 functions per sweep ----------------
+    // ---------------- radial ladder groups (acsf.F90:1287-1373): lanes = neighbours, 16 functions per sweep ----------------
+    // g_m = fc exp(-eta (u - m drs)^2) = g_{m-1} A k_{m-1}, A = exp(2 eta drs u), k_m = exp(-eta drs^2 (2m+1)): two
+    // exponentials per neighbour serve a PAIR of 8-function chunks (functions 8..15 continue the recurrence with
+    // A c16 k_{m-8}, c16 = exp(-16 eta drs^2)) -- the 16 G2 of the automatic scheme cost 2 exponentials, not 4.
     for (int g = 0; g < lt.nRadial; g++) {
       const LeanRadial *__restrict__ R = &rads[g];
       const int fCnt = R->fCnt;
@@ -553,11 +575,13 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
       double kk[FNET_RCHUNK - 1];
 #pragma unroll
       for (int m = 0; m < FNET_RCHUNK - 1; m++) kk[m] = R->kk[m];
-      for (int ch = 0; ch * FNET_RCHUNK < fCnt; ch++) {
+      const double kk7 = R->kk7, c16 = R->c16;
+      for (int ch = 0; ch * FNET_RCHUNK < fCnt; ch += 2) {
+        const bool two = (ch + 1) * FNET_RCHUNK < fCnt;      // warp-uniform: the second chunk of the pair exists
         const double rsf = rs0 + (double)(ch * FNET_RCHUNK) * drs;
-        double acc[FNET_RCHUNK];
+        double acc[FNET_RCHUNK], acc2[FNET_RCHUNK];
 #pragma unroll
-        for (int f = 0; f < FNET_RCHUNK; f++) acc[f] = 0.0;
+        for (int f = 0; f < FNET_RCHUNK; f++) { acc[f] = 0.0; acc2[f] = 0.0; }
         for (int t = sl; t < nl; t += LPA) {
           const int a = SORTED ? list_at(l, t) : t;
           const double2 rf = *(const double2 *)(rec + 6 * a + 4);
@@ -571,26 +595,37 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
             acc[0] += gv;
 #pragma unroll
             for (int m = 0; m < FNET_RCHUNK - 1; m++) { gv *= A * kk[m]; acc[m + 1] += gv; }
+            if (two) {
+              gv *= A * kk7; acc2[0] += gv;
+              const double A2 = A * c16;
+#pragma unroll
+              for (int m = 0; m < FNET_RCHUNK - 1; m++) { gv *= A2 * kk[m]; acc2[m + 1] += gv; }
+            }
           } else {                                      // out of the recurrence's safe range (rare)
 #pragma unroll 1
-            for (int m = 0; m < FNET_RCHUNK; m++) {
+            for (int m = 0; m < (two ? 2 : 1) * FNET_RCHUNK; m++) {
               const double d = u - (double)m * drs;
               const double v = radial_term_generic(FNETGPU_G2, eta, 0.0, d) * fc;
 #pragma unroll
-              for (int f = 0; f < FNET_RCHUNK; f++) acc[f] += (f == m) ? v : 0.0;
+              for (int f = 0; f < FNET_RCHUNK; f++) { acc[f] += (f == m) ? v : 0.0; acc2[f] += (f + FNET_RCHUNK == m) ? v : 0.0; }
             }
           }
         }
-        double v[RR];
-        lean_group_reduce<FNET_RCHUNK, LPA>(acc, lane, red, v);
 #pragma unroll
-        for (int q = 0; q < RR; q++) {
-          const int f = ch * FNET_RCHUNK + (FNET_RCHUNK >= LPA ? sl + q * LPA : sl);
-          if ((FNET_RCHUNK >= LPA || sl < FNET_RCHUNK) && f < fCnt) outv[tab.rfeat[R->fBeg + f]] = v[q];
+        for (int h = 0; h < 2; h++) {
+          if (h == 1 && !two) break;
+          double v[RR];
+          lean_group_reduce<FNET_RCHUNK, LPA>(h ? acc2 : acc, lane, red, v);
+#pragma unroll
+          for (int q = 0; q < RR; q++) {
+            const int f = (ch + h) * FNET_RCHUNK + (FNET_RCHUNK >= LPA ? sl + q * LPA : sl);
+            if ((FNET_RCHUNK >= LPA || sl < FNET_RCHUNK) && f < fCnt) outv[tab.rfeat[R->fBeg + f]] = v[q];
+          }
         }
       }
     }
     // ---------------- angular passes (acsf.F90:1377-1492) ----------------
+    bool sharedFe = true;                             // the records still hold fc E of the shared (rc, eta)
     for (int pi_ = 0; pi_ < lt.nPasses; pi_++) {
       const LeanPass *__restrict__ P = &passes[pi_];
       const int same = P->same, m0 = P->m0;
@@ -599,7 +634,9 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
       const int n1 = l1.n0 + l1.n1, n2 = l2.n0 + l2.n1;
       __syncwarp();
       if (P->recomp) {
+        sharedFe = false;
         const double rc = P->rc, invrc = P->invrc, eta = P->eta;
+#pragma unroll 1
         for (int t = sl; t < n; t += LPA) {
           double fc;
           const double fe = lean_fce(rec[6 * t + 4], rc, invrc, eta, ftab, fc);
@@ -624,8 +661,10 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         lean_pair_loop<NL, NC, LPA, SORTED, 2, AT>(acc, rec, recf, l1, l2, n1, n2, m0, lam, pt, ptab, lt, sl);
       }
       // diagonal of identical lists: S0 = sum fcE^2, S1 = sum fcE^2 eps, eps = 1e-13 / r^2 (a 1e-14 correction: FP32 reciprocal)
-      double S0 = 0.0, S1 = 0.0;
-      if (same) {
+      double S0 = dS0, S1 = dS1;
+      if (same && (SORTED || !sharedFe)) {
+        S0 = 0.0; S1 = 0.0;
+#pragma unroll 2
         for (int t = sl; t < n1; t += LPA) {
           const int a = SORTED ? list_at(l1, t) : t;
           const double fe = rec[6 * a + 3], rr = rec[6 * a + 4];
@@ -660,11 +699,15 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     if (act) {
       if (f32) {
         float *out = (float *)featv + (size_t)nFeat * i;
+#pragma unroll 1
         for (int a = sl; a < F; a += LPA) out[a] = (float)((outv[a] - zmu[a]) * zis[a]);
+#pragma unroll 1
         for (int e = sl; e < nExtSel; e += LPA) out[F + e] = (float)ext[(size_t)nExt * i + extIdx[e]];
       } else {
         double *out = (double *)featv + (size_t)nFeat * i;
+#pragma unroll 2
         for (int a = sl; a < F; a += LPA) out[a] = (outv[a] - zmu[a]) * zis[a];
+#pragma unroll 1
         for (int e = sl; e < nExtSel; e += LPA) out[F + e] = ext[(size_t)nExt * i + extIdx[e]];
       }
     }

@@ -303,6 +303,7 @@ __device__ __forceinline__ int stage_structure(int st, int beg, int nAt, const d
                                                const int *__restrict__ periodic, double rc, CRec *__restrict__ cand,
                                                int capC, StructGeom *__restrict__ g, int *__restrict__ flags) {
   if (nAt > capC) return -nAt;
+#pragma unroll 1
   for (int t = threadIdx.x; t < nAt; t += blockDim.x) {
     const size_t j = (size_t)beg + t;
     CRec r;

@@ -494,6 +494,7 @@ extern "C" int fnetgpu_acsf_set(fnetgpu_ctx *ctx, int F, const int *type, const 
       R.lgn = G.nChunksP2 == 1 ? 0 : (G.nChunksP2 == 2 ? 1 : 2);
       R.rc = G.rc; R.invrc = 1.0 / G.rc; R.eta = G.eta; R.rs0 = G.rs0; R.drs = G.drs;
       for (int q = 0; q < FNET_RCHUNK - 1; q++) R.kk[q] = G.kk[q];
+      R.kk7 = exp(-G.eta * G.drs * G.drs * 15.0); R.c16 = exp(-G.eta * G.drs * G.drs * 16.0);
       maxChunks = std::max(maxChunks, G.nChunksP2);
       lrad.push_back(R);
     }
@@ -797,9 +798,11 @@ static int plan_struct_launch(fnetgpu_ctx *ctx, const Slot &s, size_t warpBytes,
   L.smem = prefix + warpBytes * L.wpb;
   while (L.smem > 220 * 1024 && L.wpb > 1) { L.wpb >>= 1; L.smem = prefix + warpBytes * L.wpb; }
   if (L.smem > 220 * 1024) FNET_FAIL(ctx, "too many neighbours per atom for the shared-memory neighbour buffers");
-  // ~8 central atoms per warp (measured: 4 -> 8 is -1.1 % on C2 and C3, 16 adds nothing); more splits
-  // when there are too few structures to fill the GPU.  FNETGPU_ACSF_ATOMS_PER_WARP overrides (A/B).
-  static const int apw = [] { const char *e = getenv("FNETGPU_ACSF_ATOMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  // <= 32 central atoms per warp: the CTA prologue (structure, lattice inverse, power / pair / pass tables -> shared
+  // memory, two barriers) was 15 % of the lean kernel's stall samples at 8 atoms per warp (ncu source page); same-box
+  // A/B 8 -> 16 -> 32: C2 ACSF 0.842 -> 0.799 -> 0.800 ms, C3 15.38 -> 14.90 -> 14.74 ms.  More splits when there are
+  // too few structures to fill the GPU.  FNETGPU_ACSF_ATOMS_PER_WARP overrides (A/B).
+  static const int apw = [] { const char *e = getenv("FNETGPU_ACSF_ATOMS_PER_WARP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
   int nSplit = (s.maxAtoms + apw * L.wpb - 1) / (apw * L.wpb);
   const long long want = 8LL * ctx->nSM;
   if ((long long)s.nStruct * nSplit < want)

@@ -108,6 +108,7 @@ struct LeanRadial {            // G2 group on an arithmetic rs-ladder with one e
   int sharedFc;                // rc equals LeanTables::rcShared: the per-neighbour cutoff values are reused
   double rc, invrc, eta, rs0, drs;
   double kk[FNET_RCHUNK - 1];  // kk[m] = exp(-eta drs^2 (2m+1))
+  double kk7, c16;             // exp(-15 eta drs^2), exp(-16 eta drs^2): the value kernel chains two chunks (functions 8..15 from 0..7)
 };
 
 struct LeanPass {              // NL lambda-groups x NC chained 8-function slots of one xi-ladder each

@@ -122,8 +122,8 @@ __device__ __forceinline__ void mma_load_weights(const NetTables &net, const Mma
     for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = wb[net.boff[l] + e];
 }
 
-// transfer function as a separate element-wise pass over a warp tile (z -> f(z), optionally f'(z)): an even split
-// of the dout*8 elements over the lanes.  Inlined into its two call sites (the layer loop of the forward sweep, with
+// transfer functions other than tanh (mma_forward applies that one in registers) as a separate element-wise pass
+// over a warp tile (z -> f(z), optionally f'(z)): an even split of the dout*8 elements over the lanes.  Inlined into its two call sites (the layer loop of the forward sweep, with
 // and without derivative): as an out-of-line function its tile and table pointers were GENERIC (LD.E / ST.E instead of
 // LDS / STS) and the two-element arrays lived in local memory (ncu: 38 % of the kernel's instructions in this pass).
 template <bool DERIV>
@@ -142,10 +142,7 @@ __device__ __forceinline__ void mma_activate(int actId, int dout, double *__rest
       off[q] = (idx >> 3) * FNET_MMA_TS + (idx & 7);
       x[q] = out[off[q]];
     }
-    if (actId == FNETGPU_ACT_TANH) {
-#pragma unroll
-      for (int q = 0; q < 2; q++) v[q] = fnet_tanh_tab(x[q], etab);
-    } else if (actId == FNETGPU_ACT_SIGMOID) {
+    if (actId == FNETGPU_ACT_SIGMOID) {
 #pragma unroll
       for (int q = 0; q < 2; q++) v[q] = act_f<double>(FNETGPU_ACT_SIGMOID, x[q]);
     } else {
@@ -154,9 +151,9 @@ __device__ __forceinline__ void mma_activate(int actId, int dout, double *__rest
     }
     double d[2];
     if (DERIV) {
-      if (actId == FNETGPU_ACT_TANH || actId == FNETGPU_ACT_SIGMOID) {
+      if (actId == FNETGPU_ACT_SIGMOID) {
 #pragma unroll
-        for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId == FNETGPU_ACT_TANH ? FNETGPU_ACT_TANH : FNETGPU_ACT_SIGMOID, x[q], v[q]);
+        for (int q = 0; q < 2; q++) d[q] = act_d<double>(FNETGPU_ACT_SIGMOID, x[q], v[q]);
       } else {
 #pragma unroll
         for (int q = 0; q < 2; q++) d[q] = act_d<double>(actId, x[q], v[q]);
@@ -195,7 +192,11 @@ __device__ __forceinline__ void mma_k_dispatch(int ncnt, int KT, const double *_
 }
 
 // forward layer of one warp tile: out[o][t] = f(sum_i W[o][i] in[i][t] + b[o]); DERIV also
-// stores f'(z) (later overwritten by the delta)
+// stores f'(z) (later overwritten by the delta).  tanh -- the reference's default transfer function
+// (initprogram.F90) -- is applied to the DMMA accumulators IN REGISTERS (lane (g, c) holds z of atom g for the
+// outputs 8 nt + 2 c, + 1: two independent chains per tile) and a, f'(z) are stored once; the separate
+// element-wise pass (store z, read z, index arithmetic, store a / f') was 36 % of the kernel's instructions
+// (ncu source page).  Other transfer functions keep that pass (mma_activate).
 template <bool DERIV>
 __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const double *__restrict__ W, int wS,
                                             const double *__restrict__ bias, const double *__restrict__ in,
@@ -203,6 +204,7 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
                                             const double *__restrict__ etab) {
   const int g = lane >> 2, c = lane & 3;
   const int KT = fnet_ru4(din) >> 2, NT = fnet_ru8(dout) >> 3;
+  const bool inreg = actId == FNETGPU_ACT_TANH;
   for (int nt0 = 0; nt0 < NT; nt0 += 4) {
     double acc[4][2];
 #pragma unroll
@@ -213,17 +215,34 @@ __device__ __forceinline__ void mma_forward(int din, int dout, int actId, const 
     const double *ip = in + c * FNET_MMA_TS + g;
     const double *wp = W + (size_t)(8 * nt0 + g) * wS + c;
     mma_k_dispatch(min(4, NT - nt0), KT, ip, wp, 4 * FNET_MMA_TS, 4, (size_t)8 * wS, acc);
+    if (inreg) {
 #pragma unroll
-    for (int nc = 0; nc < 4; nc++)
-      if (nt0 + nc < NT) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int o = 8 * (nt0 + nc) + 2 * c + e;
-          if (o < dout) out[o * FNET_MMA_TS + g] = acc[nc][e];
+      for (int nc = 0; nc < 4; nc++)
+        if (nt0 + nc < NT) {
+          const int o = 8 * (nt0 + nc) + 2 * c;
+          const double v0 = fnet_tanh_em1(acc[nc][0], etab), v1 = fnet_tanh_em1(acc[nc][1], etab);
+          if (o < dout) {
+            out[o * FNET_MMA_TS + g] = v0;
+            if (DERIV) dact[o * FNET_MMA_TS + g] = fma(-v0, v0, 1.0);        // transfer.F90: 1 - tanh^2
+          }
+          if (o + 1 < dout) {
+            out[(o + 1) * FNET_MMA_TS + g] = v1;
+            if (DERIV) dact[(o + 1) * FNET_MMA_TS + g] = fma(-v1, v1, 1.0);
+          }
         }
-      }
+    } else {
+#pragma unroll
+      for (int nc = 0; nc < 4; nc++)
+        if (nt0 + nc < NT) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int o = 8 * (nt0 + nc) + 2 * c + e;
+            if (o < dout) out[o * FNET_MMA_TS + g] = acc[nc][e];
+          }
+        }
+    }
   }
-  if (actId != FNETGPU_ACT_LINEAR || DERIV) {
+  if (!inreg && (actId != FNETGPU_ACT_LINEAR || DERIV)) {
     __syncwarp();
     mma_activate<DERIV>(actId, dout, out, dact, lane, etab);
   }
@@ -435,6 +454,9 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   atom0 = load_atom(e0);
   atom1 = load_atom(e1);
   load_features(atom0);
+  // structure of this lane's atom, one round ahead too: structOf -> offsets / weights / targets is a chain of dependent
+  // global loads at the head of every round (ncu: 6 % of the kernel's stall samples on 2 % of its instructions)
+  int strc0 = (MODE == 0 && atom0 >= 0) ? structOf[atom0] : 0;
   for (int r = round0; r < round1; r++) {
     const int sp = e0[2];
     const int nTl = (e0[1] + TW - 1) / TW;          // tiles with atoms in this round
@@ -442,6 +464,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
                                                     // is swept with zero features so that no stale delta reaches the gradient sweep)
     const int count = min(max(e0[1] - TA * warp, 0), TA);
     const int myAtom = atom0;
+    const int strc1 = (MODE == 0 && atom1 >= 0) ? structOf[atom1] : 0;
     int e2[4];
     load_entry(r + 2, e2);
     if (FUSED == 2) {      // this round's half of the exchange area: its last readers passed the previous cluster barrier
@@ -460,7 +483,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
     int lgStruct = 0, lgB = 0, lgE = 0, lgSeg = 0;
     if (warp < nIn) {
       if (MODE == 0 && myAtom >= 0) {
-        lgStruct = structOf[myAtom];
+        lgStruct = strc0;
         if (FUSED == 2) lgSeg = segBE[e0[0] + TA * warp + lane];
         lgB = offsets[lgStruct]; lgE = offsets[lgStruct + 1];
         lgAw = aw[myAtom]; lgW = dsw[lgStruct];
@@ -764,6 +787,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
     e0[0] = e1[0]; e0[1] = e1[1]; e0[2] = e1[2]; e0[3] = e1[3];
     e1[0] = e2[0]; e1[1] = e2[1]; e1[2] = e2[2]; e1[3] = e2[3];
     atom0 = atom1; atom1 = atom2;
+    strc0 = strc1;
   }
   if (MODE == 0 && curSp >= 0) flush(curSp);
   if (FUSED == 2) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still read its exchange area

@@ -93,7 +93,7 @@ k_bpnn_warp(const int *__restrict__ tiles, const int *__restrict__ perm, const d
       const double z = (z0 + z1) + (z2 + z3);
       if (last) out[o] = z;                                      // network.F90:391: the output layer is linear
       else {
-        const double v = net.act == FNETGPU_ACT_TANH ? fnet_tanh_tab(z, etab) : act_f<double>(net.act, z);
+        const double v = net.act == FNETGPU_ACT_TANH ? fnet_tanh_em1(z, etab) : act_f<double>(net.act, z);
         out[o] = v;
         fp[net.aoff[l] + o] = act_d<double>(net.act, z, v);
       }

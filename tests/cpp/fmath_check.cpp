@@ -90,6 +90,27 @@ int main() {
     if (re > mtt) mtt = re;
   }
   if (fnet_tanh_tab(0.0, tab) != 0.0 || fnet_tanh_tab(1e3, tab) != 1.0 || fnet_tanh_tab(-1e3, tab) != -1.0) { printf("tanh_tab edge cases failed\n"); return 1; }
-  printf("FMATH_OK %.3e %.3e %.3e tab: %.3e %.3f %.3e\n", me, ml, mt, met, mlt, mtt);
-  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13 && met < 1e-14 && mlt < 1.0 && mtt < 5e-13) ? 0 : 2;
+  // expm1-form tanh of the DMMA subnetwork kernels: relative error on the whole axis, incl. tiny arguments
+  double mte = 0.0;
+  for (int i = 0; i < 4000000; i++) {
+    double u = urand(seed);
+    double x;
+    switch (i % 5) {
+      case 0: x = 40.0 * (u - 0.5); break;
+      case 1: x = 2.0 * (u - 0.5); break;
+      case 2: x = 0.02 * (u - 0.5); break;                       // around the k = 0 / j = 0, 1 table cells
+      case 3: x = ldexp(u - 0.5, -(int)(300 * urand(seed))); break;
+      default: x = 0.34657359 * (1.0 + 1e-6 * (u - 0.5)) * (double)(1 + (i % 7)); break;   // k boundaries (2x = m ln2)
+    }
+    if (i % 1000 == 7) x = 800.0 * (u - 0.5);
+    double a = fnet_tanh_em1(x, tab), b = tanh(x);
+    double re = (b == 0.0) ? fabs(a) : fabs(a - b) / fabs(b);
+    if (re > mte) mte = re;
+  }
+  if (fnet_tanh_em1(0.0, tab) != 0.0 || fnet_tanh_em1(1e3, tab) != 1.0 || fnet_tanh_em1(-1e3, tab) != -1.0 ||
+      fnet_tanh_em1(INFINITY, tab) != 1.0 || fnet_tanh_em1(-INFINITY, tab) != -1.0 || fnet_tanh_em1(-1e-310, tab) != -1e-310) {
+    printf("tanh_em1 edge cases failed\n"); return 1;
+  }
+  printf("FMATH_OK %.3e %.3e %.3e tab: %.3e %.3f %.3e em1: %.3e\n", me, ml, mt, met, mlt, mtt, mte);
+  return (me < 1e-14 && ml < 1e-14 && mt < 5e-13 && met < 1e-14 && mlt < 1.0 && mtt < 5e-13 && mte < 1e-14) ? 0 : 2;
 }
