@@ -241,7 +241,7 @@ __device__ __forceinline__ int list_at(const NbList &l, int t) { return t < l.n0
 // fc = 0.5 q (cos(pi r / rc) + 1) (acsf.F90:1201) for 0 <= r <= rc, evaluated as q cos^2(pi r / (2 rc))
 // with the Taylor polynomial of cos on [0, pi/2] (12 terms, truncation 2e-17; absolute error ~2e-16,
 // what the reference's own cos + 1 cancellation has near rc) -- 14 FP64 operations instead of cospi's ~55
-__constant__ double fnet_cosh_cd[12] = {
+static __constant__ double fnet_cosh_cd[12] = {
   1.0, -1.2337005501361697, 0.25366950790104803, -0.02086348076335296, 0.0009192602748394266,
   -2.5202042373060607e-05, 4.710874778818172e-07, -6.386603083791852e-09, 6.565963114979473e-11,
   -5.294400200734623e-13, 3.437739179098607e-15, -1.8359916521552453e-17 };   // (-1)^k (pi/2)^(2k) / (2k)!
@@ -255,7 +255,7 @@ __device__ __forceinline__ double cutoff_fn(double rr, double qq, double invrc) 
 
 // (1 + lam*c)^xi ladder start and ratio from b = max(1 + lam*c, 0) and L = log(b), with the
 // pow(0,0)=1 / pow(0,x>0)=0 conventions (log(0) = -inf, exp(-inf) = 0)
-__device__ __noinline__ double fnet_exp_call(double x) { return fnet_exp(x); }   // keeps rare paths out of line
+static __device__ __noinline__ double fnet_exp_call(double x) { return fnet_exp(x); }   // keeps rare paths out of line
 __device__ __forceinline__ void ladder_init(double b, double L, double xi0, double dxi, double &p, double &q,
                                             const double *__restrict__ ftab) {
   if (xi0 == 1.0) p = b;                       // auto scheme: every ladder starts at xi = 1 (acsf.F90:341)
@@ -348,7 +348,7 @@ __device__ __forceinline__ double reduce_smem(const double (&v)[M], int lane, in
 //     accumulator per lane, xor-shuffle over the sub-lanes.  Kept small on purpose: this path
 //     only has to be correct, the instruction cache belongs to the hot loops.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ double radial_term_generic(int type, double p1, double p2, double rr) {
+static __device__ __noinline__ double radial_term_generic(int type, double p1, double p2, double rr) {
   if (type == FNETGPU_G1) return 1.0;
   if (type == FNETGPU_G2) { const double d = rr - p2; return exp(-p1 * d * d); }
   return cos(p1 * rr);
@@ -596,6 +596,7 @@ __global__ void k_zstat(int N, int F, int nFeat, const real *__restrict__ feat,
   }
 }
 
+#ifndef FNET_KERNEL_TU   // non-template kernels: defined once, in fnetgpu.cu (kernels_*.cu set FNET_KERNEL_TU)
 // out[f] = sum_b part[b][f]: one CTA per feature, strided partial sums + a fixed-shape tree (deterministic)
 __global__ void __launch_bounds__(256) k_zstat_final(int nBlocks, int F, const double *__restrict__ part, double *__restrict__ out) {
   __shared__ double sh[256];
@@ -610,6 +611,7 @@ __global__ void __launch_bounds__(256) k_zstat_final(int nBlocks, int F, const d
   }
   if (threadIdx.x == 0) out[f] = sh[0];
 }
+#endif
 
 template <typename real>
 __global__ void k_zapply(size_t N, int F, int nFeat, real *__restrict__ feat, const double *__restrict__ zprec) {

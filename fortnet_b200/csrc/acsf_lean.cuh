@@ -389,6 +389,17 @@ __device__ __forceinline__ int lean_gather_linear(const CtaGeom &cg, const AcsfT
 #ifndef FNET_LEAN_MINB
 #define FNET_LEAN_MINB 4
 #endif
+// The kernel lives in its OWN translation unit (kernels_lean.cu defines FNET_DEFINE_LEAN_KERNEL and instantiates every
+// variant): in one unit with the rest of the library its code generation changed with edits to unrelated kernels -- the
+// same source compiled to 5 176 or 5 568 instructions, and the species-resolved C3 launch took 15.3 or 19.3 ms.  The
+// other units see a variable template of the same name that holds the kernel's address, so launch sites read alike.
+typedef void (*LeanKernelT)(int, GeomArgs, int, const double *, AcsfTables, LeanTables, int, int, void *, int, int,
+                            const double *, int, const int *, int *);
+LeanKernelT fnet_lean_kernel(int NL, int NC, int PATH, bool SORTED, int G, bool F32A);   // kernels_lean.cu (nullptr: not built)
+#ifndef FNET_DEFINE_LEAN_KERNEL
+template <int NL, int NC, int PATH, bool SORTED, int G, bool F32A>
+static const LeanKernelT k_acsf_lean = fnet_lean_kernel(NL, NC, PATH, SORTED, G, F32A);
+#else
 template <int NL, int NC, int PATH, bool SORTED, int G, bool F32A>
 __global__ void __launch_bounds__(128, (NL * NC <= 2 ? FNET_LEAN_MINB : 3))
 k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, AcsfTables tab, LeanTables lt, int cap,
@@ -717,3 +728,4 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   for (int o = 16; o >= LPA; o >>= 1) nmaxW = max(nmaxW, __shfl_xor_sync(0xffffffffu, nmaxW, o));
   if (lane == 0 && nmaxW > 0) atomicMax(&flags[0], nmaxW);   // exact capacity hint for the next launch
 }
+#endif   // FNET_DEFINE_LEAN_KERNEL

@@ -29,6 +29,7 @@ __device__ __forceinline__ int floor_div(int a, int b) {
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
+#ifndef FNET_KERNEL_TU   // non-template kernels: defined once, in fnetgpu.cu (kernels_*.cu set FNET_KERNEL_TU)
 // one thread per atom: fold, bin, histogram
 __global__ void k_bin_count(int N, const double *__restrict__ coords, const int *__restrict__ structOf,
                             const StructInfo *__restrict__ sinfo, double *__restrict__ fpos,
@@ -128,6 +129,7 @@ __global__ void k_bin_sort(int nBins, const int *__restrict__ cellStart, int *__
     crec[a] = r;
   }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Neighbour cells of a bin.  The bin's (2D0+1)(2D1+1)(2D2+1) neighbour cells are numbered
@@ -383,6 +385,7 @@ __device__ __forceinline__ bool is_neighbor(bool valid, double d2, double rc2, i
   return valid && (d2 <= rc2) && !(j == i && !(zs & FNET_SHIFT_FLAG));
 }
 
+#ifndef FNET_KERNEL_TU   // non-template kernels: defined once, in fnetgpu.cu (kernels_*.cu set FNET_KERNEL_TU)
 // statistics that size the shared-memory buffers (one warp per atom, cell order):
 // flags[0] = max neighbours per atom, flags[2..3] = sum of neighbours (64 bit),
 // flags[5] = max candidates per bin, flags[6] = max neighbour cells per bin
@@ -410,3 +413,4 @@ __global__ void k_neigh_count(int N, const int *__restrict__ binOfSlot_unused, c
     atomicMax(&flags[6], p.ncells);
   }
 }
+#endif

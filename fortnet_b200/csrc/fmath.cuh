@@ -37,8 +37,9 @@
   1.4285714285714285e-01, 2.0000000000000001e-01, 3.3333333333333331e-01, \
   1.90821492927058770002e-10, 6.93147180369123816490e-01 }
 #ifdef __CUDACC__
-__constant__ double fnet_exp_cd[14] = FNET_EXP_COEFFS;
-__constant__ double fnet_log_cd[12] = FNET_LOG_COEFFS;
+// static: every translation unit of the library (fnetgpu.cu, kernels_lean.cu, kernels_mma.cu) keeps its own copy
+static __constant__ double fnet_exp_cd[14] = FNET_EXP_COEFFS;
+static __constant__ double fnet_log_cd[12] = FNET_LOG_COEFFS;
 #endif
 static const double fnet_exp_ch[14] = FNET_EXP_COEFFS;
 static const double fnet_log_ch[12] = FNET_LOG_COEFFS;
@@ -186,8 +187,8 @@ static const double fnet_log_tab_h[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
 #ifdef __CUDACC__
 // global (not constant) memory: the CTAs copy the tables into shared memory with one coalesced load
 // per thread -- lane-divergent reads of the constant bank would be serialised
-__device__ const double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
-__device__ const double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
+static __device__ const double fnet_exp_tab_d[FNET_EXP_TAB_N] = FNET_EXP_TAB_INIT;
+static __device__ const double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
 #endif
 #define FNET_TAB_DOUBLES (FNET_EXP_TAB_N + 2 * FNET_LOG_TAB_N)     // exp table, then (invc, logc) pairs
 // scalar constants of the two routines: from the constant bank on the device (a 64-bit literal costs
@@ -198,7 +199,7 @@ __device__ const double fnet_log_tab_d[2 * FNET_LOG_TAB_N] = FNET_LOG_TAB_INIT;
   6.93147180369123816490e-01, 1.90821492927058770002e-10 }
 static const double fnet_tabc_h[13] = FNET_TABC_INIT;
 #ifdef __CUDACC__
-__constant__ double fnet_tabc_d[13] = FNET_TABC_INIT;
+static __constant__ double fnet_tabc_d[13] = FNET_TABC_INIT;
 #endif
 #ifdef __CUDA_ARCH__
 #define FNET_TC(i) fnet_tabc_d[i]

@@ -1504,7 +1504,7 @@ static int run_forward(fnetgpu_ctx *ctx, Slot &s) {
         LAUNCH(ctx, K_MLP_FWD, (k_bpnn_mma<2, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(       \
                                    s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,          \
                                    (const double *)ctx->d_wb, n, nullptr, nullptr, nullptr, nullptr, nullptr,     \
-                                   nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw)));                         \
+                                   nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_raw, nullptr, nullptr, nullptr, nullptr))); \
       } while (0)
       if (n.dims[0] <= 32) FNET_MMA_FWD(1); else FNET_MMA_FWD(2);
 #undef FNET_MMA_FWD
@@ -1534,7 +1534,7 @@ static int run_ingrad(fnetgpu_ctx *ctx, Slot &s) {
         LAUNCH(ctx, K_MLP_INGRAD, (k_bpnn_mma<1, 1, FCH><<<fgrid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(    \
                                       s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,       \
                                       (const double *)ctx->d_wb, n, nullptr, nullptr, nullptr, nullptr, nullptr,  \
-                                      nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_dEdG)));                     \
+                                      nullptr, s.nG, s.nA, 0, nullptr, (double *)s.d_dEdG, nullptr, nullptr, nullptr, nullptr))); \
       } while (0)
       if (n.dims[0] <= 32) FNET_MMA_ING(1); else FNET_MMA_ING(2);
 #undef FNET_MMA_ING
@@ -1626,9 +1626,6 @@ static int wait_allreduce(fnetgpu_ctx *ctx) {
 // the padding of the groups; when the two-pass path (forward kernel + k_struct_loss + gradient kernel) is estimated
 // cheaper -- or a structure needs more than 8 rounds -- it stays.
 // ------------------------------------------------------------------------------------------
-typedef void (*MmaKernelT)(int, const int *, const int *, const double *, int, const double *, NetTables, const int *,
-                           const int *, const double *, const double *, const double *, const double *, int, int, int,
-                           double *, double *, const double *, double *, double *, const int *);
 static MmaKernelT mma_cluster_kernel(const NetTables &n) {
   const MmaLayout ml = mma_layout(n);
   const int perWarp = (ml.nGradTiles + FNET_MMA_WARPS - 1) / FNET_MMA_WARPS;
@@ -1798,14 +1795,15 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                       s.nTilesS, s.d_tilesS, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                       (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, nullptr, s.d_at,   \
                                       s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr,    \
-                                      s.d_gt, s.d_Es, s.d_lossPart)));                                            \
+                                      s.d_gt, s.d_Es, s.d_lossPart, nullptr)));                                   \
           break;                                                                                                  \
         }                                                                                                         \
         CUDA_TRY(ctx, fnet_smem_attr(k_bpnn_mma<0, NSLOT, FCH>, M.smem)); \
         LAUNCH(ctx, K_MLP_GRAD, (k_bpnn_mma<0, NSLOT, FCH><<<grid, FNET_MMA_WARPS * 32, M.smem, ctx->stream>>>(   \
                                     s.nTiles16, s.d_tiles16, s.d_perm, (const double *)s.d_feat, s.nFeat,         \
                                     (const double *)ctx->d_wb, n, s.d_structOf, s.d_offsets, s.d_gS, s.d_at,      \
-                                    s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr)));   \
+                                    s.d_aw, s.d_dsw, s.nG, s.nA, lossId, ctx->d_partials, (double *)nullptr,      \
+                                    nullptr, nullptr, nullptr, nullptr)));                                        \
       } while (0)
       if (cfused) {
         MmaKernelT kc = mma_cluster_kernel(n);

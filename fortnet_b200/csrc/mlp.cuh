@@ -554,6 +554,7 @@ __global__ void k_struct_loss(int nStruct, const int *__restrict__ offsets, int 
   if (lane == 0) { lossPart[2 * s] = num; lossPart[2 * s + 1] = den; }
 }
 
+#ifndef FNET_KERNEL_TU   // non-template kernels: defined once, in fnetgpu.cu (kernels_*.cu set FNET_KERNEL_TU)
 // fixed-shape reduction of the per-structure loss terms -> out[0] = numerator, out[1] = denominator
 __global__ void k_loss_final(int nStruct, const double *__restrict__ lossPart, double *__restrict__ out) {
   __shared__ double sm[2][1024];
@@ -576,3 +577,4 @@ __global__ void k_grad_reduce(int nCta, int nDD, const double *__restrict__ part
   for (int c = 0; c < nCta; c++) s += partials[(size_t)c * nDD + p];
   dd[p] = s;
 }
+#endif

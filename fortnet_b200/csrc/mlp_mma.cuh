@@ -323,6 +323,16 @@ struct MmaWgradDispatch<0, NSLOT> {
 // round-local range of every atom's structure).  After its forward sweep each CTA leaves the partial sums of its
 // structures in shared memory, the cluster synchronises (barrier.cluster) and every CTA reads the other CTAs' partial
 // sums through distributed shared memory in rank order: E_s, loss gradient and loss terms without a second forward pass.
+// The kernel lives in its own translation unit (kernels_mma.cu defines FNET_DEFINE_MMA_KERNEL; see acsf_lean.cuh for the
+// reason); the other units see a variable template of the same name that holds the kernel's address.
+typedef void (*MmaKernelT)(int, const int *, const int *, const double *, int, const double *, NetTables, const int *,
+                           const int *, const double *, const double *, const double *, const double *, int, int, int,
+                           double *, double *, const double *, double *, double *, const int *);
+MmaKernelT fnet_mma_kernel(int MODE, int NSLOT, int FCH, int FUSED);   // kernels_mma.cu (nullptr: not built)
+#ifndef FNET_DEFINE_MMA_KERNEL
+template <int MODE, int NSLOT, int FCH, int FUSED = 0>
+static const MmaKernelT k_bpnn_mma = fnet_mma_kernel(MODE, NSLOT, FCH, FUSED);
+#else
 template <int MODE, int NSLOT, int FCH, int FUSED = 0>
 __global__ void __launch_bounds__(FNET_MMA_WARPS * 32, (NSLOT <= 4 ? 2 : 1))
 k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ perm, const double *__restrict__ feat,
@@ -336,7 +346,13 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
   const int L = net.L, d0 = net.dims[0];
-  const MmaLayout m = mma_layout(net);
+  // the layer offsets are indexed with run-time layer numbers: as a local array they live in LOCAL memory, whose L1 lines
+  // the streamed feature rows keep evicting (ncu: 5 % of the kernel's stall samples on the address arithmetic behind those
+  // LDL at the head of every layer) -- one copy per CTA in shared memory instead
+  __shared__ MmaLayout mShared;
+  if (threadIdx.x == 0) mShared = mma_layout(net);
+  __syncthreads();
+  const MmaLayout &m = mShared;
   const int rows = (MODE == 2) ? m.rowsA : m.rows;
   double *wsm = (double *)smem_raw;
   double *etab = wsm + m.wTotal;                  // 2^(j/64) table of the transfer functions (fmath.cuh)
@@ -355,31 +371,36 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   const int ES = FUSED == 2 ? 4 : 3;              // ints per entry
 
   // ---- weight-gradient tiles owned by this warp: q = warp*per + s <-> (layer, i-tile, o-tile) ----
-  int aRow[NSLOT], dRow[NSLOT], gInfo[NSLOT];
+  int aRow[NSLOT], dRow[NSLOT];
   bool newA[NSLOT];
   double acc[NSLOT][2];
   double bacc = 0.0;
-  int nMine = 0, bRow = -1, bIdx = -1;
+  int nMine = 0, bRow = -1, bIdx = -1, q0 = 0;
+  // gradient tile q -> (layer, i-tile, o-tile); recomputed in flush() rather than kept in registers
+  auto tile_of = [&](int q, int &l, int &mt, int &nt) {
+    l = 0;
+    while (true) {
+      const int cnt = (fnet_ru8(net.dims[l]) >> 3) * (fnet_ru8(net.dims[l + 1]) >> 3);
+      if (q < cnt) break;
+      q -= cnt; l++;
+    }
+    const int ntl = fnet_ru8(net.dims[l + 1]) >> 3;
+    mt = q / ntl; nt = q % ntl;
+  };
   if (MODE == 0) {
     const int per = (m.nGradTiles + NW - 1) / NW;
-    const int q0 = warp * per, q1 = min(m.nGradTiles, q0 + per);
+    q0 = warp * per;
+    const int q1 = min(m.nGradTiles, q0 + per);
     nMine = max(q1 - q0, 0);
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
       acc[s][0] = 0.0; acc[s][1] = 0.0;
-      aRow[s] = 0; dRow[s] = 0; gInfo[s] = -1; newA[s] = false;
+      aRow[s] = 0; dRow[s] = 0; newA[s] = false;
       if (s < nMine) {
-        int q = q0 + s, l = 0;
-        while (true) {
-          const int cnt = (fnet_ru8(net.dims[l]) >> 3) * (fnet_ru8(net.dims[l + 1]) >> 3);
-          if (q < cnt) break;
-          q -= cnt; l++;
-        }
-        const int ntl = fnet_ru8(net.dims[l + 1]) >> 3;
-        const int mt = q / ntl, nt = q % ntl;
+        int l, mt, nt;
+        tile_of(q0 + s, l, mt, nt);
         aRow[s] = m.aOff[l] + 8 * mt;
         dRow[s] = m.dOff[l + 1] + 8 * nt;
-        gInfo[s] = (l << 16) | (mt << 8) | nt;
       }
     }
 #pragma unroll
@@ -398,7 +419,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) {
       if (s < nMine) {
-        const int l = gInfo[s] >> 16, mt = (gInfo[s] >> 8) & 255, nt = gInfo[s] & 255;
+        int l, mt, nt;
+        tile_of(q0 + s, l, mt, nt);
         const int din = net.dims[l], dout = net.dims[l + 1];
         const int i = 8 * mt + g;
 #pragma unroll
@@ -434,6 +456,13 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       if (FUSED == 2) e[3] = t[3];
     }
   };
+  // the entry two rounds ahead is loaded lane-wise (lane & 3 = field) and broadcast by shuffles where it is first
+  // needed, behind the sweeps: as warp-uniform loads the compiler moved the values to uniform registers at the load
+  // (R2UR) and every warp waited for the global load there (ncu: 2.6 % of the stall samples)
+  auto load_entry_lanes = [&](int r) -> int {
+    const int f = lane & 3;
+    return (r < round1 && f < ES) ? tiles[(size_t)ES * ((size_t)r * CS + crank) + f] : 0;
+  };
   auto load_atom = [&](const int (&e)[4]) -> int {
     const int cnt = min(max(e[1] - TA * warp, 0), TA);
     return (lane < cnt) ? perm[e[0] + TA * warp + lane] : -1;
@@ -465,8 +494,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
     const int count = min(max(e0[1] - TA * warp, 0), TA);
     const int myAtom = atom0;
     const int strc1 = (MODE == 0 && atom1 >= 0) ? structOf[atom1] : 0;
-    int e2[4];
-    load_entry(r + 2, e2);
+    const int ev2 = load_entry_lanes(r + 2);
     if (FUSED == 2) {      // this round's half of the exchange area: its last readers passed the previous cluster barrier
       double *ex = exch + (size_t)(r & 1) * FNET_MMA_CSLOTS * (nG + 2);
       for (int e = threadIdx.x; e < FNET_MMA_CSLOTS * (nG + 2); e += blockDim.x) ex[e] = 0.0;
@@ -486,8 +514,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
         lgStruct = strc0;
         if (FUSED == 2) lgSeg = segBE[e0[0] + TA * warp + lane];
         lgB = offsets[lgStruct]; lgE = offsets[lgStruct + 1];
-        lgAw = aw[myAtom]; lgW = dsw[lgStruct];
-        lgScale = lgW * lgAw / (double)(lgE - lgB);   // bpnn.F90:446,698
+        lgAw = aw[myAtom]; lgW = dsw[lgStruct];       // (lgScale is formed after the forward sweep: no wait for these loads here)
         if (FUSED) {            // targets now, the sums after the forward sweep
           if (nG > 0) lgG0 = gt[(size_t)nG * lgStruct];
           if (nG > 1) lgG1 = gt[(size_t)nG * lgStruct + 1];
@@ -533,6 +560,7 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
                             T + m.dOff[l] * TS, lane, etab);
         __syncwarp();
       }
+      if (MODE == 0) lgScale = myAtom >= 0 ? lgW * lgAw / (double)(lgE - lgB) : 0.0;   // bpnn.F90:446,698
       if (MODE == 2) {
         const double *o = T + m.aOffF[L - 1] * TS;
         if (lane < count)
@@ -757,6 +785,9 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
       }
     }
     // atoms of round r + 2; their feature rows -> L2 (128-byte lines, four lanes per atom)
+    int e2[4];
+    e2[0] = __shfl_sync(0xffffffffu, ev2, 0); e2[1] = __shfl_sync(0xffffffffu, ev2, 1); e2[2] = __shfl_sync(0xffffffffu, ev2, 2);
+    e2[3] = FUSED == 2 ? __shfl_sync(0xffffffffu, ev2, 3) : 0;
     const int atom2 = load_atom(e2);
     if (MODE == 0) {
       __syncthreads();
@@ -792,3 +823,4 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   if (MODE == 0 && curSp >= 0) flush(curSp);
   if (FUSED == 2) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still read its exchange area
 }
+#endif   // FNET_DEFINE_MMA_KERNEL
