@@ -74,17 +74,29 @@ struct CtaGeom {                      // per-CTA view produced by acsf_cta_prolo
   int a0, a1, first;                  // central atoms [a0, a1): slots of crec (PATH 0/1) or atoms (PATH 2, first = atomBeg)
 };
 
+// asynchronous global -> shared copies (LDGSTS): no register staging, nothing waits until fnet_cp_async_wait()
+__device__ __forceinline__ void fnet_cp_async8(void *sdst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fnet_cp_async4(void *sdst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fnet_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Splits the CTA's bin (or structure) over blockIdx.y and stages the candidates.  Returns false
-// when this CTA has nothing to do (or on overflow, flagged for the host).
-template <int PATH, bool EXPONLY = false>
+// when this CTA has nothing to do (or on overflow, flagged for the host).  ASYNCTAB: the table goes to shared memory
+// by cp.async -- the caller waits (fnet_cp_async_wait) and synchronises the CTA before it reads c.ftab.
+template <int PATH, bool EXPONLY = false, bool ASYNCTAB = false>
 __device__ __forceinline__ bool acsf_cta_prologue(const GeomArgs &G, int nSplit, double rcMax, int capC,
                                                   unsigned char *smem_raw, int *__restrict__ flags, CtaGeom &c,
                                                   unsigned char *&wbase) {
   {   // tables first; the barriers of the staging below (or the explicit one of PATH 0) publish them
     double *ft = (double *)smem_raw;
 #pragma unroll 1
-    for (int e = threadIdx.x; e < (EXPONLY ? FNET_EXP_TAB_N : FNET_TAB_DOUBLES); e += blockDim.x)
-      ft[e] = e < FNET_EXP_TAB_N ? fnet_exp_tab_d[e] : fnet_log_tab_d[e - FNET_EXP_TAB_N];
+    for (int e = threadIdx.x; e < (EXPONLY ? FNET_EXP_TAB_N : FNET_TAB_DOUBLES); e += blockDim.x) {
+      if (ASYNCTAB) fnet_cp_async8(ft + e, e < FNET_EXP_TAB_N ? &fnet_exp_tab_d[e] : &fnet_log_tab_d[e - FNET_EXP_TAB_N]);
+      else ft[e] = e < FNET_EXP_TAB_N ? fnet_exp_tab_d[e] : fnet_log_tab_d[e - FNET_EXP_TAB_N];
+    }
     c.ftab = ft;
     smem_raw += EXPONLY ? FNET_EXP_TAB_N * sizeof(double) : FNET_FTAB_BYTES;
   }

@@ -262,6 +262,15 @@ __device__ __forceinline__ void lean_rect_decode(int p, int n2, int &j, int &k) 
 #ifndef FNET_LEAN_UNROLL
 #define FNET_LEAN_UNROLL 2
 #endif
+// species-resolved configurations: ONE pair per lane and iteration -- they execute two instantiations of the pair loop
+// (identical lists, two lists) plus the counting sort, and with two pairs in flight their executed code no longer fits
+// the instruction caches (L0 ~6 KB, L1.5 32 KB): C3 ACSF 17.3 -> 14.0 ms in a same-box A/B of deterministic builds
+#ifndef FNET_LEAN_UNROLL_SORTED
+#define FNET_LEAN_UNROLL_SORTED 1
+#endif
+#ifndef FNET_LEAN_PAIR_PRAGMA
+#define FNET_LEAN_PAIR_PRAGMA
+#endif
 // One angular pass over the pairs of (l1, l2); indices beyond the last pair map to (0, n1) resp. (n1, 0): the dummy
 // neighbour.  Two pairs per lane and iteration for the 16-accumulator shapes: two independent pairs hide the latency of
 // the dependent table-lookup / DFMA chains at 16 resident warps per SM (measured on C2 / C3: 0.91 -> 0.83 ms,
@@ -272,7 +281,7 @@ __device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER],
                                                const NbList &l1, const NbList &l2, int n1, int n2, int m0,
                                                const double (&lam)[NL], const double *__restrict__ pt,
                                                const unsigned short *__restrict__ ptab, const LeanTables &lt, int sl) {
-  constexpr int U = NL * NC <= 2 ? FNET_LEAN_UNROLL : 1;
+  constexpr int U = NL * NC <= 2 ? (SORTED ? FNET_LEAN_UNROLL_SORTED : FNET_LEAN_UNROLL) : 1;
   constexpr int S = U * LPA;
   const int nP = KIND == 2 ? n1 * n2 : (n1 * (n1 - 1)) >> 1;
   int jj[U], kk[U];
@@ -283,6 +292,7 @@ __device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER],
       else lean_rect_decode(u * LPA + sl, n2, jj[u], kk[u]);
     }
   }
+  FNET_LEAN_PAIR_PRAGMA
   for (int p0 = 0; p0 < nP; p0 += S) {
     int a[U], b[U];
 #pragma unroll
@@ -418,43 +428,54 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   CtaGeom cg;
   unsigned char *wbase;
   typedef typename std::conditional<F32A, float, double>::type AT;   // arithmetic type of the pair sums
-  if (!acsf_cta_prologue<PATH, true>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) return;   // exp table only
+  // Tables that do not depend on the geometry (power tables, pass / radial tables, pair table) go to shared memory as
+  // ASYNCHRONOUS copies (cp.async) issued before anything else: their global-memory latency then overlaps the staging
+  // of the structure (offsets -> coordinates, lattice inverse, a barrier) instead of following it -- the CTA prologue was
+  // 9 % of the kernel's stall samples even at 64 atoms per CTA, most of it rolled load -> store loops waiting one
+  // global-memory round trip per iteration.
   const int F = tab.F, Fp = (F + 1) & ~1;
-  double *pt = (double *)wbase;                     // power tables
+  unsigned char *wbase0 = smem_raw + FNET_EXP_TAB_N * sizeof(double) +
+      (PATH == FNET_PATH_DIRECT ? 0 : acsf_cta_prefix_bytes(capC, PATH == FNET_PATH_STRUCT ? 2 : 1) - FNET_FTAB_BYTES);
+  double *pt = (double *)wbase0;                    // power tables
   double *zmu = pt + FNET_POW_DOUBLES, *zis = zmu + Fp;
   unsigned char *zcode = (unsigned char *)(zis + Fp);   // atomic number -> species code (SORTED)
-  // staging loops stay rolled: once per CTA, and the kernel's executed code has to fit the 32 KB L1.5 instruction cache
-#pragma unroll 1
-  for (int e = threadIdx.x; e < FNET_POW_DOUBLES; e += blockDim.x) pt[e] = lt.powtab[e];
-#pragma unroll 1
-  for (int a = threadIdx.x; a < F; a += blockDim.x) {
-    double mu = 0.0, is = 1.0;
-    if (zprec) { const double sg = zprec[F + a]; if (!(sg < 1e-08)) { mu = zprec[a]; is = 1.0 / sg; } }   // acsf.F90:505-507
-    zmu[a] = mu; zis[a] = is;
-  }
-  if (SORTED)
-#pragma unroll 1
-    for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
-  // pass / radial tables (when small) and the used part of the pair table: shared-memory latency instead of L1's
-  unsigned char *stage = zcode + 128;
+  unsigned char *stage = zcode + 128;               // pass / radial tables (when small): shared-memory latency instead of L1's
+  unsigned short *ptab = (unsigned short *)(stage + ((lt.stageBytes + 15) & ~15));   // the used part of the pair table
   const LeanPass *passes = lt.pass;
   const LeanRadial *rads = lt.rad;
+#pragma unroll 1
+  for (int e = threadIdx.x; e < FNET_POW_DOUBLES; e += blockDim.x) fnet_cp_async8(pt + e, lt.powtab + e);
   if (lt.stageBytes > 0) {
     const int nw8 = lt.stageBytes >> 3, np8 = (int)((lt.nPasses * sizeof(LeanPass)) >> 3);
     double *dst = (double *)stage;
     const double *srcP = (const double *)lt.pass, *srcR = (const double *)lt.rad;
 #pragma unroll 1
-    for (int e = threadIdx.x; e < nw8; e += blockDim.x) dst[e] = e < np8 ? srcP[e] : srcR[e - np8];
+    for (int e = threadIdx.x; e < nw8; e += blockDim.x) fnet_cp_async8(dst + e, e < np8 ? srcP + e : srcR + (e - np8));
     passes = (const LeanPass *)stage;
     rads = (const LeanRadial *)(stage + (size_t)np8 * 8);
   }
-  unsigned short *ptab = (unsigned short *)(stage + ((lt.stageBytes + 15) & ~15));
   {
     const int ne2 = (lean_pair_entries(cap) + 1) >> 1;                 // 32-bit copies
     const unsigned *src = (const unsigned *)lt.pairtab;
 #pragma unroll 1
-    for (int e = threadIdx.x; e < ne2; e += blockDim.x) ((unsigned *)ptab)[e] = src[e];
+    for (int e = threadIdx.x; e < ne2; e += blockDim.x) fnet_cp_async4((unsigned *)ptab + e, src + e);
   }
+  double zMu = 0.0, zIs = 1.0;                      // z-score row of this thread (F <= blockDim.x in practice): loads in flight too
+  if (zprec && (int)threadIdx.x < F) { zMu = zprec[threadIdx.x]; zIs = zprec[F + threadIdx.x]; }
+  if (!acsf_cta_prologue<PATH, true, true>(geo, nSplit, tab.rcMax, capC, smem_raw, flags, cg, wbase)) { fnet_cp_async_wait(); return; }   // exp table only, asynchronously
+#pragma unroll 1
+  for (int a = threadIdx.x; a < F; a += blockDim.x) {
+    double mu = 0.0, is = 1.0;
+    if (zprec) {
+      const double sg = a < (int)blockDim.x ? zIs : zprec[F + a];
+      if (!(sg < 1e-08)) { mu = a < (int)blockDim.x ? zMu : zprec[a]; is = 1.0 / sg; }   // acsf.F90:505-507
+    }
+    zmu[a] = mu; zis[a] = is;
+  }
+  if (SORTED)
+#pragma unroll 1
+    for (int z = threadIdx.x; z < 128; z += blockDim.x) zcode[z] = (unsigned char)species_code(tab, z);
+  fnet_cp_async_wait();
   __syncthreads();
   wbase += lean_cta_tables_bytes(F, cap, lt.stageBytes);
   const int a0 = cg.a0, a1 = cg.a1;

@@ -1147,12 +1147,19 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
           CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
           for (int c = 0; c < 8; c++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evChunk[c], cudaEventDisableTiming));
         }
-        // chunks of doubling size (1 : 2 : 4 : 8): the first kernel starts after 1/15 of the copy, the copy of chunk
-        // c + 1 (twice the bytes, ~2.5x the kernel's rate per byte) hides behind the kernel of chunk c, and only four
-        // launches pay a partially filled last wave (eight equal chunks cost ~16 % of the kernel time in tails)
-        const int nChunk = s.nStruct >= 4096 ? 4 : (s.nStruct >= 1024 ? 2 : 1);
-        int bound[9];
-        for (int c = 0; c <= nChunk; c++) bound[c] = (int)((long long)s.nStruct * ((1 << c) - 1) / ((1 << nChunk) - 1));
+        // chunks of 1, 2, 4 full WAVES of CTAs and the rest: the first kernel starts after one wave's worth of the copy,
+        // the copy of chunk c + 1 (twice the bytes, ~2.5x the kernel's rate per byte) hides behind the kernel of chunk c,
+        // and only the last launch has a partially filled wave (chunks of nStruct / 15 ... 8 nStruct / 15 structures cost
+        // three extra waves out of 17 on C2 once a CTA takes a whole 64-atom structure)
+        const int ctasPerSM = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (L.smem + 1024)));
+        const long long wave = std::max<long long>(1, (long long)ctx->nSM * ctasPerSM / std::max(1, L.nSplit));
+        int bound[9], nChunk = 0;
+        bound[0] = 0;
+        {
+          long long done = 0, waves = 1;
+          while (nChunk < 3 && (long long)s.nStruct - done >= 2 * wave * waves) { done += wave * waves; bound[++nChunk] = (int)done; waves *= 2; }
+          bound[++nChunk] = s.nStruct;
+        }
         for (int c = 0; c < nChunk; c++) {
           const int st0 = bound[c], st1 = bound[c + 1];
           const size_t a0 = s.h_offsets[st0], a1 = s.h_offsets[st1];
