@@ -1840,7 +1840,7 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                 s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
                                 lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
   }
-  LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 127) / 128), 128, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
+  LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 31) / 32), FNET_GRED_J * 32, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
   if (fused || cfused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
   if (ctx->nRanks > 1 && ctx->comm) {
     // gradient | loss numerator | denominator: ONE all-reduce, on its own stream -- when the caller does not fetch the

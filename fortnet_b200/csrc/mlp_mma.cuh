@@ -108,15 +108,18 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
 // weights of one species: serialised ww(i,o) at i + din*o (network.F90:413-419) -> [o][wS] padded
 __device__ __forceinline__ void mma_load_weights(const NetTables &net, const MmaLayout &m,
                                                  const double *__restrict__ wb, double *__restrict__ wsm) {
-  for (int e = threadIdx.x; e < m.wTotal; e += blockDim.x) wsm[e] = 0.0;
+  // (wTotal is even and wsm 16-byte aligned: 16-byte stores; rows by warps and columns by lanes: no division -- a CTA of
+  // the C2 launch lives for 34 rounds only, and this prologue was 10 % of its instructions)
+  for (int e = threadIdx.x; 2 * e < m.wTotal; e += blockDim.x) ((double2 *)wsm)[e] = make_double2(0.0, 0.0);
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int l = 0; l + 1 < net.L; l++) {
     const int din = net.dims[l], dout = net.dims[l + 1];
     const double *W = wb + net.woff[l];
-    for (int e = threadIdx.x; e < din * dout; e += blockDim.x) {
-      const int i = e % din, o = e / din;
-      wsm[m.wOff[l] + o * m.wS[l] + i] = W[e];
-    }
+    double *dst = wsm + m.wOff[l];
+    const int wS = m.wS[l];
+    for (int o = warp; o < dout; o += nwarp)
+      for (int i = lane; i < din; i += 32) dst[o * wS + i] = W[o * din + i];
   }
   for (int l = 1; l < net.L; l++)
     for (int e = threadIdx.x; e < net.dims[l]; e += blockDim.x) wsm[m.bOff[l] + e] = wb[net.boff[l] + e];
@@ -359,7 +362,8 @@ k_bpnn_mma(int nTiles, const int *__restrict__ tiles, const int *__restrict__ pe
   double *tiles0 = etab + FNET_EXP_TAB_N;
   for (int e = threadIdx.x; e < FNET_EXP_TAB_N; e += blockDim.x) etab[e] = fnet_exp_tab_d[e];
   double *T = tiles0 + (size_t)(warp >> 1) * rows * TS + TA * (warp & 1);   // this warp's 8 columns of its tile
-  for (int e = threadIdx.x; e < FNET_MMA_TILES * rows * TS; e += blockDim.x) tiles0[e] = 0.0;   // padding rows stay zero from here on
+  for (int e = threadIdx.x; 2 * e < FNET_MMA_TILES * rows * TS; e += blockDim.x)               // padding rows stay zero from here on
+    ((double2 *)tiles0)[e] = make_double2(0.0, 0.0);                                           // (TS is even, tiles0 16-byte aligned)
   __syncthreads();
   // cluster-fused sums: CS CTAs walk the super-rounds of their cluster in lock step
   int CS = 1, crank = 0;
