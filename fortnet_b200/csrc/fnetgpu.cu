@@ -1147,6 +1147,8 @@ static int acsf_calculate_t(fnetgpu_ctx *ctx, Slot &s, int standardize, double *
           CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
           for (int c = 0; c < 8; c++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evChunk[c], cudaEventDisableTiming));
         }
+        // (measured alternative: up to 16 equal wave-aligned chunks -- every launch boundary drains the SMs: C2 +0.06 ms,
+        // C3 +0.7 ms end to end on a host whose copy is faster than the kernel; only a copy-bound host would gain)
         // chunks of 1, 2, 4 full WAVES of CTAs and the rest: the first kernel starts after one wave's worth of the copy,
         // the copy of chunk c + 1 (twice the bytes, ~2.5x the kernel's rate per byte) hides behind the kernel of chunk c,
         // and only the last launch has a partially filled wave (chunks of nStruct / 15 ... 8 nStruct / 15 structures cost
@@ -1840,8 +1842,12 @@ static int grad_t(fnetgpu_ctx *ctx, Slot &s, int lossId, double *ddSerial, doubl
                                 s.tileT, B.gInSmem, s.d_structOf, s.d_offsets, s.d_gS, s.d_at, s.d_aw, s.d_dsw, s.nG, s.nA,
                                 lossId, ctx->d_partials, (real *)nullptr, (real *)nullptr)));
   }
-  LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 31) / 32), FNET_GRED_J * 32, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
-  if (fused || cfused) LAUNCH(ctx, K_LOSS_FINAL, (k_loss_final<<<1, 1024, 0, ctx->stream>>>(s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
+  // (fused sums: the loss terms of the structures are reduced by one more CTA of the same launch)
+  if (fused || cfused)
+    LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 31) / 32) + 1, FNET_GRED_J * 32, 0, ctx->stream>>>(
+                                   grid, (int)nDD, ctx->d_partials, ctx->d_dd, s.nStruct, s.d_lossPart, ctx->d_dd + nDD)));
+  else
+    LAUNCH(ctx, K_GRAD_REDUCE, (k_grad_reduce<<<(int)((nDD + 31) / 32), FNET_GRED_J * 32, 0, ctx->stream>>>(grid, (int)nDD, ctx->d_partials, ctx->d_dd)));
   if (ctx->nRanks > 1 && ctx->comm) {
     // gradient | loss numerator | denominator: ONE all-reduce, on its own stream -- when the caller does not fetch the
     // result now, it overlaps whatever comes next on the main stream (the next step's ACSF kernel)

@@ -573,8 +573,25 @@ __global__ void k_loss_final(int nStruct, const double *__restrict__ lossPart, d
 // thread (j, pl) sums the CTAs c = j, j + J, ... (independent, coalesced loads), the J sub-sums are added in order of j.
 // (One thread per output walked all CTAs alone: 296 dependent additions behind 4 loads in flight -- 35 us on C2.)
 #define FNET_GRED_J 16
-__global__ void __launch_bounds__(FNET_GRED_J * 32) k_grad_reduce(int nCta, int nDD, const double *__restrict__ partials, double *__restrict__ dd) {
+// With lossPart != nullptr the LAST CTA of the grid instead reduces the per-structure loss terms of the fused gradient
+// kernels (what k_loss_final does as a launch of its own): lossOut[0] = numerator, lossOut[1] = denominator.
+__global__ void __launch_bounds__(FNET_GRED_J * 32) k_grad_reduce(int nCta, int nDD, const double *__restrict__ partials, double *__restrict__ dd,
+                                                                   int nStruct = 0, const double *__restrict__ lossPart = nullptr,
+                                                                   double *__restrict__ lossOut = nullptr) {
   __shared__ double sh[FNET_GRED_J][32];
+  if (lossPart && blockIdx.x == gridDim.x - 1) {
+    __shared__ double sm[2][FNET_GRED_J * 32];
+    double a = 0.0, b = 0.0;
+    for (int s = threadIdx.x; s < nStruct; s += blockDim.x) { a += lossPart[2 * s]; b += lossPart[2 * s + 1]; }
+    sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if (threadIdx.x < o) { sm[0][threadIdx.x] += sm[0][threadIdx.x + o]; sm[1][threadIdx.x] += sm[1][threadIdx.x + o]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { lossOut[0] = sm[0][0]; lossOut[1] = sm[1][0]; }
+    return;
+  }
   const int pl = threadIdx.x & 31, j = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
   double s = 0.0;
