@@ -8,9 +8,9 @@ want = [("k_acsf_lean<2,1,STRUCT,unsorted,G=4,f64>  (C2 values)", "_Z11k_acsf_le
         ("k_acsf_lean<2,1,STRUCT,sorted,G=2,f64>  (C3 values)", "_Z11k_acsf_leanILi2ELi1ELi2ELb1ELi2ELb0E"),
         ("k_acsf_lean<1,4,DIRECT,unsorted,G=1,f64>  (C5 values)", "_Z11k_acsf_leanILi1ELi4ELi0ELb0ELi1ELb0E"),
         ("k_acsf_force_lean<2,1,STRUCT,sorted,G=2,local>  (C4 forces)", "_Z17k_acsf_force_leanILi2ELi1ELi2ELb1ELi2ELb1E"),
-        ("k_bpnn_mma<0,4,1,fused>  (C2 training gradient)", "_Z10k_bpnn_mmaILi0ELi4ELi1ELb1E"),
-        ("k_bpnn_mma<0,9,2,unfused>  (C3 training gradient)", "_Z10k_bpnn_mmaILi0ELi9ELi2ELb0E"),
-        ("k_bpnn_mma<1,1,2>  (C4 input gradients)", "_Z10k_bpnn_mmaILi1ELi1ELi2ELb0E")]
+        ("k_bpnn_mma<0,4,1,fused>  (C2 training gradient)", "_Z10k_bpnn_mmaILi0ELi4ELi1ELi1E"),
+        ("k_bpnn_mma<0,9,2,cluster-fused>  (C3 training gradient)", "_Z10k_bpnn_mmaILi0ELi9ELi2ELi2E"),
+        ("k_bpnn_mma<1,1,2>  (C4 input gradients)", "_Z10k_bpnn_mmaILi1ELi1ELi2ELi0E")]
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
 print("static SASS opcode histogram, sm_100a, %s" % os.path.basename(lib))
