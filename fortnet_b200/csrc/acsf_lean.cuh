@@ -268,6 +268,12 @@ __device__ __forceinline__ void lean_rect_decode(int p, int n2, int &j, int &k) 
 #ifndef FNET_LEAN_UNROLL_SORTED
 #define FNET_LEAN_UNROLL_SORTED 1
 #endif
+// neighbours per lane in flight in the record and radial loops of single-list configurations.  Measured: 2 (two
+// independent rsqrt / cutoff / exp chains per lane) LOSES -- C2 ACSF 0.722 -> 0.860 ms in a same-box A/B: at the
+// 128-register cap the second chain is paid with rematerialisation, and the executed code grows past the caches.
+#ifndef FNET_LEAN_NB_UNROLL
+#define FNET_LEAN_NB_UNROLL 1
+#endif
 #ifndef FNET_LEAN_PAIR_PRAGMA
 #define FNET_LEAN_PAIR_PRAGMA
 #endif
@@ -419,6 +425,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
   constexpr int LPA = 32 / G;                       // lanes per central atom
   constexpr int RA = M >= LPA ? M / LPA : 1;        // finished angular values per lane after a reduction
   constexpr int RR = FNET_RCHUNK >= LPA ? FNET_RCHUNK / LPA : 1;
+  constexpr int NBU = SORTED ? 1 : FNET_LEAN_NB_UNROLL;   // neighbours per lane in flight (record / radial loops)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -568,6 +575,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
     // single list (!SORTED): the diagonal sums of the passes with the shared (rc, eta) -- S0 = sum (fc E)^2,
     // S1 = sum (fc E)^2 eps -- are formed here, once per atom, instead of in a loop of their own per pass
     double dS0 = 0.0, dS1 = 0.0;
+#pragma unroll NBU
     for (int t = sl; t <= n; t += LPA) {
       double ux = 0.0, uy = 0.0, uz = 0.0, fe = 0.0, rr = 2.0 * tab.rcMax, fc = 0.0;
       if (t < n) {
@@ -614,6 +622,7 @@ k_acsf_lean(int nSplit, GeomArgs geo, int nExt, const double *__restrict__ ext, 
         double acc[FNET_RCHUNK], acc2[FNET_RCHUNK];
 #pragma unroll
         for (int f = 0; f < FNET_RCHUNK; f++) { acc[f] = 0.0; acc2[f] = 0.0; }
+#pragma unroll NBU
         for (int t = sl; t < nl; t += LPA) {
           const int a = SORTED ? list_at(l, t) : t;
           const double2 rf = *(const double2 *)(rec + 6 * a + 4);
