@@ -28,6 +28,14 @@
 #include <cooperative_groups.h>
 #include "mlp.cuh"
 
+// build-time knobs of the K loops (A/B, tools/gpu_ab2.sh, same box: unroll 4 instead of 2: C2 0.400 -> 0.398 ms, C3 7.13 -> 7.17;
+// plain asm instead of asm volatile: 0.402 / 7.19 ms -- neither moves the kernel, the defaults stay)
+#ifndef FNET_MMA_ASM
+#define FNET_MMA_ASM asm volatile
+#endif
+#ifndef FNET_MMA_KUNROLL
+#define FNET_MMA_KUNROLL 2
+#endif
 #define FNET_MMA_TA 8              // atoms per warp (one m8 tile)
 #define FNET_MMA_TW 16             // atoms per shared-memory tile: two warps share a tile (columns 0-7 / 8-15)
 #define FNET_MMA_TS 20             // row stride of the [row][atom] tiles, doubles
@@ -101,7 +109,7 @@ __host__ inline bool bpnn_mma_fits(const NetTables &net) {
 // D += A(8x4, row) * B(4x8, col).  Lane (g = lane / 4, c = lane % 4) holds A[g][c], B[c][g] and
 // D[g][2c], D[g][2c + 1].
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  FNET_MMA_ASM("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
@@ -177,7 +185,8 @@ __device__ __forceinline__ void mma_activate(int actId, int dout, double *__rest
 template <int NC>
 __device__ __forceinline__ void mma_k_loop(int KT, const double *__restrict__ ip, const double *__restrict__ wp,
                                            size_t aStep, size_t bStep, size_t bTile, double (&acc)[4][2]) {
-#pragma unroll 2
+  constexpr int KU = FNET_MMA_KUNROLL;
+#pragma unroll KU
   for (int kt = 0; kt < KT; kt++) {
     const double a0 = ip[kt * aStep];
 #pragma unroll
