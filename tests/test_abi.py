@@ -62,3 +62,18 @@ def test_fortran_shim_is_consistent_with_the_header():
     assert len(re.findall(r"^\s*subroutine\s", low, flags=re.M)) == len(re.findall(r"^\s*end subroutine", low, flags=re.M))
     assert len(re.findall(r"^\s*(?:integer\(c_int\)|type\(c_ptr\))\s+function\s", low, flags=re.M)) == \
         len(re.findall(r"^\s*end function", low, flags=re.M))
+
+
+def test_build_is_deterministic_by_construction():
+    """nvcc -split-compile gave different kernels from run to run (profiles/r02_build_determinism.txt): the build must not
+    use it, and the two dominant kernels keep translation units of their own."""
+    mk = open(os.path.join(ROOT, "fortnet_b200", "csrc", "Makefile")).read()
+    flags = [l for l in mk.splitlines() if l.startswith("NVFLAGS")]
+    assert flags and all("-split-compile" not in l for l in flags)
+    for unit in ("fnetgpu.cu", "kernels_lean.cu", "kernels_mma.cu"):
+        assert os.path.exists(os.path.join(ROOT, "fortnet_b200", "csrc", unit))
+    lean = open(os.path.join(ROOT, "fortnet_b200", "csrc", "kernels_lean.cu")).read()
+    mma = open(os.path.join(ROOT, "fortnet_b200", "csrc", "kernels_mma.cu")).read()
+    assert "FNET_DEFINE_LEAN_KERNEL" in lean and "FNET_DEFINE_MMA_KERNEL" in mma
+    main = open(os.path.join(ROOT, "fortnet_b200", "csrc", "fnetgpu.cu")).read()
+    assert "FNET_DEFINE_LEAN_KERNEL" not in main and "FNET_DEFINE_MMA_KERNEL" not in main
