@@ -192,7 +192,9 @@ extern "C" int fnetgpu_profile_get(fnetgpu_ctx *ctx, int kid, double *ms, long l
 static int ensure_pinned(fnetgpu_ctx *ctx, size_t n) {
   if (ctx->pinnedN >= n) return 0;
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->h_pinIn) cudaFreeHost(ctx->h_pinIn);
+  // (h_pinIn, the socket step's staged geometry, has its own capacity and is NOT released here: it used to be freed without
+  // being reset, so that growing this buffer after a socket step left a dangling pointer for the next step and a second
+  // cudaFreeHost in fnetgpu_finalize -- found by compute-sanitizer on test_reconfigure_with_larger_features_and_outputs)
   ctx->h_pinned = nullptr; ctx->pinnedN = 0;
   CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinned, n * sizeof(double)));
   ctx->pinnedN = n;

@@ -707,6 +707,33 @@ def test_socket_step(fb, orc, path, precision):
     ctx2.close()
 
 
+def test_socket_step_survives_growth_of_the_result_buffer(fb):
+    """the pinned result buffer (gradient fetch, socket outputs) and the socket step's staged geometry are separate
+    allocations: growing the first after a socket step must not release the second (it once did, without resetting
+    the pointer: the next MD step read freed host memory and fnetgpu_finalize freed it twice -- found by
+    compute-sanitizer)"""
+    from fortnet_b200 import synthetic
+    rng = np.random.default_rng(5)
+    ds = synthetic.si_bulk(n_struct=1, seed=3)
+    funcs = fb.GFunctions.from_auto_scheme(4.0 * fb.BOHR_PER_AA, 6, 6)
+    dims = [12, 24, 24, 1]                              # 937 parameters > 64 + 192 + 16 doubles of socket results
+    wb = rng.uniform(-0.5, 0.5, size=(1, _ntot(dims)))
+    ctx = fb.Context()
+    ctx.upload(0, ds)
+    acsf = fb.Acsf(ctx, funcs, standardize=True)
+    acsf.calculate(0)
+    net = fb.Bpnn(ctx, dims, 1, "tanh")
+    net.set_params(wb)
+    c = ds.coords + rng.normal(scale=0.02, size=ds.coords.shape)
+    first = [np.array(a) for a in ctx.socket_step(0, c)]
+    first2 = [np.array(a) for a in ctx.socket_step(0, c)]       # (graph captured on the second step)
+    net.update_gradients(0, "mse", fetch=True)                  # grows the pinned result buffer
+    again = [np.array(a) for a in ctx.socket_step(0, c)]
+    for a, b, d in zip(first, first2, again):
+        assert np.array_equal(a, b) and np.array_equal(a, d)
+    ctx.close()
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_atom_id_scaling_and_external_features(fb, orc, path):
     """q_i q_j prefactors from an external-feature row (acsf.F90:836-840,1003-1052) and external
