@@ -278,9 +278,10 @@ __device__ __forceinline__ void lean_rect_decode(int p, int n2, int &j, int &k) 
 #define FNET_LEAN_PAIR_PRAGMA
 #endif
 // One angular pass over the pairs of (l1, l2); indices beyond the last pair map to (0, n1) resp. (n1, 0): the dummy
-// neighbour.  Two pairs per lane and iteration for the 16-accumulator shapes: two independent pairs hide the latency of
-// the dependent table-lookup / DFMA chains at 16 resident warps per SM (measured on C2 / C3: 0.91 -> 0.83 ms,
-// 18.4 -> 16.7 ms with 128 registers and 4 CTAs per SM; 5 CTAs at 96 registers spill and lose)
+// neighbour.  Two pairs per lane and iteration for the 16-accumulator shapes of SINGLE-LIST configurations: two
+// independent pairs hide the latency of the dependent table-lookup / DFMA chains at 16 resident warps per SM (C2,
+// deterministic builds: 0.749 -> 0.725 ms; 5 CTAs at 96 registers spill and lose).  Species-resolved configurations
+// walk one pair per lane (FNET_LEAN_UNROLL_SORTED above): their code has to fit the instruction caches first.
 template <int NL, int NC, int LPA, bool SORTED, int KIND, typename AT>
 __device__ __forceinline__ void lean_pair_loop(AT (&acc)[NL * NC * FNET_LADDER], const double *__restrict__ rec,
                                                const float4 *__restrict__ recf,
